@@ -1,0 +1,205 @@
+/*
+ * b200ols.h — C ABI of the B200-native batched least-squares engine (libb200ols.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of azmyrajab/polars_ols: the six plugin
+ * expressions  least_squares{,_coefficients}, recursive_least_squares{,_coefficients},
+ * rolling_least_squares{,_coefficients}  (reference: src/expressions.rs:390-446, :593-701, exported by
+ * `#[polars_expr]` as `_polars_plugin_<fn>(SeriesExport* inputs, size_t n, const u8* kwargs, size_t len,
+ * SeriesExport* ret)`), *batched over the groups of a `.over()` / `group_by` context* so that one call
+ * carries every group instead of one FFI call per group (SURVEY.md §7 hard part 3).
+ *
+ * Plain C: pointers, sizes, POD structs.  No C++/torch types.  Thread-safe per context; errors are
+ * returned as negative codes, the message is thread-local (`b200ols_last_error`), nothing unwinds
+ * across the boundary (the reference's `catch_unwind` + `_polars_plugin_get_last_error_message`).
+ *
+ * Data model = the Arrow C Data Interface view the reference receives inside `SeriesExport`:
+ * one contiguous values buffer per column (the reference rechunks, src/expressions.rs:40,55,88) plus
+ * an optional validity bitmap (bit i of byte i/8, LSB first, 1 = valid).  NaN is a value, not a null.
+ * Columns may live in host memory (the engine stages them through pinned buffers) or already in
+ * device memory (zero-copy; torch / cudf / cupy pointers).
+ */
+#ifndef B200OLS_H
+#define B200OLS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200OLS_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define B200OLS_API __attribute__((visibility("default")))
+#else
+#define B200OLS_API
+#endif
+
+/* ---- enums (values are part of the ABI) --------------------------------------------------------- */
+
+/* element type of the values buffers; the reference casts every input to f64 before any arithmetic
+ * (src/expressions.rs:33,47,80) and always returns Float64 — so do we (outputs are f64). */
+enum { B200OLS_F64 = 0, B200OLS_F32 = 1 };
+
+enum { B200OLS_HOST = 0, B200OLS_DEVICE = 1 };
+
+/* OutputMode, polars_ols/least_squares.py:57 ("statistics" is out of scope) */
+enum { B200OLS_PREDICTIONS = 0, B200OLS_RESIDUALS = 1, B200OLS_COEFFICIENTS = 2 };
+
+/* NullPolicy, src/least_squares.rs:68-91 */
+enum {
+    B200OLS_NULL_IGNORE = 0,
+    B200OLS_NULL_ZERO = 1,
+    B200OLS_NULL_DROP = 2,
+    B200OLS_NULL_DROP_ZERO = 3,
+    B200OLS_NULL_DROP_Y_ZERO_X = 4,
+    B200OLS_NULL_DROP_WINDOW = 5
+};
+
+/* SolveMethod, src/least_squares.rs:42-65 (NONE = Option::None) */
+enum {
+    B200OLS_SOLVE_NONE = 0,
+    B200OLS_SOLVE_QR = 1,
+    B200OLS_SOLVE_SVD = 2,
+    B200OLS_SOLVE_CHOL = 3,
+    B200OLS_SOLVE_LU = 4,
+    B200OLS_SOLVE_CD = 5,
+    B200OLS_SOLVE_CD_ACTIVE_SET = 6
+};
+
+/* return codes */
+enum {
+    B200OLS_OK = 0,
+    B200OLS_ERR_INVALID = -1,     /* bad argument (the reference's assert!/expect panics) */
+    B200OLS_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented on the device yet */
+    B200OLS_ERR_CUDA = -3,        /* CUDA runtime failure (message has the cudaError string) */
+    B200OLS_ERR_NO_DEVICE = -4    /* no CUDA device: there is NO CPU fallback */
+};
+
+/* ---- data descriptors --------------------------------------------------------------------------- */
+
+typedef struct b200ols_column {
+    const void *values;      /* n_rows elements of `dtype`; 16-byte aligned when in device memory */
+    const uint8_t *validity; /* Arrow validity bitmap (offset 0) or NULL = no nulls */
+} b200ols_column;
+
+/* One `.over()` / `group_by` evaluation: every input Series of the plugin call, for all groups.
+ * inputs[0] of the reference = target, inputs[1..] = features (src/expressions.rs:391,431).
+ * Groups are polars' GroupsProxy in CSR form:
+ *   group_offsets[g] .. group_offsets[g+1]   = the rows of group g in PACKED order,
+ *   row_index[p]                             = original row of packed position p (GroupsIdx), or
+ *   row_index == NULL                        = groups are contiguous row slices (GroupsSlice).
+ * Row order inside a group is the frame's order (it matters for rls / rolling). */
+typedef struct b200ols_frame {
+    int64_t n_rows;
+    int32_t n_features; /* data feature columns (the intercept is NOT included here) */
+    int32_t dtype;      /* B200OLS_F64 | B200OLS_F32, shared by target, features and weights */
+    int32_t memspace;   /* B200OLS_HOST | B200OLS_DEVICE, shared by every pointer in this struct */
+    int32_t add_intercept; /* append `const` = 1.0 AFTER all features (polars_ols/least_squares.py:184-188) */
+    b200ols_column target;
+    const b200ols_column *features;       /* [n_features] (host array of descriptors) */
+    const b200ols_column *sample_weights; /* NULL = unweighted; else WLS: sqrt(w) scaling of target and
+                                             features, null w -> sqrt(w)=1e-12, predictions un-scaled by
+                                             1/sqrt(w) (polars_ols/least_squares.py:190-196,234-235) */
+    int64_t n_groups;             /* >= 1 */
+    const int64_t *group_offsets; /* [n_groups+1], ALWAYS a host pointer (plan metadata, like this struct);
+                                     NULL => one group spanning all rows */
+    const int64_t *row_index;     /* [n_rows] or NULL */
+} b200ols_frame;
+
+/* serde kwargs structs of src/expressions.rs:298-330 as POD; NaN / negative encode Option::None */
+typedef struct b200ols_ols_kwargs {
+    double alpha;         /* NaN = None (-> 0.0) */
+    double l1_ratio;      /* NaN = None */
+    int64_t max_iter;     /* < 0 = None (-> 1000) */
+    double tol;           /* NaN = None (-> 1e-5) */
+    int32_t positive;     /* 0/1 */
+    int32_t solve_method; /* B200OLS_SOLVE_* */
+    int32_t null_policy;  /* B200OLS_NULL_* (None -> IGNORE, src/expressions.rs:340-343) */
+    int32_t _reserved;
+    double rcond;         /* NaN = None */
+} b200ols_ols_kwargs;
+
+typedef struct b200ols_rls_kwargs {
+    double half_life;                 /* NaN = None (lambda = 1) */
+    double initial_state_covariance;  /* NaN = None (-> 10.0) */
+    const double *initial_state_mean; /* host [n_coef] or NULL; honoured in coefficients mode only
+                                         (src/expressions.rs:604-610 vs :636) */
+    int32_t null_policy;
+    int32_t _reserved;
+} b200ols_rls_kwargs;
+
+typedef struct b200ols_rolling_kwargs {
+    int64_t window_size;
+    int64_t min_periods;  /* < 0 = None (-> min(k, window)) */
+    int32_t use_woodbury; /* < 0 = None; accepted for parity, the device solves S beta = v directly */
+    int32_t null_policy;
+    double alpha;         /* NaN = None (-> 0) */
+} b200ols_rolling_kwargs;
+
+/* Outputs are always f64 (reference: output_type=Float64 / struct of Float64).
+ *   predictions / residuals : values[n_rows]            (original row order)
+ *   static coefficients     : values[n_groups * n_coef] row-major, n_coef = n_features + add_intercept,
+ *                             field order = feature order then `const` (one struct row per group,
+ *                             `returns_scalar`; polars broadcasts it under .over())
+ *   rls / rolling coefs     : values[n_rows * n_coef]   row-major (original row order)
+ * validity (optional, may be NULL): one BYTE per output element, 1 = valid, 0 = polars null.
+ * For coefficient outputs null <=> NaN (src/expressions.rs:137-139 fill_nan(NULL)).
+ * memspace must equal the frame's memspace. */
+typedef struct b200ols_output {
+    double *values;
+    uint8_t *validity;
+} b200ols_output;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+
+typedef struct b200ols_ctx b200ols_ctx; /* owns: device id, stream, pinned + device scratch */
+
+B200OLS_API int b200ols_create(int device, b200ols_ctx **out);
+/* use an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */
+B200OLS_API int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_ctx **out);
+B200OLS_API void b200ols_destroy(b200ols_ctx *ctx);
+B200OLS_API int b200ols_synchronize(b200ols_ctx *ctx);
+B200OLS_API const char *b200ols_last_error(void);
+B200OLS_API int b200ols_version(void);
+/* number of kernels of THIS library launched through ctx since creation (bench.py's gpu_launches) */
+B200OLS_API int64_t b200ols_launch_count(const b200ols_ctx *ctx);
+/* page-locked host memory for frames that are uploaded every call (full-speed, async H2D/D2H) */
+B200OLS_API void *b200ols_host_alloc(size_t bytes);
+B200OLS_API void b200ols_host_free(void *p);
+/* tuning knobs (0 = default): rows per shared-memory tile and consumer warps per CTA of the
+ * row-streaming Gram kernel */
+B200OLS_API int b200ols_set_tuning(b200ols_ctx *ctx, int tile_rows, int warps_per_cta, int ctas_per_sm);
+
+/* ---- the six entry points (one per reference plugin symbol), batched over groups ------------------ */
+
+/* replaces _polars_plugin_least_squares (src/expressions.rs:391-428): mode PREDICTIONS | RESIDUALS */
+B200OLS_API int b200ols_least_squares(b200ols_ctx *ctx, const b200ols_frame *frame, const b200ols_ols_kwargs *kwargs,
+                          int mode, b200ols_output *out);
+/* replaces _polars_plugin_least_squares_coefficients (src/expressions.rs:431-446) */
+B200OLS_API int b200ols_least_squares_coefficients(b200ols_ctx *ctx, const b200ols_frame *frame,
+                                       const b200ols_ols_kwargs *kwargs, b200ols_output *out);
+/* replaces _polars_plugin_recursive_least_squares (src/expressions.rs:625-646) */
+B200OLS_API int b200ols_recursive_least_squares(b200ols_ctx *ctx, const b200ols_frame *frame,
+                                    const b200ols_rls_kwargs *kwargs, int mode, b200ols_output *out);
+/* replaces _polars_plugin_recursive_least_squares_coefficients (src/expressions.rs:594-622) */
+B200OLS_API int b200ols_recursive_least_squares_coefficients(b200ols_ctx *ctx, const b200ols_frame *frame,
+                                                 const b200ols_rls_kwargs *kwargs, b200ols_output *out);
+/* replaces _polars_plugin_rolling_least_squares (src/expressions.rs:679-701) */
+B200OLS_API int b200ols_rolling_least_squares(b200ols_ctx *ctx, const b200ols_frame *frame,
+                                  const b200ols_rolling_kwargs *kwargs, int mode, b200ols_output *out);
+/* replaces _polars_plugin_rolling_least_squares_coefficients (src/expressions.rs:649-676) */
+B200OLS_API int b200ols_rolling_least_squares_coefficients(b200ols_ctx *ctx, const b200ols_frame *frame,
+                                               const b200ols_rolling_kwargs *kwargs, b200ols_output *out);
+
+/* Per-group diagnostics of the last static call on ctx (host copy): bit 0 = Cholesky failed and the
+ * LU fallback ran (src/least_squares.rs:299-316), bit 1 = group had no rows after null filtering
+ * (coefficients = 0, src/expressions.rs:357-359), bit 2 = re-solved by the pivoted-QR kernel
+ * (ill-conditioned Gram).  flags must hold n_groups ints. */
+B200OLS_API int b200ols_last_group_flags(b200ols_ctx *ctx, int32_t *flags, int64_t n_groups);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OLS_H */

@@ -1,0 +1,942 @@
+// engine.cu — host side of libb200ols.so: the C ABI of include/b200ols.h over the sm_100a kernels.
+//
+// What the reference does per group and per call (polars `.over()` -> one `_polars_plugin_*` FFI call
+// per group -> Series -> row-major ndarray -> solver -> Series; src/expressions.rs:390-446) is done
+// here once per frame: stage columns (H2D / gather / null policy), ONE streaming Gram+solve launch for
+// all groups, optionally one prediction pass, copy results back.  No CPU fallback exists: without a
+// CUDA device every entry point fails with B200OLS_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200ols.h"
+#include "gram_stream.cuh"
+#include "moving.cuh"
+#include "predict.cuh"
+#include "prep.cuh"
+#include "qr_fallback.cuh"
+#include "small_solve.cuh"
+
+using namespace b200;
+
+static __global__ void nan_mask_kernel(const double *v, uint8_t *m, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) m[i] = (v[i] == v[i]) ? 1 : 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(B200OLS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                        \
+    } while (0)
+
+#define TRY(expr)              \
+    do {                       \
+        int rc__ = (expr);     \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct b200ols_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    int smem_optin = 0;
+    int64_t launches = 0;
+    int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
+    // bump arena in device memory, reset at the start of every call
+    char *arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    bool arena_overflow = false;
+    std::vector<void *> retired;  // old arenas, freed after the next synchronise
+    // pinned host staging for small metadata (offsets, segment tables)
+    char *pinned = nullptr;
+    size_t pinned_cap = 0, pinned_off = 0;
+    // diagnostics of the last static call
+    int32_t *last_flags = nullptr;  // device pointer inside the arena
+    int64_t last_flags_n = 0;
+};
+
+static int arena_reserve(b200ols_ctx *c, size_t bytes) {
+    if (bytes <= c->arena_cap) return 0;
+    size_t cap = std::max(bytes + (bytes >> 2), static_cast<size_t>(64) << 20);
+    void *p = nullptr;
+    CU(cudaMalloc(&p, cap));
+    if (c->arena) c->retired.push_back(c->arena);
+    c->arena = static_cast<char *>(p);
+    c->arena_cap = cap;
+    return 0;
+}
+
+template <typename U>
+static U *arena_alloc(b200ols_ctx *c, size_t count) {
+    const size_t bytes = (count * sizeof(U) + 255) & ~static_cast<size_t>(255);
+    U *p = reinterpret_cast<U *>(c->arena + c->arena_off);
+    c->arena_off += bytes;
+    if (c->arena_off > c->arena_cap) c->arena_overflow = true;  // checked by ARENA_GUARD before any launch
+    return p;
+}
+
+#define ARENA_GUARD(c)                                                                                  \
+    do {                                                                                                \
+        if ((c)->arena_overflow) {                                                                      \
+            (c)->arena_overflow = false;                                                                \
+            return fail(B200OLS_ERR_CUDA, "internal: device arena under-sized (%zu > %zu)", (c)->arena_off, \
+                        (c)->arena_cap);                                                                \
+        }                                                                                               \
+    } while (0)
+
+static int pinned_reserve(b200ols_ctx *c, size_t bytes) {
+    if (bytes <= c->pinned_cap) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr;
+    c->pinned_cap = 0;
+    size_t cap = std::max(bytes + (bytes >> 1), static_cast<size_t>(4) << 20);
+    CU(cudaMallocHost(reinterpret_cast<void **>(&c->pinned), cap));
+    c->pinned_cap = cap;
+    return 0;
+}
+
+static int free_retired(b200ols_ctx *c) {
+    if (c->retired.empty()) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    for (void *p : c->retired) cudaFree(p);
+    c->retired.clear();
+    return 0;
+}
+
+extern "C" int b200ols_version(void) { return B200OLS_VERSION; }
+extern "C" const char *b200ols_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_ctx **out) {
+    if (!out) return fail(B200OLS_ERR_INVALID, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(B200OLS_ERR_NO_DEVICE,
+                    "no CUDA device available (%s): libb200ols has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(B200OLS_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    CU(cudaSetDevice(device));
+    b200ols_ctx *c = new b200ols_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9)
+        return fail(B200OLS_ERR_NO_DEVICE, "device sm_%d%d: this library is built for sm_100a only", prop.major,
+                    prop.minor);
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    if (cuda_stream) {
+        c->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int b200ols_create(int device, b200ols_ctx **out) { return b200ols_create_on_stream(device, nullptr, out); }
+
+extern "C" void b200ols_destroy(b200ols_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void *p : c->retired) cudaFree(p);
+    if (c->arena) cudaFree(c->arena);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int b200ols_synchronize(b200ols_ctx *c) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" void *b200ols_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(B200OLS_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void b200ols_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int64_t b200ols_launch_count(const b200ols_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int b200ols_set_tuning(b200ols_ctx *c, int tile_rows, int warps_per_cta, int ctas_per_sm) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (tile_rows < 0 || (tile_rows % 8) != 0) return fail(B200OLS_ERR_INVALID, "tile_rows must be a multiple of 8");
+    if (warps_per_cta < 0 || warps_per_cta > GRAM_MAX_WARPS) return fail(B200OLS_ERR_INVALID, "warps_per_cta out of range");
+    c->tile_rows = tile_rows;
+    c->warps_per_cta = warps_per_cta;
+    c->ctas_per_sm = ctas_per_sm;
+    return 0;
+}
+
+extern "C" int b200ols_last_group_flags(b200ols_ctx *c, int32_t *flags, int64_t n_groups) {
+    if (!c || !flags) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    if (!c->last_flags || n_groups != c->last_flags_n) return fail(B200OLS_ERR_INVALID, "no flags for %lld groups", (long long)n_groups);
+    CU(cudaMemcpyAsync(flags, c->last_flags, sizeof(int32_t) * n_groups, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// staging: frame -> device-resident, packed, null-cleaned SoA columns
+// ------------------------------------------------------------------------------------------------
+struct Staged {
+    int kd = 0, has_w = 0, w_is_sqrt = 0, F = 0, intercept = 0;
+    size_t esz = 8;
+    int64_t n = 0, n_pad = 0;
+    const void *feat[GRAM_MAX_COLS] = {};  // fit + prediction features (null-cleaned)
+    const void *y = nullptr;               // fit target (cleaned)
+    const void *w = nullptr;
+    const void *mask = nullptr;            // T-typed row mask or nullptr
+    const void *y_raw = nullptr;           // target for residuals
+    int y_raw_packed = 0;                  // y_raw indexed by packed position
+    const uint8_t *y_validity = nullptr;   // device bitmap (original rows) or nullptr
+    const int64_t *row_index = nullptr;    // device
+    int64_t n_groups = 1;
+    std::vector<int64_t> offsets;          // host copy [G+1]
+    int64_t max_group_rows = 0;
+    bool prepped = false;
+};
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int validate_frame(const b200ols_frame *f) {
+    if (!f) return fail(B200OLS_ERR_INVALID, "frame is NULL");
+    if (f->n_rows < 0) return fail(B200OLS_ERR_INVALID, "n_rows < 0");
+    if (f->n_features < 0) return fail(B200OLS_ERR_INVALID, "n_features < 0");
+    // src/expressions.rs:72 `assert!(m > 1, "must pass at least 2 series")`
+    if (f->n_features + (f->add_intercept ? 1 : 0) < 1) return fail(B200OLS_ERR_INVALID, "must pass at least 2 series");
+    if (f->n_features + (f->add_intercept ? 1 : 0) > 64)
+        return fail(B200OLS_ERR_UNSUPPORTED, "more than 64 coefficients (%d) is not implemented on the device yet",
+                    f->n_features + (f->add_intercept ? 1 : 0));
+    if (f->dtype != B200OLS_F64 && f->dtype != B200OLS_F32) return fail(B200OLS_ERR_INVALID, "bad dtype %d", f->dtype);
+    if (f->memspace != B200OLS_HOST && f->memspace != B200OLS_DEVICE) return fail(B200OLS_ERR_INVALID, "bad memspace");
+    if (f->n_rows > 0 && !f->target.values) return fail(B200OLS_ERR_INVALID, "target.values is NULL");
+    if (f->n_features > 0 && !f->features) return fail(B200OLS_ERR_INVALID, "features is NULL");
+    for (int j = 0; j < f->n_features; ++j)
+        if (f->n_rows > 0 && !f->features[j].values) return fail(B200OLS_ERR_INVALID, "features[%d].values is NULL", j);
+    if (f->n_groups < 1) return fail(B200OLS_ERR_INVALID, "n_groups must be >= 1");
+    if (f->group_offsets) {
+        if (f->group_offsets[0] != 0 || f->group_offsets[f->n_groups] != f->n_rows)
+            return fail(B200OLS_ERR_INVALID, "group_offsets must start at 0 and end at n_rows");
+    } else if (f->n_groups != 1) {
+        return fail(B200OLS_ERR_INVALID, "group_offsets is NULL but n_groups != 1");
+    }
+    return 0;
+}
+
+// mask_kind / fill derived from the null policy; `moving` = rls / rolling (always zero fill,
+// src/expressions.rs:603,629,656,683)
+static void policy_to_prep(int policy, bool moving, int *fill, int *mask_kind) {
+    *fill = PREP_ZERO;
+    *mask_kind = MASK_NONE;
+    switch (policy) {
+        case B200OLS_NULL_IGNORE: *fill = moving ? PREP_ZERO : PREP_NAN; break;
+        case B200OLS_NULL_ZERO: break;
+        case B200OLS_NULL_DROP:
+        case B200OLS_NULL_DROP_ZERO:
+        case B200OLS_NULL_DROP_WINDOW: *mask_kind = MASK_ALL; break;
+        case B200OLS_NULL_DROP_Y_ZERO_X: *mask_kind = MASK_TARGET; break;
+    }
+}
+
+template <typename T>
+static void launch_prep(b200ols_ctx *c, const PrepParams &pp) {
+    const int64_t blocks = std::min<int64_t>((pp.n_rows_pad + 255) / 256, static_cast<int64_t>(c->sm_count) * 16);
+    prep_kernel<T><<<static_cast<unsigned>(std::max<int64_t>(blocks, 1)), 256, 0, c->stream>>>(pp);
+    c->launches++;
+}
+
+// Brings every column of the frame onto the device (arena), applies gather + null policy when needed.
+// Arena must already be reserved.  `moving`: rls / rolling semantics for the null policy.
+static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool moving, Staged *st) {
+    const int kd = f->n_features;
+    const size_t esz = f->dtype == B200OLS_F64 ? 8 : 4;
+    const int64_t n = f->n_rows;
+    const int64_t A = 16 / static_cast<int64_t>(esz);
+    const int64_t n_pad = static_cast<int64_t>(round_up(static_cast<size_t>(n), static_cast<size_t>(A)));
+    st->kd = kd;
+    st->esz = esz;
+    st->n = n;
+    st->n_pad = n_pad;
+    st->intercept = f->add_intercept ? 1 : 0;
+    st->F = kd + st->intercept;
+    st->has_w = f->sample_weights ? 1 : 0;
+    st->n_groups = f->n_groups;
+    st->offsets.resize(static_cast<size_t>(f->n_groups) + 1);
+    if (f->group_offsets) {
+        std::memcpy(st->offsets.data(), f->group_offsets, sizeof(int64_t) * (f->n_groups + 1));
+        for (int64_t g = 0; g < f->n_groups; ++g) {
+            const int64_t len = st->offsets[g + 1] - st->offsets[g];
+            if (len < 0) return fail(B200OLS_ERR_INVALID, "group_offsets must be non-decreasing");
+            st->max_group_rows = std::max(st->max_group_rows, len);
+        }
+    } else {
+        st->offsets[0] = 0;
+        st->offsets[1] = n;
+        st->max_group_rows = n;
+    }
+
+    const int ncol = kd + 1 + st->has_w;  // features, target, weights
+    const b200ols_column *cols[GRAM_MAX_COLS];
+    for (int j = 0; j < kd; ++j) cols[j] = &f->features[j];
+    cols[kd] = &f->target;
+    if (st->has_w) cols[kd + 1] = f->sample_weights;
+    bool any_validity = false;
+    for (int cidx = 0; cidx < ncol; ++cidx) any_validity = any_validity || (cols[cidx]->validity != nullptr);
+    const size_t bm_bytes = static_cast<size_t>((n + 7) / 8);
+
+    // 1) raw columns on the device
+    const void *dev_vals[GRAM_MAX_COLS];
+    const uint8_t *dev_bm[GRAM_MAX_COLS];
+    const int64_t *dev_rowidx = nullptr;
+    for (int cidx = 0; cidx < ncol; ++cidx) {
+        dev_bm[cidx] = nullptr;
+        if (f->memspace == B200OLS_DEVICE) {
+            dev_vals[cidx] = cols[cidx]->values;
+            dev_bm[cidx] = cols[cidx]->validity;
+        } else {
+            char *d = arena_alloc<char>(c, static_cast<size_t>(n_pad) * esz);
+            if (n > 0) CU(cudaMemcpyAsync(d, cols[cidx]->values, static_cast<size_t>(n) * esz, cudaMemcpyHostToDevice, c->stream));
+            if (n_pad > n) CU(cudaMemsetAsync(d + static_cast<size_t>(n) * esz, 0, static_cast<size_t>(n_pad - n) * esz, c->stream));
+            dev_vals[cidx] = d;
+            if (cols[cidx]->validity) {
+                uint8_t *b = arena_alloc<uint8_t>(c, bm_bytes);
+                CU(cudaMemcpyAsync(b, cols[cidx]->validity, bm_bytes, cudaMemcpyHostToDevice, c->stream));
+                dev_bm[cidx] = b;
+            }
+        }
+    }
+    if (f->row_index) {
+        if (f->memspace == B200OLS_DEVICE) {
+            dev_rowidx = f->row_index;
+        } else {
+            int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(n));
+            CU(cudaMemcpyAsync(d, f->row_index, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
+            dev_rowidx = d;
+        }
+    }
+    st->row_index = dev_rowidx;
+    st->y_validity = dev_bm[kd];
+    st->y_raw = dev_vals[kd];
+    st->y_raw_packed = 0;
+
+    // 2) gather / null policy pass (only when needed)
+    int fill, mask_kind;
+    policy_to_prep(policy, moving, &fill, &mask_kind);
+    const bool need_prep = any_validity || dev_rowidx != nullptr;
+    if (!need_prep) {
+        if (f->memspace == B200OLS_DEVICE) {
+            for (int cidx = 0; cidx < ncol; ++cidx)
+                if ((reinterpret_cast<uintptr_t>(dev_vals[cidx]) & 15u) != 0)
+                    return fail(B200OLS_ERR_INVALID, "device column %d is not 16-byte aligned", cidx);
+        }
+        for (int j = 0; j < kd; ++j) st->feat[j] = dev_vals[j];
+        st->y = dev_vals[kd];
+        st->w = st->has_w ? dev_vals[kd + 1] : nullptr;
+        st->w_is_sqrt = 0;
+        st->mask = nullptr;
+        return 0;
+    }
+    PrepParams pp;
+    std::memset(&pp, 0, sizeof(pp));
+    pp.kd = kd;
+    pp.has_w = st->has_w;
+    pp.fill = fill;
+    pp.mask_kind = any_validity ? mask_kind : MASK_NONE;
+    pp.n_rows = n;
+    pp.n_rows_pad = n_pad;
+    pp.row_index = dev_rowidx;
+    for (int cidx = 0; cidx < ncol; ++cidx) {
+        pp.in[cidx] = dev_vals[cidx];
+        pp.validity[cidx] = dev_bm[cidx];
+        pp.out[cidx] = arena_alloc<char>(c, static_cast<size_t>(n_pad) * esz);
+    }
+    if (pp.mask_kind != MASK_NONE) pp.mask_out = arena_alloc<char>(c, static_cast<size_t>(n_pad) * esz);
+    if (f->dtype == B200OLS_F64) launch_prep<double>(c, pp); else launch_prep<float>(c, pp);
+    CU(cudaGetLastError());
+    for (int j = 0; j < kd; ++j) st->feat[j] = pp.out[j];
+    st->y = pp.out[kd];
+    st->w = st->has_w ? pp.out[kd + 1] : nullptr;
+    st->w_is_sqrt = 1;
+    st->mask = pp.mask_out;
+    st->prepped = true;
+    return 0;
+}
+
+// upper bound of the arena bytes stage_frame() may take
+static size_t stage_bytes_bound(const b200ols_frame *f) {
+    const size_t esz = f->dtype == B200OLS_F64 ? 8 : 4;
+    const size_t n_pad = round_up(static_cast<size_t>(f->n_rows), 16 / esz) + 64;
+    const size_t ncol = static_cast<size_t>(f->n_features) + 2;
+    size_t b = 0;
+    const size_t per_col = round_up(n_pad * esz, 256) + 256;
+    if (f->memspace == B200OLS_HOST) b += ncol * (per_col + round_up(static_cast<size_t>(f->n_rows) / 8 + 1, 256) + 256);
+    if (f->row_index && f->memspace == B200OLS_HOST) b += round_up(static_cast<size_t>(f->n_rows) * 8, 256) + 256;
+    b += (ncol + 1) * per_col;  // prep outputs + mask
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment plan: groups longer than SEG_MAX rows are split so that one warp never owns more than that
+// ------------------------------------------------------------------------------------------------
+struct Plan {
+    int64_t nseg = 0;
+    const int64_t *seg_off = nullptr;        // device [nseg+1]
+    const int32_t *seg_group = nullptr;      // device [nseg] or nullptr when segment == group
+    const int64_t *group_seg_off = nullptr;  // device [G+1] or nullptr
+    bool split = false;
+};
+
+static int build_plan(b200ols_ctx *c, const Staged &st, int64_t seg_max, Plan *pl) {
+    const int64_t G = st.n_groups;
+    std::vector<int64_t> seg_off;
+    std::vector<int32_t> seg_group;
+    std::vector<int64_t> gso;
+    pl->split = st.max_group_rows > seg_max;
+    if (!pl->split) {
+        pl->nseg = G;
+        const size_t bytes = sizeof(int64_t) * (G + 1);
+        TRY(pinned_reserve(c, c->pinned_off + bytes + 256));
+        char *h = c->pinned + c->pinned_off;
+        std::memcpy(h, st.offsets.data(), bytes);
+        c->pinned_off += round_up(bytes, 256);
+        int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(G) + 1);
+        CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+        pl->seg_off = d;
+        return 0;
+    }
+    gso.resize(G + 1);
+    seg_off.push_back(0);
+    for (int64_t g = 0; g < G; ++g) {
+        gso[g] = static_cast<int64_t>(seg_group.size());
+        const int64_t a = st.offsets[g], b = st.offsets[g + 1];
+        if (b == a) {  // empty group still owns one (empty) segment so that it gets its zero coefficients
+            seg_group.push_back(static_cast<int32_t>(g));
+            seg_off.push_back(b);
+            continue;
+        }
+        const int64_t parts = (b - a + seg_max - 1) / seg_max;
+        const int64_t step = ((b - a + parts - 1) / parts + 15) & ~static_cast<int64_t>(15);
+        for (int64_t s = a; s < b; s += step) {
+            seg_group.push_back(static_cast<int32_t>(g));
+            seg_off.push_back(std::min(s + step, b));
+        }
+    }
+    gso[G] = static_cast<int64_t>(seg_group.size());
+    pl->nseg = static_cast<int64_t>(seg_group.size());
+    const size_t b0 = sizeof(int64_t) * seg_off.size(), b1 = sizeof(int32_t) * seg_group.size(), b2 = sizeof(int64_t) * gso.size();
+    TRY(pinned_reserve(c, c->pinned_off + b0 + b1 + b2 + 1024));
+    char *h0 = c->pinned + c->pinned_off; c->pinned_off += round_up(b0, 256);
+    char *h1 = c->pinned + c->pinned_off; c->pinned_off += round_up(b1, 256);
+    char *h2 = c->pinned + c->pinned_off; c->pinned_off += round_up(b2, 256);
+    std::memcpy(h0, seg_off.data(), b0);
+    std::memcpy(h1, seg_group.data(), b1);
+    std::memcpy(h2, gso.data(), b2);
+    int64_t *d0 = arena_alloc<int64_t>(c, seg_off.size());
+    int32_t *d1 = arena_alloc<int32_t>(c, seg_group.size());
+    int64_t *d2 = arena_alloc<int64_t>(c, gso.size());
+    CU(cudaMemcpyAsync(d0, h0, b0, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d1, h1, b1, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d2, h2, b2, cudaMemcpyHostToDevice, c->stream));
+    pl->seg_off = d0;
+    pl->seg_group = d1;
+    pl->group_seg_off = d2;
+    return 0;
+}
+
+static size_t plan_bytes_bound(const b200ols_frame *f, int64_t seg_max) {
+    const size_t nseg = static_cast<size_t>(f->n_groups) + static_cast<size_t>(f->n_rows / std::max<int64_t>(seg_max / 2, 1)) + 2;
+    return (nseg + static_cast<size_t>(f->n_groups) + 4) * 24 + 4096;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gram launch
+// ------------------------------------------------------------------------------------------------
+// choose tile rows / stages / warps so that the CTA's shared memory fits, then launch
+template <typename T>
+static int launch_gram(b200ols_ctx *c, GramParams &gp) {
+    const int F = gp.F;
+    const int KB = (F + 7) / 8;
+    const int NC = gp.kd + 1 + gp.has_w + gp.has_mask;
+    const size_t budget = static_cast<size_t>(c->smem_optin) - 2048;  // static mbarriers + slack
+    const int KBT = KB <= 1 ? 1 : (KB <= 2 ? 2 : (KB <= 4 ? 4 : 8));  // instantiated block counts
+    int warps = c->warps_per_cta > 0 ? c->warps_per_cta : 8;
+    warps = std::min(warps, gram_max_warps(KBT));
+    int R = c->tile_rows > 0 ? c->tile_rows : 64;
+    int S = 4;
+    auto need = [&](int r, int s, int w) {
+        return (static_cast<size_t>(s) * NC * gram_col_stride<T>(r) + gram_scratch_bytes<T>(F, gp.fused)) * w;
+    };
+    while (need(R, S, warps) > budget) {
+        if (R > 16) R -= 8;
+        else if (S > 2) --S;
+        else if (warps > 1) --warps;
+        else return fail(B200OLS_ERR_UNSUPPORTED, "Gram tile does not fit in shared memory (%d columns)", NC);
+    }
+    gp.tile_rows = R;
+    gp.stages = S;
+    const size_t smem = need(R, S, warps);
+    const int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : 1;
+    int64_t grid = std::min<int64_t>(static_cast<int64_t>(c->sm_count) * ctas_per_sm, (gp.nseg + warps - 1) / warps);
+    grid = std::max<int64_t>(grid, 1);
+    CU(sizeof(T) == 8 ? gram_launch_f64(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream)
+                      : gram_launch_f32(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream));
+    c->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// static models: least_squares / least_squares_coefficients
+// ------------------------------------------------------------------------------------------------
+struct StaticRoute {
+    int route = ROUTE_CHOL;   // ROUTE_*
+    bool ols_qr_guard = false;  // OLS branch (QR in the reference): re-solve ill-conditioned groups by QR
+    double alpha = 0.0, l1_ratio = 0.0, tol = 1e-5;
+    int64_t max_iter = 1000;
+    int positive = 0;
+};
+
+// _get_least_squares_coefficients dispatch (src/expressions.rs:361-387) + argument checks of
+// solve_ols / solve_ridge / solve_elastic_net (src/least_squares.rs:231,349,366,402-413)
+static int resolve_route(const b200ols_ols_kwargs *kw, StaticRoute *r) {
+    const double alpha = std::isnan(kw->alpha) ? 0.0 : kw->alpha;
+    const bool positive = kw->positive != 0;
+    const int m = kw->solve_method;
+    if (m < B200OLS_SOLVE_NONE || m > B200OLS_SOLVE_CD_ACTIVE_SET) return fail(B200OLS_ERR_INVALID, "invalid solve_method detected!");
+    if (kw->null_policy < B200OLS_NULL_IGNORE || kw->null_policy > B200OLS_NULL_DROP_Y_ZERO_X)
+        return fail(B200OLS_ERR_INVALID, "Invalid null_policy detected!");  // drop_window is rolling-only
+    r->alpha = alpha;
+    r->positive = positive ? 1 : 0;
+    r->max_iter = kw->max_iter < 0 ? 1000 : kw->max_iter;
+    r->tol = std::isnan(kw->tol) ? 1e-5 : kw->tol;
+    if (alpha == 0.0 && !positive && (m == B200OLS_SOLVE_NONE || m == B200OLS_SOLVE_SVD || m == B200OLS_SOLVE_QR)) {
+        if (m == B200OLS_SOLVE_SVD)
+            return fail(B200OLS_ERR_UNSUPPORTED, "solve_method='svd' (LAPACK dgelsd min-norm) is not implemented on the device yet");
+        r->route = ROUTE_CHOL;
+        r->ols_qr_guard = true;
+        return 0;
+    }
+    const double l1 = std::isnan(kw->l1_ratio) ? 0.0 : kw->l1_ratio;
+    if (alpha >= 0.0 && l1 == 0.0 && !positive) {
+        if (m == B200OLS_SOLVE_NONE || m == B200OLS_SOLVE_CHOL) r->route = ROUTE_CHOL;
+        else if (m == B200OLS_SOLVE_LU) r->route = ROUTE_LU;
+        else if (m == B200OLS_SOLVE_SVD)
+            return fail(B200OLS_ERR_UNSUPPORTED, "ridge solve_method='svd' is not implemented on the device yet");
+        else return fail(B200OLS_ERR_INVALID, "Only 'Cholesky', 'LU', & 'SVD' are currently supported solver methods for Ridge.");
+        return 0;
+    }
+    // elastic net
+    if (!(m == B200OLS_SOLVE_NONE || m == B200OLS_SOLVE_CD || m == B200OLS_SOLVE_CD_ACTIVE_SET))
+        return fail(B200OLS_ERR_INVALID, "Only solve_method 'CD' (coordinate descent) is currently supported for Elastic Net / Lasso problems.");
+    if (!(alpha > 0.0)) return fail(B200OLS_ERR_INVALID, "'alpha' must be strictly positive");
+    r->l1_ratio = std::isnan(kw->l1_ratio) ? 0.5 : kw->l1_ratio;
+    if (!(r->l1_ratio >= 0.0 && r->l1_ratio <= 1.0)) return fail(B200OLS_ERR_INVALID, "'l1_ratio' must be strictly between 0. and 1.");
+    r->route = (m == B200OLS_SOLVE_CD_ACTIVE_SET) ? ROUTE_CD_ACTIVE : ROUTE_CD;
+    return 0;
+}
+
+static constexpr int64_t SEG_MAX_ROWS = 4096;
+static constexpr double ILLCOND_RATIO = 1.0e7;  // squared-pivot ratio above which OLS is re-solved by QR
+
+static int run_static(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (!kw || !out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    TRY(validate_frame(f));
+    if (mode != B200OLS_PREDICTIONS && mode != B200OLS_RESIDUALS && mode != B200OLS_COEFFICIENTS)
+        return fail(B200OLS_ERR_INVALID, "bad mode %d", mode);
+    StaticRoute rt;
+    TRY(resolve_route(kw, &rt));
+    CU(cudaSetDevice(c->device));
+    TRY(free_retired(c));
+
+    const int F = f->n_features + (f->add_intercept ? 1 : 0);
+    const int64_t G = f->n_groups, N = f->n_rows;
+    const size_t P = static_cast<size_t>(F) * F + F + 1;
+    // arena budget
+    size_t bytes = stage_bytes_bound(f) + plan_bytes_bound(f, SEG_MAX_ROWS);
+    const size_t nseg_bound = static_cast<size_t>(G) + static_cast<size_t>(N / (SEG_MAX_ROWS / 2)) + 2;
+    bytes += nseg_bound * P * 8 + static_cast<size_t>(G) * (static_cast<size_t>(F) * F + 4 * F) * 8;  // partials + work
+    bytes += static_cast<size_t>(G) * F * 8 + static_cast<size_t>(G) * 4 + 4096;                     // beta + flags
+    if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * 9 + 4096;                         // out + validity
+    if (rt.ols_qr_guard) bytes += static_cast<size_t>(F + 1) * static_cast<size_t>(N) * 8 + 4096;  // QR workspace
+    bytes += 1 << 20;
+    TRY(arena_reserve(c, bytes));
+    c->arena_off = 0;
+    c->pinned_off = 0;
+
+    Staged st;
+    TRY(stage_frame(c, f, kw->null_policy, false, &st));
+    Plan pl;
+    TRY(build_plan(c, st, SEG_MAX_ROWS, &pl));
+
+    double *beta = arena_alloc<double>(c, static_cast<size_t>(G) * F);
+    int32_t *flags = arena_alloc<int32_t>(c, static_cast<size_t>(G));
+    c->last_flags = flags;
+    c->last_flags_n = G;
+
+    // wide / under-determined groups take the LAPACK SVD path in the reference (src/least_squares.rs:225-229)
+    if (rt.ols_qr_guard && !st.prepped) {
+        for (int64_t g = 0; g < G; ++g) {
+            const int64_t len = st.offsets[g + 1] - st.offsets[g];
+            if (len > 0 && len <= F)
+                return fail(B200OLS_ERR_UNSUPPORTED,
+                            "group %lld has n=%lld <= k=%d rows: the min-norm SVD path is not implemented on the device yet",
+                            (long long)g, (long long)len, F);
+        }
+    }
+
+    GramParams gp;
+    std::memset(&gp, 0, sizeof(gp));
+    for (int j = 0; j < st.kd; ++j) gp.cols[j] = st.feat[j];
+    gp.cols[st.kd] = st.y;
+    int nc = st.kd + 1;
+    if (st.has_w) gp.cols[nc++] = st.w;
+    if (st.mask) gp.cols[nc++] = st.mask;
+    gp.kd = st.kd;
+    gp.intercept = st.intercept;
+    gp.F = F;
+    gp.has_w = st.has_w;
+    gp.w_is_sqrt = st.w_is_sqrt;
+    gp.has_mask = st.mask ? 1 : 0;
+    gp.n_rows_pad = st.n_pad;
+    gp.nseg = pl.nseg;
+    gp.seg_off = pl.seg_off;
+    gp.seg_group = pl.seg_group;
+    gp.alpha = rt.alpha;
+    gp.use_lu = rt.route == ROUTE_LU;
+    gp.illcond_ratio = ILLCOND_RATIO;
+    gp.beta = beta;
+    gp.flags = flags;
+    const bool cd = rt.route == ROUTE_CD || rt.route == ROUTE_CD_ACTIVE;
+    gp.fused = (!pl.split && !cd && F <= 16) ? 1 : 0;
+    if (!gp.fused) gp.partial = arena_alloc<double>(c, static_cast<size_t>(pl.nseg) * P);
+
+    ARENA_GUARD(c);
+    if (f->dtype == B200OLS_F64) TRY(launch_gram<double>(c, gp)); else TRY(launch_gram<float>(c, gp));
+
+    if (!gp.fused) {
+        SolveParams sp;
+        std::memset(&sp, 0, sizeof(sp));
+        sp.F = F;
+        sp.n_groups = G;
+        sp.partial = gp.partial;
+        sp.group_seg_off = pl.group_seg_off;
+        sp.work = arena_alloc<double>(c, static_cast<size_t>(G) * (static_cast<size_t>(F) * F + 4 * F));
+        sp.beta = beta;
+        sp.flags = flags;
+        sp.route = rt.route;
+        sp.alpha = rt.alpha;
+        sp.l1_ratio = rt.l1_ratio;
+        sp.tol = rt.tol;
+        sp.illcond_ratio = ILLCOND_RATIO;
+        sp.max_iter = rt.max_iter;
+        sp.positive = rt.positive;
+        const unsigned blocks = static_cast<unsigned>((G + 63) / 64);
+        small_solve_kernel<<<blocks, 64, 0, c->stream>>>(sp);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+
+    if (rt.ols_qr_guard) {
+        // groups whose Gram is too ill-conditioned for 1e-6 parity with the reference's QR are re-solved
+        // from the data by Householder QR with column pivoting (faer col_piv_qr, src/least_squares.rs:195-205)
+        QrParams qp;
+        std::memset(&qp, 0, sizeof(qp));
+        for (int j = 0; j < st.kd; ++j) qp.cols[j] = st.feat[j];
+        qp.cols[st.kd] = st.y;
+        qp.w = st.w;
+        qp.mask = st.mask;
+        qp.kd = st.kd;
+        qp.intercept = st.intercept;
+        qp.F = F;
+        qp.w_is_sqrt = st.w_is_sqrt;
+        qp.n_groups = G;
+        qp.group_off = pl.split ? nullptr : pl.seg_off;
+        if (pl.split) {
+            // group offsets on the device (the split plan only holds segment offsets)
+            const size_t ob = sizeof(int64_t) * (G + 1);
+            TRY(pinned_reserve(c, c->pinned_off + ob + 256));
+            char *h = c->pinned + c->pinned_off;
+            c->pinned_off += round_up(ob, 256);
+            std::memcpy(h, st.offsets.data(), ob);
+            int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(G) + 1);
+            CU(cudaMemcpyAsync(d, h, ob, cudaMemcpyHostToDevice, c->stream));
+            qp.group_off = d;
+        }
+        qp.beta = beta;
+        qp.flags = flags;
+        qp.n_rows = st.n;
+        qp.ws = arena_alloc<double>(c, static_cast<size_t>(F + 1) * static_cast<size_t>(st.n) + 8);
+        ARENA_GUARD(c);
+        CU(launch_qr_fallback_kernel(c->stream, qp, f->dtype == B200OLS_F64));
+        c->launches++;
+    }
+
+    // outputs
+    if (mode == B200OLS_COEFFICIENTS) {
+        const size_t ob = static_cast<size_t>(G) * F * sizeof(double);
+        if (f->memspace == B200OLS_HOST) {
+            CU(cudaMemcpyAsync(out->values, beta, ob, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (out->validity)
+                for (size_t i = 0; i < static_cast<size_t>(G) * F; ++i) out->validity[i] = std::isnan(out->values[i]) ? 0 : 1;
+        } else {
+            CU(cudaMemcpyAsync(out->values, beta, ob, cudaMemcpyDeviceToDevice, c->stream));
+            if (out->validity) {
+                nan_mask_kernel<<<static_cast<unsigned>((static_cast<size_t>(G) * F + 255) / 256), 256, 0, c->stream>>>(out->values, out->validity, static_cast<int64_t>(G) * F);
+                c->launches++;
+            }
+        }
+        return 0;
+    }
+
+    PredictParams pr;
+    std::memset(&pr, 0, sizeof(pr));
+    for (int j = 0; j < st.kd; ++j) pr.cols[j] = st.feat[j];
+    if (st.has_w) pr.cols[st.kd] = st.w;
+    pr.kd = st.kd;
+    pr.intercept = st.intercept;
+    pr.F = F;
+    pr.has_w = st.has_w;
+    pr.w_is_sqrt = st.w_is_sqrt;
+    pr.target = st.y_raw;
+    pr.target_is_packed = st.y_raw_packed;
+    pr.target_validity = st.y_validity;
+    pr.mask = (kw->null_policy == B200OLS_NULL_DROP) ? st.mask : nullptr;
+    pr.nseg = pl.nseg;
+    pr.seg_off = pl.seg_off;
+    pr.seg_group = pl.seg_group;
+    pr.beta = beta;
+    pr.row_index = st.row_index;
+    pr.residuals = mode == B200OLS_RESIDUALS;
+    double *dout = out->values;
+    uint8_t *dval = out->validity;
+    if (f->memspace == B200OLS_HOST) {
+        dout = arena_alloc<double>(c, static_cast<size_t>(N));
+        dval = out->validity ? arena_alloc<uint8_t>(c, static_cast<size_t>(N)) : nullptr;
+    }
+    pr.out = dout;
+    pr.out_valid = dval;
+    {
+        const int64_t warps_needed = pl.nseg;
+        const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
+        if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
+        else predict_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (f->memspace == B200OLS_HOST) {
+        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(N), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+extern "C" int b200ols_least_squares(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode,
+                                     b200ols_output *out) {
+    if (mode == B200OLS_COEFFICIENTS) return fail(B200OLS_ERR_INVALID, "use b200ols_least_squares_coefficients for mode=coefficients");
+    return run_static(c, f, kw, mode, out);
+}
+
+extern "C" int b200ols_least_squares_coefficients(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw,
+                                                  b200ols_output *out) {
+    return run_static(c, f, kw, B200OLS_COEFFICIENTS, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// moving-window models: rls / rolling (moving.cuh)
+// ------------------------------------------------------------------------------------------------
+int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets, bool f64, int sm_count, char *ws,
+                         int64_t *launches) {
+    const int64_t G = p.n_groups;
+    const int64_t L = moving_chunk_len(p.n_rows, sm_count, p.kind, p.window);
+    std::vector<int64_t> r0, r1, gco(static_cast<size_t>(G) + 1);
+    std::vector<int32_t> cg;
+    for (int64_t g = 0; g < G; ++g) {
+        gco[g] = static_cast<int64_t>(r0.size());
+        for (int64_t a = offsets[g]; a < offsets[g + 1]; a += L) {
+            r0.push_back(a);
+            r1.push_back(std::min(a + L, offsets[g + 1]));
+            cg.push_back(static_cast<int32_t>(g));
+        }
+    }
+    gco[G] = static_cast<int64_t>(r0.size());
+    const size_t nc = r0.size();
+    p.n_chunks = static_cast<int64_t>(nc);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *q = ws + off; off += (bytes + 255) & ~static_cast<size_t>(255); return q; };
+    int64_t *d_r0 = reinterpret_cast<int64_t *>(take(nc * 8 + 8));
+    int64_t *d_r1 = reinterpret_cast<int64_t *>(take(nc * 8 + 8));
+    int32_t *d_cg = reinterpret_cast<int32_t *>(take(nc * 4 + 8));
+    int64_t *d_gco = reinterpret_cast<int64_t *>(take((G + 1) * 8));
+    p.series_info = reinterpret_cast<int64_t *>(take(static_cast<size_t>(G) * 24 + 8));
+    p.summaries = reinterpret_cast<double *>(take(p.kind == MOVING_RLS ? nc * MOVING_REC * 8 + 8 : 8));
+    if (off > moving_workspace_bytes(p.n_rows, G, p.F)) return fail(B200OLS_ERR_CUDA, "internal: moving workspace under-sized");
+    // pageable -> device async copies are staged by the driver before the call returns
+    if (nc) {
+        CU(cudaMemcpyAsync(d_r0, r0.data(), nc * 8, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(d_r1, r1.data(), nc * 8, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(d_cg, cg.data(), nc * 4, cudaMemcpyHostToDevice, stream));
+    }
+    CU(cudaMemcpyAsync(d_gco, gco.data(), (G + 1) * 8, cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));  // host vectors go out of scope; tables are tiny
+    p.chunk_r0 = d_r0;
+    p.chunk_r1 = d_r1;
+    p.chunk_group = d_cg;
+    CU(f64 ? moving_launch_f64(stream, p, d_gco, launches) : moving_launch_f32(stream, p, d_gco, launches));
+    return 0;
+}
+
+static int run_moving(b200ols_ctx *c, const b200ols_frame *f, int kind, const b200ols_rls_kwargs *rk,
+                      const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (!out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    TRY(validate_frame(f));
+    const int policy = kind == MOVING_RLS ? rk->null_policy : wk->null_policy;
+    if (policy < B200OLS_NULL_IGNORE || policy > B200OLS_NULL_DROP_WINDOW) return fail(B200OLS_ERR_INVALID, "Invalid null_policy detected!");
+    const int F = f->n_features + (f->add_intercept ? 1 : 0);
+    if (F > MOVING_MAX_K)
+        return fail(B200OLS_ERR_UNSUPPORTED, "rls/rolling with more than %d coefficients is not implemented on the device yet", MOVING_MAX_K);
+    CU(cudaSetDevice(c->device));
+    TRY(free_retired(c));
+    const int64_t N = f->n_rows, G = f->n_groups;
+
+    MovingParams mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.kind = kind;
+    mp.F = F;
+    if (kind == MOVING_RLS) {
+        const double hl = rk->half_life;
+        mp.lambda = (!std::isnan(hl) && hl > 0.0) ? std::exp(std::log(0.5) / hl) : 1.0;  // src/least_squares.rs:513-517
+        // Some(half_life <= 0) is not rejected by the reference either: exp(ln(.5)/hl)
+        if (!std::isnan(hl) && hl <= 0.0) mp.lambda = std::exp(std::log(0.5) / hl);
+        mp.p0 = std::isnan(rk->initial_state_covariance) ? 10.0 : rk->initial_state_covariance;
+        mp.has_mean = (rk->initial_state_mean != nullptr && mode == B200OLS_COEFFICIENTS) ? 1 : 0;  // quirk A.5.1
+        if (mp.has_mean)
+            for (int j = 0; j < F; ++j) mp.mean[j] = rk->initial_state_mean[j];
+    } else {
+        if (wk->window_size < 1) return fail(B200OLS_ERR_INVALID, "window_size must be >= 1");
+        mp.window = wk->window_size;
+        mp.min_periods = wk->min_periods < 0 ? std::min<int64_t>(F, wk->window_size) : wk->min_periods;  // :860
+        if (mp.min_periods < 1) return fail(B200OLS_ERR_INVALID, "min_periods must be >= 1");
+        mp.alpha = std::isnan(wk->alpha) ? 0.0 : wk->alpha;
+        mp.fixed_window = !(policy == B200OLS_NULL_DROP || policy == B200OLS_NULL_DROP_ZERO || policy == B200OLS_NULL_DROP_Y_ZERO_X);  // :947-950
+    }
+
+    size_t bytes = stage_bytes_bound(f) + (static_cast<size_t>(G) + 8) * 64 + moving_workspace_bytes(N, G, F) + (1 << 20);
+    if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * (static_cast<size_t>(F) * 9 + 16) + 4096;
+    TRY(arena_reserve(c, bytes));
+    c->arena_off = 0;
+    c->pinned_off = 0;
+    c->last_flags = nullptr;
+
+    Staged st;
+    TRY(stage_frame(c, f, policy, true, &st));
+    // group offsets on the device
+    {
+        const size_t ob = sizeof(int64_t) * (G + 1);
+        TRY(pinned_reserve(c, c->pinned_off + ob + 256));
+        char *h = c->pinned + c->pinned_off;
+        c->pinned_off += round_up(ob, 256);
+        std::memcpy(h, st.offsets.data(), ob);
+        int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(G) + 1);
+        CU(cudaMemcpyAsync(d, h, ob, cudaMemcpyHostToDevice, c->stream));
+        mp.group_off = d;
+    }
+    for (int j = 0; j < st.kd; ++j) mp.cols[j] = st.feat[j];
+    mp.cols[st.kd] = st.y;
+    mp.w = st.w;
+    mp.w_is_sqrt = st.w_is_sqrt;
+    mp.mask = st.mask;
+    mp.kd = st.kd;
+    mp.intercept = st.intercept;
+    mp.n_groups = G;
+    mp.n_rows = N;
+    mp.row_index = st.row_index;
+    mp.mode = mode;
+    mp.target = st.y_raw;
+    mp.target_is_packed = st.y_raw_packed;
+    mp.target_validity = st.y_validity;
+    mp.mask_predictions = (st.mask != nullptr) ? 1 : 0;  // src/expressions.rs:640-645,695-700
+    const size_t out_elems = mode == B200OLS_COEFFICIENTS ? static_cast<size_t>(N) * F : static_cast<size_t>(N);
+    double *dout = out->values;
+    uint8_t *dval = out->validity;
+    if (f->memspace == B200OLS_HOST) {
+        dout = arena_alloc<double>(c, out_elems);
+        dval = out->validity ? arena_alloc<uint8_t>(c, out_elems) : nullptr;
+    }
+    mp.out = dout;
+    mp.out_valid = dval;
+    char *ws = arena_alloc<char>(c, moving_workspace_bytes(N, G, F));
+    ARENA_GUARD(c);
+    TRY(launch_moving(c->stream, mp, st.offsets.data(), f->dtype == B200OLS_F64, c->sm_count, ws, &c->launches));
+    if (f->memspace == B200OLS_HOST) {
+        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * out_elems, cudaMemcpyDeviceToHost, c->stream));
+        if (dval) CU(cudaMemcpyAsync(out->validity, dval, out_elems, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+extern "C" int b200ols_recursive_least_squares(b200ols_ctx *c, const b200ols_frame *f, const b200ols_rls_kwargs *kw, int mode,
+                                               b200ols_output *out) {
+    if (!kw) return fail(B200OLS_ERR_INVALID, "kwargs is NULL");
+    if (mode != B200OLS_PREDICTIONS && mode != B200OLS_RESIDUALS) return fail(B200OLS_ERR_INVALID, "bad mode %d", mode);
+    return run_moving(c, f, MOVING_RLS, kw, nullptr, mode, out);
+}
+extern "C" int b200ols_recursive_least_squares_coefficients(b200ols_ctx *c, const b200ols_frame *f,
+                                                            const b200ols_rls_kwargs *kw, b200ols_output *out) {
+    if (!kw) return fail(B200OLS_ERR_INVALID, "kwargs is NULL");
+    return run_moving(c, f, MOVING_RLS, kw, nullptr, B200OLS_COEFFICIENTS, out);
+}
+extern "C" int b200ols_rolling_least_squares(b200ols_ctx *c, const b200ols_frame *f, const b200ols_rolling_kwargs *kw, int mode,
+                                             b200ols_output *out) {
+    if (!kw) return fail(B200OLS_ERR_INVALID, "kwargs is NULL");
+    if (mode != B200OLS_PREDICTIONS && mode != B200OLS_RESIDUALS) return fail(B200OLS_ERR_INVALID, "bad mode %d", mode);
+    return run_moving(c, f, MOVING_ROLLING, nullptr, kw, mode, out);
+}
+extern "C" int b200ols_rolling_least_squares_coefficients(b200ols_ctx *c, const b200ols_frame *f,
+                                                          const b200ols_rolling_kwargs *kw, b200ols_output *out) {
+    if (!kw) return fail(B200OLS_ERR_INVALID, "kwargs is NULL");
+    return run_moving(c, f, MOVING_ROLLING, nullptr, kw, B200OLS_COEFFICIENTS, out);
+}

@@ -1,0 +1,296 @@
+// moving.cuh — kernels + launcher for recursive_least_squares{,_coefficients} and
+// rolling_least_squares{,_coefficients} (src/expressions.rs:594-701 of /root/reference) over the
+// chunk algorithms of moving_core.cuh.  One thread per (series, time chunk); all series (groups of the
+// `.over()` context) and all chunks of one frame run in a single launch per pass:
+//   rolling : [prepass per series (only with a row mask)] -> rolling_main
+//   rls     : rls_summary -> rls_scan (per series, lanes = matrix elements) -> rls_main
+// Outputs are scattered to the original row order; predictions are (X o Theta).sum(1) with the WLS
+// un-scaling and the null masks of src/expressions.rs:640-645,695-700 and
+// polars_ols/least_squares.py:234-239,407-408 fused in.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "gram_stream.cuh"
+#include "moving_core.cuh"
+
+namespace b200 {
+
+struct MovingParams {
+    const void *cols[GRAM_MAX_COLS];  // [0,kd) features, [kd] target (cleaned: zero filled)
+    const void *w;                    // weights / sqrt-weights or nullptr
+    const void *mask;                 // T-typed row validity or nullptr (all valid)
+    int kd, intercept, F, w_is_sqrt;
+    int kind;                         // MOVING_RLS | MOVING_ROLLING
+    int mode;                         // B200OLS_PREDICTIONS(0) | RESIDUALS(1) | COEFFICIENTS(2)
+    int mask_predictions;             // policy has a validity mask: invalid rows -> null predictions
+    int64_t n_groups, n_rows;
+    const int64_t *group_off;         // device [G+1]
+    const int64_t *row_index;         // packed -> original or nullptr
+    const void *target;               // raw target (residuals)
+    int target_is_packed;
+    const uint8_t *target_validity;   // bitmap over original rows or nullptr
+    double *out;
+    uint8_t *out_valid;
+    // rls
+    double lambda, p0;
+    int has_mean;
+    double mean[MOVING_MAX_K];
+    // rolling
+    int64_t window, min_periods;
+    double alpha;
+    int fixed_window;
+    // chunk table (device) + workspace
+    int64_t n_chunks;
+    const int64_t *chunk_r0, *chunk_r1;
+    const int32_t *chunk_group;
+    double *summaries;                // [n_chunks][REC]  rls
+    int64_t *series_info;             // [G][3] rolling: mpv, n_valid, all_nan
+};
+
+constexpr int MOVING_REC = MOVING_MAX_K * MOVING_MAX_K + MOVING_MAX_K + 1;
+
+template <typename T, int K>
+struct DevSrc {
+    const T *x[K];
+    const T *y, *w, *mask;
+    int kd, w_is_sqrt;
+    __device__ __forceinline__ bool valid(int64_t r) const { return mask ? (mask[r] != T(0)) : true; }
+    __device__ __forceinline__ T scale(int64_t r) const {
+        if (!w) return T(1);
+        const T v = w[r];
+        return w_is_sqrt ? v : static_cast<T>(sqrt(v));
+    }
+    __device__ __forceinline__ void load(int64_t r, double (&xo)[K], double &yo) const {
+        const T s = scale(r);
+#pragma unroll
+        for (int j = 0; j < K; ++j) xo[j] = (j < kd) ? static_cast<double>(static_cast<T>(x[j][r] * s)) : static_cast<double>(s);
+        yo = static_cast<double>(static_cast<T>(y[r] * s));
+    }
+};
+
+template <typename T, int K>
+__device__ __forceinline__ DevSrc<T, K> make_src(const MovingParams &p) {
+    DevSrc<T, K> s;
+#pragma unroll
+    for (int j = 0; j < K; ++j) s.x[j] = (j < p.kd) ? static_cast<const T *>(p.cols[j]) : nullptr;
+    s.y = static_cast<const T *>(p.cols[p.kd]);
+    s.w = static_cast<const T *>(p.w);
+    s.mask = static_cast<const T *>(p.mask);
+    s.kd = p.kd;
+    s.w_is_sqrt = p.w_is_sqrt;
+    return s;
+}
+
+template <typename T, int K>
+struct DevEmit {
+    const MovingParams &p;
+    const DevSrc<T, K> &src;
+    __device__ __forceinline__ void operator()(int64_t r, const double (&beta)[K], bool) const {
+        const int64_t orow = p.row_index ? p.row_index[r] : r;
+        if (p.mode == 2) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                p.out[orow * K + j] = beta[j];
+                if (p.out_valid) p.out_valid[orow * K + j] = (beta[j] == beta[j]) ? 1 : 0;
+            }
+            return;
+        }
+        double x[K], y;
+        src.load(r, x, y);
+        double pred = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) pred += x[j] * beta[j];  // (features * coefficients).sum_axis(1)
+        if (p.w) pred *= static_cast<double>(T(1) / src.scale(r));
+        bool valid = true;
+        if (p.mask_predictions) valid = src.valid(r);
+        if (p.mode == 1) {
+            const int64_t trow = p.target_is_packed ? r : orow;
+            pred = static_cast<double>(static_cast<const T *>(p.target)[trow]) - pred;
+            if (p.target_validity) valid = valid && ((p.target_validity[orow >> 3] >> (orow & 7)) & 1);
+        }
+        if (p.kind == MOVING_ROLLING) valid = valid && (pred == pred);  // fill_nan(None)
+        p.out[orow] = pred;
+        if (p.out_valid) p.out_valid[orow] = valid ? 1 : 0;
+    }
+};
+
+template <typename T, int K>
+__global__ void __launch_bounds__(128) rolling_prepass_kernel(const MovingParams p) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (g >= p.n_groups) return;
+    const DevSrc<T, K> src = make_src<T, K>(p);
+    const RollingSeries rs = rolling_prepass(src, p.group_off[g], p.group_off[g + 1], p.min_periods);
+    p.series_info[g * 3 + 0] = rs.mpv;
+    p.series_info[g * 3 + 1] = rs.n_valid;
+    p.series_info[g * 3 + 2] = rs.all_nan;
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(128) rolling_main_kernel(const MovingParams p) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    const DevSrc<T, K> src = make_src<T, K>(p);
+    const int64_t g = p.chunk_group[c];
+    const int64_t g0 = p.group_off[g], g1 = p.group_off[g + 1];
+    RollingSeries rs;
+    if (p.series_info) {
+        rs.mpv = p.series_info[g * 3 + 0];
+        rs.n_valid = p.series_info[g * 3 + 1];
+        rs.all_nan = static_cast<int>(p.series_info[g * 3 + 2]);
+    } else {  // no mask: every row is valid
+        rs.mpv = p.min_periods;
+        rs.n_valid = (g1 - g0 < p.min_periods) ? (g1 - g0) : p.min_periods;
+        rs.all_nan = (g1 - g0) < p.min_periods;
+    }
+    RollingCfg cfg{p.window, p.min_periods, p.alpha, p.fixed_window};
+    DevEmit<T, K> emit{p, src};
+    rolling_chunk<K>(src, cfg, rs, g0, g1, p.chunk_r0[c], p.chunk_r1[c], emit);
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(128) rls_summary_kernel(const MovingParams p) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    const DevSrc<T, K> src = make_src<T, K>(p);
+    RlsCfg cfg{p.lambda, p.p0};
+    RlsSummary<K> s;
+    rls_summarise<K>(src, cfg, p.chunk_r0[c], p.chunk_r1[c], s);
+    double *rec = p.summaries + c * MOVING_REC;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) rec[i * K + j] = (j <= i) ? s.ab.S[i][j] : 0.0;
+        rec[K * K + i] = s.ab.v[i];
+    }
+    rec[K * K + K] = s.D;
+}
+
+// Exclusive scan over the chunks of each series: rec[c] <- information state ENTERING chunk c.
+// One warp per series, lanes over the K*K+K elements; the chunk loop is sequential (a few 10^4 steps at
+// most, each an FMA on coalesced 8-byte loads).
+template <int K>
+__global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, const int64_t *group_chunk_off) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (g >= p.n_groups) return;
+    constexpr int NE = K * K + K;
+    const int64_t c0 = group_chunk_off[g], c1 = group_chunk_off[g + 1];
+    double carry[(NE + 31) / 32];
+#pragma unroll
+    for (int t = 0; t < (NE + 31) / 32; ++t) {
+        const int e = lane + 32 * t;
+        double v = 0.0;
+        if (e < K * K) {
+            const int i = e / K, j = e % K;
+            v = (i == j) ? 1.0 / p.p0 : 0.0;            // A0 = I / p0
+        } else if (e < NE) {
+            v = (p.has_mean ? p.mean[e - K * K] : 0.0) / p.p0;  // b0 = A0 theta0
+        }
+        carry[t] = v;
+    }
+    for (int64_t c = c0; c < c1; ++c) {
+        double *rec = p.summaries + c * MOVING_REC;
+        const double D = rec[NE];
+#pragma unroll
+        for (int t = 0; t < (NE + 31) / 32; ++t) {
+            const int e = lane + 32 * t;
+            if (e < NE) {
+                const double add = rec[e];
+                rec[e] = carry[t];
+                carry[t] = fma(D, carry[t], add);
+            }
+        }
+    }
+}
+
+template <typename T, int K>
+__global__ void __launch_bounds__(128) rls_main_kernel(const MovingParams p) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    const DevSrc<T, K> src = make_src<T, K>(p);
+    const int64_t g = p.chunk_group[c];
+    const int64_t r0 = p.chunk_r0[c];
+    const bool first = r0 == p.group_off[g];
+    RlsCfg cfg{p.lambda, p.p0};
+    NormalState<K> in;
+    if (!first) {
+        const double *rec = p.summaries + c * MOVING_REC;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) in.S[i][j] = rec[i * K + j];
+            in.v[i] = rec[K * K + i];
+        }
+    }
+    DevEmit<T, K> emit{p, src};
+    rls_chunk<K>(src, cfg, first, p.has_mean ? p.mean : nullptr, &in, r0, p.chunk_r1[c], emit);
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+inline int64_t moving_chunk_len(int64_t n_rows, int sm_count, int kind, int64_t window) {
+    int64_t L = (n_rows + static_cast<int64_t>(sm_count) * 1024 - 1) / (static_cast<int64_t>(sm_count) * 1024);
+    L = ((L + 63) / 64) * 64;
+    if (L < 64) L = 64;
+    if (kind == MOVING_ROLLING) {
+        const int64_t w4 = std::min<int64_t>(window, 1 << 16) / 4;
+        if (L < w4) L = ((w4 + 63) / 64) * 64;
+    }
+    return L;
+}
+
+inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int /*F*/) {
+    const size_t max_chunks = static_cast<size_t>(n_rows / 64 + n_groups + 2);
+    return max_chunks * (MOVING_REC * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (3 * 8 + 8) + 8192;
+}
+
+template <typename T, int K>
+static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const int64_t *group_chunk_off_dev,
+                                   int64_t *launches) {
+    const unsigned cb = static_cast<unsigned>((p.n_chunks + 127) / 128);
+    if (p.n_chunks == 0) return cudaSuccess;
+    if (p.kind == MOVING_ROLLING) {
+        if (p.mask) {
+            rolling_prepass_kernel<T, K><<<static_cast<unsigned>((p.n_groups + 127) / 128), 128, 0, stream>>>(p);
+            ++*launches;
+        } else {
+            p.series_info = nullptr;
+        }
+        rolling_main_kernel<T, K><<<cb, 128, 0, stream>>>(p);
+        ++*launches;
+    } else {
+        rls_summary_kernel<T, K><<<cb, 128, 0, stream>>>(p);
+        rls_scan_kernel<K><<<static_cast<unsigned>((p.n_groups * 32 + 127) / 128), 128, 0, stream>>>(p, group_chunk_off_dev);
+        rls_main_kernel<T, K><<<cb, 128, 0, stream>>>(p);
+        *launches += 3;
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_moving_k(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches) {
+    switch (p.F) {
+        case 1: return launch_moving_t<T, 1>(s, p, gco, launches);
+        case 2: return launch_moving_t<T, 2>(s, p, gco, launches);
+        case 3: return launch_moving_t<T, 3>(s, p, gco, launches);
+        case 4: return launch_moving_t<T, 4>(s, p, gco, launches);
+        case 5: return launch_moving_t<T, 5>(s, p, gco, launches);
+        case 6: return launch_moving_t<T, 6>(s, p, gco, launches);
+        case 7: return launch_moving_t<T, 7>(s, p, gco, launches);
+        default: return launch_moving_t<T, 8>(s, p, gco, launches);
+    }
+}
+
+// defined in moving_f64.cu / moving_f32.cu
+cudaError_t moving_launch_f64(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
+cudaError_t moving_launch_f32(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
+
+// builds the chunk table on the host (group offsets are host metadata), uploads it into `ws` and launches
+int launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets_host, bool f64, int sm_count, char *ws,
+                  int64_t *launches);
+
+}  // namespace b200

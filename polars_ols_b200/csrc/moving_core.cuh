@@ -1,0 +1,437 @@
+// moving_core.cuh — time-parallel recursive / rolling least squares, one THREAD per time chunk with the
+// whole k x k state in registers (k <= 8).  Host/device templates: the kernels in moving.cuh and the CPU
+// host-check harness (tests/hostcheck) instantiate exactly this code.
+//
+// Reference recurrences restated (files relative to /root/reference):
+//   RecursiveLeastSquares::update           src/least_squares.rs:531-540
+//   solve_recursive_least_squares           src/least_squares.rs:568-598   (forward fill on invalid rows)
+//   solve_rolling_ols                       src/least_squares.rs:848-1032  (warm-up, both null branches)
+//   NonWoodburyState::{update,subtract,solve} src/least_squares.rs:700-735 (Cholesky -> LU per row)
+// The reference walks each series strictly sequentially.  Here a series is cut into chunks that run
+// concurrently; what a chunk needs from its past is rebuilt exactly:
+//   rolling : the window sums at the chunk start = a direct Gram over the previous W (valid) rows;
+//   rls     : information form A_t = lam A_{t-1} + x x^T, b_t = lam b_{t-1} + x y is associative, so a
+//             per-chunk summary pass + a scan over chunks gives (A, b) entering every chunk and
+//             P = A^-1, theta = P b restart the covariance-form recurrence (equal to the sequential
+//             result to rounding: SURVEY.md §7 hard part 2, verified in tests/test_hostcheck.py).
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#include "solvers.cuh"
+
+namespace b200 {
+
+constexpr int MOVING_MAX_K = 8;
+enum : int { MOVING_RLS = 0, MOVING_ROLLING = 1 };
+
+// ---- register-resident small matrices --------------------------------------------------------------
+template <int K>
+struct NormalState {   // S = sum x x^T (+ alpha I), v = sum x y   (lower triangle of S is authoritative)
+    double S[K][K];
+    double v[K];
+    B200_HD void clear() {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            v[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) S[i][j] = 0.0;
+        }
+    }
+    B200_HD void add(const double (&x)[K], double y, double sign) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const double xi = sign * x[i];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) S[i][j] = fma(xi, x[j], S[i][j]);
+            v[i] = fma(xi, y, v[i]);
+        }
+    }
+    B200_HD void decay(double lam) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            v[i] *= lam;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) S[i][j] *= lam;
+        }
+    }
+    B200_HD void add_diag(double a) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) S[i][i] += a;
+    }
+};
+
+// beta = S^-1 v by Cholesky (register resident); on a non-positive pivot fall back to LU with partial
+// pivoting on a local copy (solve_normal_equations(.., None, Some(LU)), src/least_squares.rs:732-734).
+template <int K>
+B200_HD void solve_normal(const NormalState<K> &st, double (&beta)[K]) {
+    double L[K][K];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double d = st.S[j][j];
+#pragma unroll
+        for (int p = 0; p < j; ++p) d = fma(-L[j][p], L[j][p], d);
+        if (!(d > 0.0)) ok = false;
+        const double sd = sqrt(d);
+        L[j][j] = sd;
+#pragma unroll
+        for (int i = j + 1; i < K; ++i) {
+            double s = st.S[i][j];
+#pragma unroll
+            for (int p = 0; p < j; ++p) s = fma(-L[i][p], L[j][p], s);
+            L[i][j] = s / sd;
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            double s = st.v[i];
+#pragma unroll
+            for (int p = 0; p < i; ++p) s = fma(-L[i][p], beta[p], s);
+            beta[i] = s / L[i][i];
+        }
+#pragma unroll
+        for (int i = K - 1; i >= 0; --i) {
+            double s = beta[i];
+#pragma unroll
+            for (int p = i + 1; p < K; ++p) s = fma(-L[p][i], beta[p], s);
+            beta[i] = s / L[i][i];
+        }
+        return;
+    }
+    double A[K * K], b[K];
+    for (int i = 0; i < K; ++i) {
+        b[i] = st.v[i];
+        for (int j = 0; j < K; ++j) A[i * K + j] = (j <= i) ? st.S[i][j] : st.S[j][i];
+    }
+    lu_solve_inplace(A, K, K, b);
+    for (int i = 0; i < K; ++i) beta[i] = b[i];
+}
+
+// ---- row access ------------------------------------------------------------------------------------
+// A RowSource provides, for a packed row index r of the series:
+//   bool valid(r)                      row enters the fit
+//   void load(r, double (&x)[K], double &y)   scaled features (incl. intercept) and target, f64
+template <int K, typename Src>
+B200_HD void gram_range(const Src &src, int64_t a, int64_t b, NormalState<K> &st) {
+    double x[K], y;
+    for (int64_t r = a; r < b; ++r)
+        if (src.valid(r)) {
+            src.load(r, x, y);
+            st.add(x, y, 1.0);
+        }
+}
+
+// ---- rolling ---------------------------------------------------------------------------------------
+struct RollingCfg {
+    int64_t window;       // W
+    int64_t min_periods;  // resolved (>= 1)
+    double alpha;         // >= 0, added once to the diagonal (src/least_squares.rs:924-926)
+    int fixed_window;     // 0: "last W valid rows" (drop*), 1: fixed row window (drop_window / zero / ignore)
+};
+
+// Per-series facts computed once (rolling_prepass): position of the min_periods-th valid row etc.
+struct RollingSeries {
+    int64_t mpv;      // min_periods_valid (src/least_squares.rs:881-891); rows < mpv-1 are NaN
+    int64_t n_valid;  // the reference's `n_valid` after that loop (= min_periods when reached)
+    int all_nan;      // n < max(n_valid, min_periods)  (:893-900)
+};
+
+template <typename Src>
+B200_HD RollingSeries rolling_prepass(const Src &src, int64_t g0, int64_t g1, int64_t min_periods) {
+    RollingSeries rs;
+    rs.mpv = min_periods;
+    rs.n_valid = 0;
+    for (int64_t i = g0; i < g1; ++i) {
+        if (src.valid(i)) rs.n_valid += 1;
+        if (rs.n_valid == min_periods) {
+            rs.mpv = (i - g0) + 1;
+            break;
+        }
+    }
+    const int64_t n = g1 - g0;
+    rs.all_nan = n < ((rs.n_valid > min_periods) ? rs.n_valid : min_periods);
+    return rs;
+}
+
+// Processes rows [c0, c1) of the series [g0, g1) (packed indices).  emit(r, beta, is_nan) is called once
+// per row in increasing r.
+template <int K, typename Src, typename Emit>
+B200_HD void rolling_chunk(const Src &src, const RollingCfg &cfg, const RollingSeries &rs, int64_t g0, int64_t g1,
+                           int64_t c0, int64_t c1, Emit &emit) {
+    double beta[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) beta[j] = NAN;
+    if (rs.all_nan) {
+        for (int64_t r = c0; r < c1; ++r) emit(r, beta, true);
+        return;
+    }
+    const int64_t W = cfg.window;
+    const int64_t first = g0 + rs.mpv - 1;  // first row that carries coefficients
+    int64_t r = c0;
+    for (; r < c1 && r < first; ++r) emit(r, beta, true);
+    if (r >= c1) return;
+
+    NormalState<K> st;
+    st.clear();
+    double x[K], y, xo[K], yo;
+
+    if (!cfg.fixed_window) {
+        // ---- branch 0: window = last W VALID rows (src/least_squares.rs:947-986) -------------------
+        // state entering row r = Gram over the last W valid rows strictly before r (all valid rows
+        // before r while fewer than W have been seen).  `tail` = oldest row inside the window.
+        int64_t cnt = 0, tail = r;
+        if (r == first) {
+            // warm-up (:909-921): valid rows of [g0, g0+mpv) — row `first` itself included
+            for (int64_t i = g0; i <= first; ++i)
+                if (src.valid(i)) {
+                    src.load(i, x, y);
+                    st.add(x, y, 1.0);
+                    if (cnt == 0) tail = i;
+                    ++cnt;
+                }
+            if (cnt == 0) tail = first + 1;
+            if (cfg.alpha > 0.0) st.add_diag(cfg.alpha);
+            solve_normal<K>(st, beta);
+            emit(r, beta, false);
+            ++r;
+        } else {
+            for (int64_t i = r - 1; i >= g0 && cnt < W; --i)
+                if (src.valid(i)) {
+                    src.load(i, x, y);
+                    st.add(x, y, 1.0);
+                    tail = i;
+                    ++cnt;
+                }
+            if (cfg.alpha > 0.0) st.add_diag(cfg.alpha);
+            solve_normal<K>(st, beta);  // coefficients carried into the chunk (forward fill source)
+        }
+        for (; r < c1; ++r) {
+            if (src.valid(r)) {
+                src.load(r, x, y);
+                if (cnt == W) {  // saturated: drop the oldest valid row
+                    src.load(tail, xo, yo);
+                    st.add(x, y, 1.0);
+                    st.add(xo, yo, -1.0);
+                    do { ++tail; } while (!src.valid(tail));  // terminates at r at the latest
+                } else {
+                    st.add(x, y, 1.0);
+                    if (cnt == 0) tail = r;
+                    ++cnt;
+                }
+                solve_normal<K>(st, beta);
+            }
+            emit(r, beta, false);
+        }
+        return;
+    }
+
+    // ---- branch 1: fixed row window (src/least_squares.rs:987-1029) ---------------------------------
+    // series-relative index i = r - g0.  State after processing row i:
+    //   S = alpha I + Gram(valid rows in (i-W, i])  [+ valid rows < mpv-W that the reference never
+    //   subtracts when the warm-up is longer than the window]
+    //   cnt_i = #valid in [max(i-W,0)+1, i]   (index 0 is excluded while i < W: quirk at :990-997)
+    const int64_t mpv = rs.mpv;
+    auto valid_rel = [&](int64_t i) { return src.valid(g0 + i); };
+    int64_t i = r - g0;
+    int64_t cnt = 0;
+    if (r == first) {
+        for (int64_t t = 0; t < mpv; ++t)
+            if (valid_rel(t)) {
+                src.load(g0 + t, x, y);
+                st.add(x, y, 1.0);
+            }
+        if (cfg.alpha > 0.0) st.add_diag(cfg.alpha);
+        solve_normal<K>(st, beta);
+        emit(r, beta, false);
+        // cnt after row mpv-1 under the reference's sliding definition
+        {
+            const int64_t ii = mpv - 1, lo = ((ii >= W) ? ii - W : 0) + 1;
+            for (int64_t t = lo; t <= ii; ++t) cnt += valid_rel(t) ? 1 : 0;
+        }
+        ++r;
+        ++i;
+    } else {
+        // rebuild the state after row i-1 and the coefficients carried into the chunk
+        const int64_t ip = i - 1;
+        auto build = [&](int64_t at, NormalState<K> &s) {
+            s.clear();
+            // rows of the warm-up [0, mpv) are all present until they are subtracted at step t+W (t+W >= mpv);
+            // rows >= mpv are present from their own step.  Row t is subtracted at step t+W iff t+W >= mpv.
+            const int64_t lo = (at - W + 1 > 0) ? at - W + 1 : 0;
+            for (int64_t t = lo; t <= at; ++t)
+                if (valid_rel(t)) {
+                    src.load(g0 + t, x, y);
+                    s.add(x, y, 1.0);
+                }
+            // never-subtracted warm-up rows: t + W < mpv  and t < lo
+            const int64_t stuck_hi = (mpv - W < lo) ? mpv - W : lo;
+            for (int64_t t = 0; t < stuck_hi; ++t)
+                if (valid_rel(t)) {
+                    src.load(g0 + t, x, y);
+                    s.add(x, y, 1.0);
+                }
+            if (cfg.alpha > 0.0) s.add_diag(cfg.alpha);
+        };
+        {
+            const int64_t lo = ((ip >= W) ? ip - W : 0) + 1;
+            for (int64_t t = lo; t <= ip; ++t) cnt += valid_rel(t) ? 1 : 0;
+        }
+        // walk back to the last row whose coefficients were refreshed
+        int64_t j = ip, cj = cnt;
+        bool found = false;
+        while (j >= mpv) {
+            const bool vi = valid_rel(j);
+            const bool vs = (j >= W) && valid_rel(j - W);
+            const bool changed = vi || vs;
+            if (changed && cj >= rs.n_valid) {
+                found = true;
+                break;
+            }
+            // cnt_{j-1} = cnt_j - valid[j] + (j > W ? valid[j-W] : 0)
+            cj = cj - (vi ? 1 : 0) + ((j > W && valid_rel(j - W)) ? 1 : 0);
+            --j;
+        }
+        if (found) {
+            NormalState<K> sj;
+            build(j, sj);
+            solve_normal<K>(sj, beta);
+        } else {
+            // nothing refreshed since the warm-up: carry the warm-up coefficients
+            NormalState<K> sw;
+            sw.clear();
+            for (int64_t t = 0; t < mpv; ++t)
+                if (valid_rel(t)) {
+                    src.load(g0 + t, x, y);
+                    sw.add(x, y, 1.0);
+                }
+            if (cfg.alpha > 0.0) sw.add_diag(cfg.alpha);
+            solve_normal<K>(sw, beta);
+        }
+        build(ip, st);
+    }
+    for (; r < c1; ++r, ++i) {
+        const bool vi = valid_rel(i);
+        const bool sat = i >= W;
+        const bool vs = sat && valid_rel(i - W);
+        cnt += (vi ? 1 : 0) - ((i > W && valid_rel(i - W)) ? 1 : 0);
+        if (vi) {
+            src.load(r, x, y);
+            st.add(x, y, 1.0);
+            if (vs) {
+                src.load(r - W, xo, yo);
+                st.add(xo, yo, -1.0);
+            }
+            if (cnt >= rs.n_valid) solve_normal<K>(st, beta);
+        } else if (vs) {
+            src.load(r - W, xo, yo);
+            st.add(xo, yo, -1.0);
+            if (cnt >= rs.n_valid) solve_normal<K>(st, beta);
+        }
+        emit(r, beta, false);
+    }
+}
+
+// ---- recursive least squares -----------------------------------------------------------------------
+struct RlsCfg {
+    double lambda;  // forgetting factor (src/least_squares.rs:513-517)
+    double p0;      // initial_state_covariance
+};
+
+// chunk summary in information form: after the chunk, (A, b)_out = D (A, b)_in + (A_c, b_c)
+template <int K>
+struct RlsSummary {
+    NormalState<K> ab;
+    double D;
+};
+
+template <int K, typename Src>
+B200_HD void rls_summarise(const Src &src, const RlsCfg &cfg, int64_t c0, int64_t c1, RlsSummary<K> &out) {
+    out.ab.clear();
+    out.D = 1.0;
+    double x[K], y;
+    for (int64_t r = c0; r < c1; ++r)
+        if (src.valid(r)) {
+            src.load(r, x, y);
+            out.ab.decay(cfg.lambda);
+            out.ab.add(x, y, 1.0);
+            out.D *= cfg.lambda;
+        }
+}
+
+// One covariance-form update (src/least_squares.rs:531-540), operation order as in the reference.
+template <int K>
+B200_HD void rls_update(double (&P)[K][K], double (&theta)[K], const double (&x)[K], double y, double lam) {
+    double xp[K], px[K], kg[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) s = fma(x[i], P[i][j], s);
+        xp[j] = s;
+    }
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) q = fma(xp[j], x[j], q);
+    const double r = 1.0 + q / lam;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) s = fma(P[i][j], x[j], s);
+        px[i] = s;
+    }
+    const double rl = r * lam;
+#pragma unroll
+    for (int i = 0; i < K; ++i) kg[i] = px[i] / rl;
+    double pred = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) pred = fma(x[j], theta[j], pred);
+    const double resid = y - pred;
+#pragma unroll
+    for (int j = 0; j < K; ++j) theta[j] = fma(kg[j], resid, theta[j]);
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) P[i][j] = P[i][j] / lam - (kg[i] * kg[j]) * r;
+}
+
+// Runs rows [c0, c1).  `first_chunk`: the series starts here -> P = p0 I, theta = theta0 exactly as the
+// reference.  Otherwise (A_in, b_in) is the information state entering the chunk (prior included).
+template <int K, typename Src, typename Emit>
+B200_HD void rls_chunk(const Src &src, const RlsCfg &cfg, bool first_chunk, const double *theta0,
+                       const NormalState<K> *in, int64_t c0, int64_t c1, Emit &emit) {
+    double P[K][K], theta[K];
+    if (first_chunk) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            theta[i] = theta0 ? theta0[i] : 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) P[i][j] = (i == j) ? cfg.p0 : 0.0;
+        }
+    } else {
+        // P = A^-1 column by column, theta = A^-1 b  (A is SPD: prior I/p0 plus PSD terms)
+        NormalState<K> t = *in;
+        solve_normal<K>(t, theta);
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+            double col[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) t.v[i] = (i == c) ? 1.0 : 0.0;
+            solve_normal<K>(t, col);
+#pragma unroll
+            for (int i = 0; i < K; ++i) P[i][c] = col[i];
+        }
+    }
+    double x[K], y;
+    for (int64_t r = c0; r < c1; ++r) {
+        if (src.valid(r)) {
+            src.load(r, x, y);
+            rls_update<K>(P, theta, x, y, cfg.lambda);
+        }
+        emit(r, theta, false);
+    }
+}
+
+}  // namespace b200

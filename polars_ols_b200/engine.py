@@ -1,0 +1,297 @@
+"""Python handle on a ``b200ols_ctx`` + marshalling of columns into the C-ABI frame descriptor.
+
+Mirrors what ``src/expressions.rs`` does between polars Series and the solvers (cast, validity,
+grouping) — but only describes the buffers; no arithmetic happens on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # torch is plumbing (device tensors / streams), not required for host frames
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+@dataclass
+class Col:
+    """One input column: values buffer (numpy array or CUDA torch tensor) + optional Arrow validity bitmap."""
+    values: object
+    validity: object = None  # np.uint8 bitmap (host) / torch.uint8 tensor (device) / None
+
+    @property
+    def is_device(self) -> bool:
+        return _is_torch(self.values) and self.values.is_cuda
+
+    def __len__(self):
+        return int(self.values.shape[0])
+
+
+def _bitmap_from_bool(mask: np.ndarray) -> Optional[np.ndarray]:
+    mask = np.asarray(mask, dtype=bool)
+    if mask.all():
+        return None
+    return np.packbits(mask, bitorder="little")
+
+
+def as_col(x) -> Col:
+    """numpy array | (values, bool mask) | numpy masked array | pyarrow Array | torch tensor -> Col."""
+    if isinstance(x, Col):
+        return x
+    if _is_torch(x):
+        if x.is_cuda:
+            t = x if x.dtype in (torch.float32, torch.float64) else x.to(torch.float64)
+            return Col(t.contiguous())
+        x = x.numpy()
+    if isinstance(x, tuple) and len(x) == 2:
+        v, m = x
+        c = as_col(v)
+        if m is not None:
+            c = Col(c.values, _bitmap_from_bool(m))
+        return c
+    if isinstance(x, np.ma.MaskedArray):
+        return Col(_float_array(np.ma.getdata(x)), _bitmap_from_bool(~np.ma.getmaskarray(x)))
+    try:
+        import pyarrow as pa
+        if isinstance(x, pa.ChunkedArray):
+            x = x.combine_chunks()
+        if isinstance(x, pa.Array):
+            if not (pa.types.is_floating(x.type) and x.type.bit_width in (32, 64)):
+                x = x.cast(pa.float64())
+            bufs = x.buffers()
+            dt = np.float32 if x.type.bit_width == 32 else np.float64
+            vals = np.frombuffer(bufs[1], dtype=dt, count=len(x) + x.offset)[x.offset:]
+            validity = None
+            if x.null_count > 0:
+                if x.offset == 0:
+                    validity = np.frombuffer(bufs[0], dtype=np.uint8, count=(len(x) + 7) // 8)
+                else:
+                    validity = _bitmap_from_bool(np.asarray(x.is_valid()))
+            return Col(vals, validity)
+    except ImportError:  # pragma: no cover
+        pass
+    return Col(_float_array(np.asarray(x)))
+
+
+def _float_array(a: np.ndarray) -> np.ndarray:
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)  # cast(&DataType::Float64), src/expressions.rs:33,47,80
+    return np.ascontiguousarray(a)
+
+
+@dataclass
+class Batch:
+    """All inputs of one `.over()` evaluation, as the C ABI wants them."""
+    target: Col
+    features: List[Col]
+    weights: Optional[Col] = None
+    add_intercept: bool = False
+    offsets: Optional[np.ndarray] = None    # int64 [G+1], host
+    row_index: object = None                # int64 [N] (numpy or CUDA tensor) or None
+    n_groups: int = 1
+
+    def harmonise(self) -> Tuple[int, int]:
+        """common dtype (polars supertype) + common memory space; returns (dtype, memspace)."""
+        cols = [self.target, *self.features] + ([self.weights] if self.weights is not None else [])
+        dev = [c.is_device for c in cols]
+        if any(dev) and not all(dev):
+            raise ValueError("all columns of a frame must live in the same memory space (host or CUDA)")
+        n = len(self.target)
+        for c in cols:
+            if len(c) != n:
+                raise ValueError("all input series passed must be of equal length")  # src/expressions.rs:96-100
+        if all(dev):
+            f32 = all(c.values.dtype == torch.float32 for c in cols)
+            want = torch.float32 if f32 else torch.float64
+            for c in cols:
+                if c.values.dtype != want:
+                    c.values = c.values.to(want)
+            return (L.F32 if f32 else L.F64), L.DEVICE
+        f32 = all(c.values.dtype == np.float32 for c in cols)
+        want = np.float32 if f32 else np.float64
+        for c in cols:
+            if c.values.dtype != want or not c.values.flags.c_contiguous:
+                c.values = np.ascontiguousarray(c.values, dtype=want)
+        return (L.F32 if f32 else L.F64), L.HOST
+
+
+def _ptr(x) -> Optional[int]:
+    if x is None:
+        return None
+    if _is_torch(x):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class Engine:
+    """One ``b200ols_ctx``: a device, a stream, and the engine's device scratch."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = L.load()
+        self._ctx = C.c_void_p()
+        if stream is None:
+            L.check(self._lib.b200ols_create(device, C.byref(self._ctx)))
+        else:
+            L.check(self._lib.b200ols_create_on_stream(device, C.c_void_p(stream), C.byref(self._ctx)))
+        self.device = device
+
+    def close(self):
+        if self._ctx:
+            self._lib.b200ols_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- misc ---------------------------------------------------------------------------------------
+    def synchronize(self):
+        L.check(self._lib.b200ols_synchronize(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.b200ols_launch_count(self._ctx))
+
+    def set_tuning(self, tile_rows: int = 0, warps_per_cta: int = 0, ctas_per_sm: int = 0):
+        L.check(self._lib.b200ols_set_tuning(self._ctx, tile_rows, warps_per_cta, ctas_per_sm))
+
+    def last_group_flags(self, n_groups: int) -> np.ndarray:
+        out = np.empty(n_groups, dtype=np.int32)
+        L.check(self._lib.b200ols_last_group_flags(self._ctx, out.ctypes.data, n_groups))
+        return out
+
+    def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
+        """numpy array over page-locked host memory (freed with the process); for per-call uploads."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self._lib.b200ols_host_alloc(max(n, 1))
+        if not p:
+            raise L.B200OLSError(L.ERR_CUDA, self._lib.b200ols_last_error().decode())
+        buf = (C.c_char * max(n, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    # -- frame marshalling ----------------------------------------------------------------------------
+    def _frame(self, b: Batch):
+        dtype, memspace = b.harmonise()
+        n = len(b.target)
+        keep = []
+        feats = (L.Column * max(len(b.features), 1))()
+        for j, c in enumerate(b.features):
+            feats[j].values = _ptr(c.values)
+            feats[j].validity = _ptr(c.validity)
+        fr = L.Frame()
+        fr.n_rows = n
+        fr.n_features = len(b.features)
+        fr.dtype = dtype
+        fr.memspace = memspace
+        fr.add_intercept = 1 if b.add_intercept else 0
+        fr.target.values = _ptr(b.target.values)
+        fr.target.validity = _ptr(b.target.validity)
+        fr.features = feats
+        wcol = None
+        if b.weights is not None:
+            wcol = L.Column(_ptr(b.weights.values), _ptr(b.weights.validity))
+            fr.sample_weights = C.pointer(wcol)
+        offs = None
+        if b.offsets is not None:
+            offs = np.ascontiguousarray(b.offsets, dtype=np.int64)
+            fr.n_groups = len(offs) - 1
+            fr.group_offsets = offs.ctypes.data
+        else:
+            fr.n_groups = 1
+        ridx = b.row_index
+        if ridx is not None:
+            if memspace == L.DEVICE:
+                if not _is_torch(ridx):
+                    ridx = torch.as_tensor(np.ascontiguousarray(ridx, dtype=np.int64), device=b.target.values.device)
+                ridx = ridx.to(torch.int64).contiguous()
+            else:
+                ridx = np.ascontiguousarray(ridx, dtype=np.int64)
+            fr.row_index = _ptr(ridx)
+        keep += [feats, wcol, offs, ridx, b]
+        return fr, keep, dtype, memspace, n, int(fr.n_groups)
+
+    def _alloc_out(self, memspace, shape, want_validity, like):
+        if memspace == L.DEVICE:
+            v = torch.empty(shape, dtype=torch.float64, device=like.device)
+            m = torch.empty(shape, dtype=torch.uint8, device=like.device) if want_validity else None
+        else:
+            v = np.empty(shape, dtype=np.float64)
+            m = np.empty(shape, dtype=np.uint8) if want_validity else None
+        out = L.Output(_ptr(v), _ptr(m))
+        return out, v, m
+
+    # -- the six entry points ---------------------------------------------------------------------------
+    def least_squares(self, b: Batch, kw: L.OLSKwargs, mode: int, want_validity: bool = True, out=None):
+        fr, keep, dtype, memspace, n, G = self._frame(b)
+        F = len(b.features) + (1 if b.add_intercept else 0)
+        shape = (G, F) if mode == L.COEFFICIENTS else (n,)
+        if out is None:
+            o, v, m = self._alloc_out(memspace, shape, want_validity and mode != L.COEFFICIENTS, b.target.values)
+        else:
+            v, m = out
+            o = L.Output(_ptr(v), _ptr(m))
+        if mode == L.COEFFICIENTS:
+            L.check(self._lib.b200ols_least_squares_coefficients(self._ctx, C.byref(fr), C.byref(kw), C.byref(o)))
+        else:
+            L.check(self._lib.b200ols_least_squares(self._ctx, C.byref(fr), C.byref(kw), mode, C.byref(o)))
+        del keep
+        return v, m
+
+    def recursive_least_squares(self, b: Batch, kw: L.RLSKwargs, mode: int, mean_keepalive=None):
+        fr, keep, dtype, memspace, n, G = self._frame(b)
+        F = len(b.features) + (1 if b.add_intercept else 0)
+        shape = (n, F) if mode == L.COEFFICIENTS else (n,)
+        o, v, m = self._alloc_out(memspace, shape, True, b.target.values)
+        if mode == L.COEFFICIENTS:
+            L.check(self._lib.b200ols_recursive_least_squares_coefficients(self._ctx, C.byref(fr), C.byref(kw), C.byref(o)))
+        else:
+            L.check(self._lib.b200ols_recursive_least_squares(self._ctx, C.byref(fr), C.byref(kw), mode, C.byref(o)))
+        del keep, mean_keepalive
+        return v, m
+
+    def rolling_least_squares(self, b: Batch, kw: L.RollingKwargs, mode: int):
+        fr, keep, dtype, memspace, n, G = self._frame(b)
+        F = len(b.features) + (1 if b.add_intercept else 0)
+        shape = (n, F) if mode == L.COEFFICIENTS else (n,)
+        o, v, m = self._alloc_out(memspace, shape, True, b.target.values)
+        if mode == L.COEFFICIENTS:
+            L.check(self._lib.b200ols_rolling_least_squares_coefficients(self._ctx, C.byref(fr), C.byref(kw), C.byref(o)))
+        else:
+            L.check(self._lib.b200ols_rolling_least_squares(self._ctx, C.byref(fr), C.byref(kw), mode, C.byref(o)))
+        del keep
+        return v, m
+
+
+_engines = {}
+
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle of the (legacy) default stream
+
+
+def get_engine(device: int = 0, torch_stream: bool = False) -> Engine:
+    """process-wide default engines.  Host frames use the engine's own stream; frames of CUDA torch tensors
+    run on torch's current stream so that they are ordered with the producer of those tensors."""
+    stream = None
+    if torch_stream and torch is not None:
+        stream = torch.cuda.current_stream(device).cuda_stream or CUDA_STREAM_LEGACY
+    key = (device, stream)
+    e = _engines.get(key)
+    if e is None:
+        e = _engines[key] = Engine(device, stream)
+    return e
+
+
+def nan_or(x: Optional[float]) -> float:
+    return math.nan if x is None else float(x)

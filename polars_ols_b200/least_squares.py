@@ -1,0 +1,389 @@
+"""Host-side mirror of ``polars_ols/least_squares.py`` + ``polars_ols/__init__.py`` of the reference.
+
+Same names, argument meaning, defaults and error behaviour:
+``OLSKwargs / RLSKwargs / RollingKwargs`` (reference ``polars_ols/least_squares.py:66-160``),
+``compute_least_squares / compute_recursive_least_squares / compute_rolling_least_squares`` (``:242-409``)
+and the ``least_squares`` expression namespace ``LeastSquares`` (``polars_ols/__init__.py:35-295``:
+``ols, wls, ridge, lasso, elastic_net, rls, rolling_ols, expanding_ols, least_squares``).
+
+polars is not available in this image, so expressions are evaluated against a minimal ``Frame``
+(dict of numpy arrays / pyarrow arrays / CUDA torch tensors) instead of a ``pl.DataFrame``:
+
+    df = Frame({"y": y, "x1": x1, "x2": x2, "group": g})
+    out = df.select(col("y").least_squares.ridge(col("x1"), col("x2"), alpha=1e-3, mode="coefficients").over("group"))
+
+What differs from the reference by design: `.over()` is evaluated as ONE batched call into the CUDA
+engine (all groups at once) instead of one plugin call per group, and the WLS pre/post-processing
+(``_pre_process_data`` / ``predictions *= 1/sqrt_w`` / ``target - predictions``, reference
+``polars_ols/least_squares.py:163-239``) is fused into the kernels rather than run as extra column passes.
+There is no CPU path: without a CUDA device evaluation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+from dataclasses import asdict, dataclass
+from typing import Any, Dict, List, Literal, Optional, Sequence, Set, Union, get_args
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Batch, Col, Engine, as_col, get_engine, nan_or, _is_torch
+
+logger = logging.getLogger(__name__)
+
+__all__ = [
+    "compute_least_squares", "compute_recursive_least_squares", "compute_rolling_least_squares",
+    "OLSKwargs", "RLSKwargs", "RollingKwargs", "NullPolicy", "OutputMode", "SolveMethod",
+    "LeastSquares", "Frame", "col", "Expr", "Result",
+]
+
+NullPolicy = Literal["zero", "drop", "ignore", "drop_zero", "drop_y_zero_x", "drop_window"]
+OutputMode = Literal["predictions", "residuals", "coefficients", "statistics"]
+SolveMethod = Literal["qr", "svd", "chol", "lu", "cd", "cd_active_set"]
+
+_VALID_NULL_POLICIES: Set[str] = set(get_args(NullPolicy))
+_VALID_OUTPUT_MODES: Set[str] = set(get_args(OutputMode))
+_VALID_SOLVE_METHODS: Set[Optional[str]] = set(get_args(SolveMethod)).union({None})
+
+
+# ------------------------------------------------------------------------------------------------
+# kwargs dataclasses — field for field the reference's (polars_ols/least_squares.py:66-160)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Kwargs:
+    null_policy: NullPolicy = "ignore"
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+    def __post_init__(self):
+        assert (
+            self.null_policy in _VALID_NULL_POLICIES
+        ), f"'null_policy' must be one of {_VALID_NULL_POLICIES}. You passed: {self.null_policy}"
+
+
+@dataclass
+class OLSKwargs(Kwargs):
+    alpha: Optional[float] = 0.0
+    l1_ratio: Optional[float] = None
+    max_iter: Optional[int] = 1_000
+    tol: Optional[float] = 1.0e-5
+    positive: Optional[bool] = False
+    solve_method: Optional[SolveMethod] = None
+    rcond: Optional[float] = None
+
+    def __post_init__(self):
+        valid_ols_policies = _VALID_NULL_POLICIES - {"drop_window"}
+        assert (
+            self.null_policy in valid_ols_policies
+        ), f"'null_policy' must be one of {valid_ols_policies}. You passed: {self.null_policy}"
+        assert (
+            self.solve_method in _VALID_SOLVE_METHODS
+        ), f"'solve_method' must be one of {_VALID_SOLVE_METHODS}. You passed: {self.solve_method}"
+
+    def to_c(self) -> L.OLSKwargs:
+        return L.OLSKwargs(nan_or(self.alpha), nan_or(self.l1_ratio), -1 if self.max_iter is None else int(self.max_iter),
+                           nan_or(self.tol), 1 if self.positive else 0, L.SOLVE_METHOD[self.solve_method],
+                           L.NULL_POLICY[self.null_policy], 0, nan_or(self.rcond))
+
+
+@dataclass
+class RLSKwargs(Kwargs):
+    half_life: Optional[float] = None
+    initial_state_covariance: Optional[float] = 10.0
+    initial_state_mean: Union[Optional[List[float]], float] = None
+    null_policy: NullPolicy = "drop"
+
+
+@dataclass
+class RollingKwargs(Kwargs):
+    window_size: int = 1_000_000
+    min_periods: Optional[int] = None
+    use_woodbury: Optional[bool] = None
+    alpha: Optional[float] = None
+    null_policy: NullPolicy = "drop_window"
+
+    def to_c(self) -> L.RollingKwargs:
+        return L.RollingKwargs(int(self.window_size), -1 if self.min_periods is None else int(self.min_periods),
+                               -1 if self.use_woodbury is None else int(bool(self.use_woodbury)),
+                               L.NULL_POLICY[self.null_policy], nan_or(self.alpha))
+
+
+# ------------------------------------------------------------------------------------------------
+# results
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Result:
+    """Output of one expression.  ``values`` is f64; ``valid`` (uint8, same shape, or None = all valid)
+    marks polars nulls.  Static coefficients carry one row per group (``keys``) plus the row->group map
+    needed to broadcast them the way ``.over()`` does."""
+    name: str
+    values: Any
+    valid: Any = None
+    fields: Optional[List[str]] = None      # coefficient struct field names
+    keys: Optional[np.ndarray] = None       # group keys (per-group results)
+    group_of_row: Optional[np.ndarray] = None
+
+    def to_numpy(self, broadcast: bool = False) -> np.ndarray:
+        v = self.values.cpu().numpy() if _is_torch(self.values) else np.asarray(self.values)
+        v = v.copy()
+        if self.valid is not None:
+            m = self.valid.cpu().numpy() if _is_torch(self.valid) else np.asarray(self.valid)
+            v[m == 0] = np.nan
+        elif self.fields is not None:
+            pass  # coefficient NaN <=> null already
+        if broadcast and self.group_of_row is not None:
+            v = v[self.group_of_row]
+        return v
+
+    def is_null(self) -> np.ndarray:
+        if self.valid is not None:
+            m = self.valid.cpu().numpy() if _is_torch(self.valid) else np.asarray(self.valid)
+            return m == 0
+        v = self.to_numpy()
+        return np.isnan(v) if self.fields is not None else np.zeros(v.shape, dtype=bool)
+
+
+# ------------------------------------------------------------------------------------------------
+# grouping: polars' `.over()` / group_by split (reference: 3rd-party polars engine)
+# ------------------------------------------------------------------------------------------------
+def _group_plan(keys: Sequence[np.ndarray]):
+    """keys -> (unique keys, offsets [G+1], row_index [N] or None if groups are contiguous slices,
+    group_of_row [N])."""
+    if len(keys) == 1:
+        k = np.asarray(keys[0])
+        uniq, inv = np.unique(k, return_inverse=True)
+    else:
+        stacked = np.rec.fromarrays([np.asarray(k) for k in keys])
+        uniq, inv = np.unique(stacked, return_inverse=True)
+    inv = inv.reshape(-1)
+    counts = np.bincount(inv, minlength=len(uniq))
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    if len(inv) == 0 or np.all(inv[1:] >= inv[:-1]):
+        return uniq, offsets, None, inv           # already sorted & contiguous: GroupsSlice
+    order = np.argsort(inv, kind="stable").astype(np.int64)  # row order inside a group is preserved
+    return uniq, offsets, order, inv
+
+
+# ------------------------------------------------------------------------------------------------
+# expressions
+# ------------------------------------------------------------------------------------------------
+class Expr:
+    """A column reference (``col("x")``) or a literal buffer."""
+
+    def __init__(self, name: Optional[str] = None, data=None):
+        self._name = name
+        self._data = data
+
+    @property
+    def output_name(self) -> str:
+        return self._name or ""
+
+    def resolve(self, frame: "Frame") -> Col:
+        if self._data is not None:
+            return as_col(self._data)
+        return as_col(frame[self._name])
+
+    @property
+    def least_squares(self) -> "LeastSquares":
+        return LeastSquares(self)
+
+
+def col(name: str) -> Expr:
+    return Expr(name)
+
+
+ExprOrStr = Union[Expr, str, Any]
+
+
+def parse_into_expr(e: ExprOrStr) -> Expr:
+    """reference polars_ols/utils.py:21-58: strings are column names."""
+    if isinstance(e, Expr):
+        return e
+    if isinstance(e, str):
+        return Expr(e)
+    return Expr(None, e)
+
+
+class LsExpr:
+    """A pending least-squares expression (what ``register_plugin_function`` returns in the reference)."""
+
+    def __init__(self, kind: str, target: Expr, features: List[Expr], sample_weights: Optional[Expr],
+                 add_intercept: bool, mode: str, kwargs: Kwargs):
+        self.kind = kind
+        self.target, self.features, self.sample_weights = target, features, sample_weights
+        self.add_intercept, self.mode, self.kwargs = add_intercept, mode, kwargs
+        self._over: List[ExprOrStr] = []
+        self._alias: Optional[str] = None
+        self._per_group = False
+
+    def over(self, *keys: ExprOrStr) -> "LsExpr":
+        self._over = list(keys)
+        return self
+
+    def alias(self, name: str) -> "LsExpr":
+        self._alias = name
+        return self
+
+    @property
+    def output_name(self) -> str:
+        if self._alias:
+            return self._alias
+        # reference: coefficients / statistics are aliased to the mode (least_squares.py:224);
+        # predictions keep the target's name (src/expressions.rs:404)
+        return self.mode if self.mode == "coefficients" else self.target.output_name or self.mode
+
+    # -- evaluation ----------------------------------------------------------------------------------
+    def evaluate(self, frame: "Frame", engine: Optional[Engine] = None) -> Result:
+        target = self.target.resolve(frame)
+        feats = [f.resolve(frame) for f in self.features]
+        names = [f.output_name or str(i) for i, f in enumerate(self.features)]  # src/expressions.rs:126-130
+        add_intercept = self.add_intercept
+        if add_intercept and any(n == "const" for n in names):
+            logger.info("feature named 'const' already detected, assuming it is an intercept")  # least_squares.py:185-186
+            add_intercept = False
+        if add_intercept:
+            names = names + ["const"]
+        weights = self.sample_weights.resolve(frame) if self.sample_weights is not None else None
+        b = Batch(target, feats, weights, add_intercept)
+        keys = group_of_row = None
+        if self._over:
+            key_arrays = []
+            for k in self._over:
+                kv = frame[k] if isinstance(k, str) else parse_into_expr(k).resolve(frame).values
+                if _is_torch(kv):
+                    kv = kv.cpu().numpy()
+                key_arrays.append(np.asarray(kv))
+            keys, offsets, row_index, group_of_row = _group_plan(key_arrays)
+            b.offsets, b.row_index = offsets, row_index
+        if engine is None:
+            dev = target.values.device.index if target.is_device else 0
+            engine = get_engine(dev or 0, torch_stream=target.is_device)
+        mode = L.MODE[self.mode]
+        if self.kind == "least_squares":
+            v, m = engine.least_squares(b, self.kwargs.to_c(), mode)
+            if self.mode == "coefficients":
+                return Result(self.output_name, v, None, names, keys, group_of_row)
+            return Result(self.output_name, v, m)
+        if self.kind == "recursive_least_squares":
+            kw: RLSKwargs = self.kwargs
+            mean = kw.initial_state_mean
+            n_coef = len(names)
+            mean_arr = None
+            if mean is not None:
+                mean_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(mean, dtype=np.float64), (n_coef,)))
+            ckw = L.RLSKwargs(nan_or(kw.half_life), nan_or(kw.initial_state_covariance),
+                              None if mean_arr is None else mean_arr.ctypes.data, L.NULL_POLICY[kw.null_policy], 0)
+            v, m = engine.recursive_least_squares(b, ckw, mode, mean_arr)
+        else:
+            v, m = engine.rolling_least_squares(b, self.kwargs.to_c(), mode)
+        if self.mode == "coefficients":
+            return Result(self.output_name, v, m, names)
+        return Result(self.output_name, v, m)
+
+
+class Frame(dict):
+    """Minimal stand-in for ``pl.DataFrame``: a dict of equal-length columns (numpy arrays, pyarrow arrays,
+    ``(values, valid_mask)`` pairs, numpy masked arrays or CUDA torch tensors)."""
+
+    def select(self, *exprs: LsExpr, engine: Optional[Engine] = None) -> Dict[str, Result]:
+        out: Dict[str, Result] = {}
+        for e in exprs:
+            out[e.output_name] = e.evaluate(self, engine)
+        return out
+
+    def with_columns(self, *exprs: LsExpr, engine: Optional[Engine] = None) -> "Frame":
+        new = Frame(self)
+        for e in exprs:
+            r = e.evaluate(self, engine)
+            new[e.output_name] = r.to_numpy(broadcast=True)
+        return new
+
+
+# ------------------------------------------------------------------------------------------------
+# compute_* functions (reference polars_ols/least_squares.py:242-409)
+# ------------------------------------------------------------------------------------------------
+def _make(kind, target, features, sample_weights, add_intercept, mode, kwargs) -> LsExpr:
+    return LsExpr(kind, parse_into_expr(target), [parse_into_expr(f) for f in features],
+                  None if sample_weights is None else parse_into_expr(sample_weights), add_intercept, mode, kwargs)
+
+
+def compute_least_squares(target: ExprOrStr, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None,
+                          add_intercept: bool = False, mode: OutputMode = "predictions",
+                          ols_kwargs: Optional[OLSKwargs] = None) -> LsExpr:
+    assert mode in _VALID_OUTPUT_MODES, f"'mode' must be one of {_VALID_OUTPUT_MODES}"
+    if mode == "statistics":
+        raise NotImplementedError("mode='statistics' is outside the accelerated hot path (SURVEY.md §8)")
+    return _make("least_squares", target, features, sample_weights, add_intercept, mode, ols_kwargs or OLSKwargs())
+
+
+def compute_recursive_least_squares(target: ExprOrStr, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None,
+                                    add_intercept: bool = False, mode: OutputMode = "predictions",
+                                    rls_kwargs: Optional[RLSKwargs] = None) -> LsExpr:
+    valid_output_modes = _VALID_OUTPUT_MODES - {"statistics"}
+    assert mode in valid_output_modes, f"'mode' must be one of {valid_output_modes}"
+    return _make("recursive_least_squares", target, features, sample_weights, add_intercept, mode, rls_kwargs or RLSKwargs())
+
+
+def compute_rolling_least_squares(target: ExprOrStr, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None,
+                                  add_intercept: bool = False, mode: OutputMode = "predictions",
+                                  rolling_kwargs: Optional[RollingKwargs] = None) -> LsExpr:
+    valid_output_modes = _VALID_OUTPUT_MODES - {"statistics"}
+    assert mode in valid_output_modes, f"'mode' must be one of {valid_output_modes}"
+    return _make("rolling_least_squares", target, features, sample_weights, add_intercept, mode,
+                 rolling_kwargs or RollingKwargs())
+
+
+# ------------------------------------------------------------------------------------------------
+# the `least_squares` namespace (reference polars_ols/__init__.py:35-295)
+# ------------------------------------------------------------------------------------------------
+class LeastSquares:
+    def __init__(self, expr: Expr):
+        self._expr = expr
+
+    def least_squares(self, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None, add_intercept: bool = False,
+                      mode: OutputMode = "predictions", null_policy: NullPolicy = "ignore",
+                      solve_method: Optional[SolveMethod] = None, multi_target: bool = False, **ols_kwargs) -> LsExpr:
+        if multi_target:
+            raise NotImplementedError("multi_target_ols is a 'next' row of SURVEY.md §8f")
+        return compute_least_squares(self._expr, *features, sample_weights=sample_weights, add_intercept=add_intercept,
+                                     mode=mode,
+                                     ols_kwargs=OLSKwargs(null_policy=null_policy, solve_method=solve_method, **ols_kwargs))
+
+    def ols(self, *features: ExprOrStr, **kwargs) -> LsExpr:
+        return self.least_squares(*features, **kwargs)
+
+    def wls(self, *features: ExprOrStr, sample_weights: ExprOrStr, **kwargs) -> LsExpr:
+        return self.least_squares(*features, sample_weights=sample_weights, **kwargs)
+
+    def ridge(self, *features: ExprOrStr, alpha: float, **kwargs) -> LsExpr:
+        return self.least_squares(*features, alpha=alpha, l1_ratio=0.0, **kwargs)
+
+    def lasso(self, *features: ExprOrStr, alpha: float, **kwargs) -> LsExpr:
+        return self.least_squares(*features, alpha=alpha, l1_ratio=1.0, **kwargs)
+
+    def elastic_net(self, *features: ExprOrStr, alpha: float, l1_ratio: float = 0.5, positive: bool = False, **kwargs) -> LsExpr:
+        return self.least_squares(*features, alpha=alpha, l1_ratio=l1_ratio, positive=positive, **kwargs)
+
+    def rls(self, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None, add_intercept: bool = False,
+            mode: OutputMode = "predictions", null_policy: NullPolicy = "drop", half_life: Optional[float] = None,
+            initial_state_covariance: Optional[float] = 10.0,
+            initial_state_mean: Union[Optional[List[float]], float] = None) -> LsExpr:
+        return compute_recursive_least_squares(
+            self._expr, *features, sample_weights=sample_weights, add_intercept=add_intercept, mode=mode,
+            rls_kwargs=RLSKwargs(null_policy=null_policy, half_life=half_life, initial_state_mean=initial_state_mean,
+                                 initial_state_covariance=initial_state_covariance))
+
+    def rolling_ols(self, *features: ExprOrStr, window_size: int, sample_weights: Optional[ExprOrStr] = None,
+                    add_intercept: bool = False, mode: OutputMode = "predictions", null_policy: NullPolicy = "drop",
+                    min_periods: Optional[int] = None, use_woodbury: Optional[bool] = None,
+                    alpha: Optional[float] = None) -> LsExpr:
+        return compute_rolling_least_squares(
+            self._expr, *features, sample_weights=sample_weights, add_intercept=add_intercept, mode=mode,
+            rolling_kwargs=RollingKwargs(window_size=window_size, min_periods=min_periods, use_woodbury=use_woodbury,
+                                         alpha=alpha, null_policy=null_policy))
+
+    def expanding_ols(self, *features: ExprOrStr, **kwargs) -> LsExpr:
+        return self.rls(*features, half_life=None, **kwargs)
