@@ -168,6 +168,12 @@ B200OLS_API int64_t b200ols_launch_count(const b200ols_ctx *ctx);
 /* page-locked host memory for frames that are uploaded every call (full-speed, async H2D/D2H) */
 B200OLS_API void *b200ols_host_alloc(size_t bytes);
 B200OLS_API void b200ols_host_free(void *p);
+/* Device-side timing of the dominant kernel of each call (the row-streaming Gram kernel for the static
+ * models, the main pass for rls / rolling): when enabled, every such launch is bracketed by CUDA events
+ * on the context's stream.  b200ols_profile_drain synchronises, writes up to `max` durations (ms, oldest
+ * first) and clears the list; returns the number written (or a negative error code). */
+B200OLS_API int b200ols_set_profiling(b200ols_ctx *ctx, int enabled);
+B200OLS_API int b200ols_profile_drain(b200ols_ctx *ctx, float *ms, int max);
 /* tuning knobs (0 = default): rows per shared-memory tile and consumer warps per CTA of the
  * row-streaming Gram kernel */
 B200OLS_API int b200ols_set_tuning(b200ols_ctx *ctx, int tile_rows, int warps_per_cta, int ctas_per_sm);

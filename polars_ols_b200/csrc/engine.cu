@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200ols.h"
@@ -82,6 +83,23 @@ struct b200ols_ctx {
     // diagnostics of the last static call
     int32_t *last_flags = nullptr;  // device pointer inside the arena
     int64_t last_flags_n = 0;
+    // optional device-side timing of the dominant kernel
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+};
+
+struct ProfScope {  // brackets a launch with events when profiling is on
+    b200ols_ctx *c;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit ProfScope(b200ols_ctx *ctx) : c(ctx) {
+        if (c->profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() {
+        if (a && b) {
+            cudaEventRecord(b, c->stream);
+            c->prof.emplace_back(a, b);
+        }
+    }
 };
 
 static int arena_reserve(b200ols_ctx *c, size_t bytes) {
@@ -196,6 +214,27 @@ extern "C" void b200ols_host_free(void *p) {
 }
 
 extern "C" int64_t b200ols_launch_count(const b200ols_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int b200ols_set_profiling(b200ols_ctx *c, int enabled) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    c->profiling = enabled != 0;
+    return 0;
+}
+
+extern "C" int b200ols_profile_drain(b200ols_ctx *c, float *ms, int max) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    CU(cudaStreamSynchronize(c->stream));
+    int n = 0;
+    for (auto &pr : c->prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, pr.first, pr.second);
+        if (ms && n < max) ms[n++] = t;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    c->prof.clear();
+    return n;
+}
 
 extern "C" int b200ols_set_tuning(b200ols_ctx *c, int tile_rows, int warps_per_cta, int ctas_per_sm) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
@@ -518,8 +557,11 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     const int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : 1;
     int64_t grid = std::min<int64_t>(static_cast<int64_t>(c->sm_count) * ctas_per_sm, (gp.nseg + warps - 1) / warps);
     grid = std::max<int64_t>(grid, 1);
-    CU(sizeof(T) == 8 ? gram_launch_f64(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream)
-                      : gram_launch_f32(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream));
+    {
+        ProfScope prof(c);
+        CU(sizeof(T) == 8 ? gram_launch_f64(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream)
+                          : gram_launch_f32(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream));
+    }
     c->launches++;
     return 0;
 }
@@ -909,7 +951,10 @@ static int run_moving(b200ols_ctx *c, const b200ols_frame *f, int kind, const b2
     mp.out_valid = dval;
     char *ws = arena_alloc<char>(c, moving_workspace_bytes(N, G, F));
     ARENA_GUARD(c);
-    TRY(launch_moving(c->stream, mp, st.offsets.data(), f->dtype == B200OLS_F64, c->sm_count, ws, &c->launches));
+    {
+        ProfScope prof(c);
+        TRY(launch_moving(c->stream, mp, st.offsets.data(), f->dtype == B200OLS_F64, c->sm_count, ws, &c->launches));
+    }
     if (f->memspace == B200OLS_HOST) {
         CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * out_elems, cudaMemcpyDeviceToHost, c->stream));
         if (dval) CU(cudaMemcpyAsync(out->validity, dval, out_elems, cudaMemcpyDeviceToHost, c->stream));

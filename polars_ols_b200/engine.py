@@ -168,6 +168,17 @@ class Engine:
     def set_tuning(self, tile_rows: int = 0, warps_per_cta: int = 0, ctas_per_sm: int = 0):
         L.check(self._lib.b200ols_set_tuning(self._ctx, tile_rows, warps_per_cta, ctas_per_sm))
 
+    def set_profiling(self, enabled: bool):
+        L.check(self._lib.b200ols_set_profiling(self._ctx, 1 if enabled else 0))
+
+    def profile_drain(self, max_n: int = 4096) -> np.ndarray:
+        """device durations (ms) of the dominant kernel of every call since the last drain"""
+        buf = np.empty(max_n, dtype=np.float32)
+        n = self._lib.b200ols_profile_drain(self._ctx, buf.ctypes.data, max_n)
+        if n < 0:
+            L.check(n)
+        return buf[:n].copy()
+
     def last_group_flags(self, n_groups: int) -> np.ndarray:
         out = np.empty(n_groups, dtype=np.int32)
         L.check(self._lib.b200ols_last_group_flags(self._ctx, out.ctypes.data, n_groups))
@@ -249,6 +260,22 @@ class Engine:
             L.check(self._lib.b200ols_least_squares(self._ctx, C.byref(fr), C.byref(kw), mode, C.byref(o)))
         del keep
         return v, m
+
+    def prepare_least_squares(self, b: Batch, kw: L.OLSKwargs, mode: int, out_values, out_validity=None):
+        """Marshal once, call many times: returns a zero-argument callable that re-issues the same C-ABI
+        call (same buffers).  Used by steady-state loops (bench.py) to keep Python out of the timed region."""
+        fr, keep, dtype, memspace, n, G = self._frame(b)
+        o = L.Output(_ptr(out_values), _ptr(out_validity))
+        fn = self._lib.b200ols_least_squares_coefficients if mode == L.COEFFICIENTS else None
+        ctx, lib = self._ctx, self._lib
+        frp, kwp, op = C.byref(fr), C.byref(kw), C.byref(o)
+
+        def call(_keep=(keep, fr, kw, o, out_values, out_validity)):
+            rc = fn(ctx, frp, kwp, op) if fn is not None else lib.b200ols_least_squares(ctx, frp, kwp, mode, op)
+            if rc != 0:
+                L.check(rc)
+
+        return call
 
     def recursive_least_squares(self, b: Batch, kw: L.RLSKwargs, mode: int, mean_keepalive=None):
         fr, keep, dtype, memspace, n, G = self._frame(b)

@@ -1,0 +1,328 @@
+"""Parity tests proper (`-m gpu`): the CUDA path, called through the public API -> ctypes -> C ABI of
+libb200ols.so, against the CPU oracle on the same seeded inputs and against the reference's README
+known-answer frame.  Tolerances: 1e-6 relative for f64, 1e-4 for f32 inputs (BASELINE.json north_star).
+The structure follows the reference's tests/test_ols.py (cited per test)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import semantics as S  # noqa: E402  (checker only)
+
+import polars_ols_b200 as pls  # noqa: E402
+from polars_ols_b200 import Frame, OLSKwargs, RLSKwargs, RollingKwargs, col  # noqa: E402
+
+GOLD = json.loads((Path(__file__).parent / "golden" / "readme_frame.json").read_text())
+RTOL, ATOL = 1e-6, 1e-9
+
+
+def _make_data(n_samples=5000, n_features=2, n_groups=None, scale=0.1, sparsity=0.0, add_missing=False, seed=0,
+               dtype=np.float64):
+    """tests/test_ols.py:22-51"""
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n_samples, n_features))
+    eps = rng.normal(size=n_samples, scale=scale)
+    y = x[:, : int(n_features * (1.0 - sparsity))].sum(1) + eps
+    d = {f"x{i + 1}": np.ascontiguousarray(x[:, i]).astype(dtype) for i in range(n_features)}
+    d["y"] = y.astype(dtype)
+    if n_groups is not None:
+        d["group"] = rng.integers(n_groups, size=n_samples)
+    if add_missing:
+        for c in [c for c in d if c != "group"]:
+            d[c] = (d[c], rng.random(n_samples) >= 0.1)
+    return d
+
+
+def _xs(d):
+    return [k for k in d if k.startswith("x")]
+
+
+def _close(got, ref, rtol=RTOL, atol=ATOL):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert (np.isnan(got) == np.isnan(ref)).all(), "null/NaN pattern differs"
+    m = ~np.isnan(ref)
+    if m.any():
+        err = np.abs(got[m] - ref[m]) / (atol / rtol + np.abs(ref[m]))
+        assert err.max() <= rtol, f"max rel err {err.max():.3e}"
+
+
+def _oracle_cols(d, names):
+    return [d[n] for n in names]
+
+
+def _ref(values_mask):
+    v, m = values_mask
+    return np.where(m, v, np.nan) if m is not None else v
+
+
+# ----------------------------------------------------------------------------------- golden frame
+def test_readme_golden_frame():
+    F = Frame({k: np.asarray(v, dtype=np.float64) for k, v in GOLD["frame"].items()})
+    tolc, tolr = GOLD["printed_abs_tol_coefficients"], GOLD["printed_abs_tol_round2"]
+    r = F.select(col("y").least_squares.ols(col("x1"), col("x2"), add_intercept=True, mode="coefficients"))["coefficients"]
+    assert r.fields == ["x1", "x2", "const"]
+    assert np.allclose(r.to_numpy()[0], GOLD["coefficients_ols_intercept"], atol=tolc, rtol=0)
+    r = F.select(col("y").least_squares.ols("x1", "x2", add_intercept=True, mode="coefficients").over("group"))["coefficients"]
+    for i, k in enumerate(r.keys):
+        assert np.allclose(r.to_numpy()[i], GOLD["coefficients_ols_intercept_by_group"][str(int(k))], atol=tolc, rtol=0)
+    assert r.to_numpy(broadcast=True).shape == (10, 3)               # tests/test_ols.py:404-433 shapes
+    r = F.select(col("y").least_squares.rls(col("x1"), col("x2"), mode="coefficients").over("group"))["coefficients"]
+    assert np.allclose(r.to_numpy()[:5], GOLD["coefficients_rls_group1"], atol=tolc, rtol=0)
+    r = F.select(col("y").least_squares.lasso("x1", "x2", alpha=0.0001, add_intercept=True).over("group"))["y"]
+    assert np.allclose(r.to_numpy()[:5], GOLD["predictions_lasso_head5_round2"], atol=tolr, rtol=0)
+    r = F.select(col("y").least_squares.wls("x1", "x2", sample_weights="weights"))["y"]
+    assert np.allclose(r.to_numpy()[:5], GOLD["predictions_wls_head5_round2"], atol=tolr, rtol=0)
+
+
+# ----------------------------------------------------------------------------------- static models
+@pytest.mark.parametrize("solve_method", ["qr", "chol", "lu", None])
+def test_ols(solve_method):                                                # tests/test_ols.py:54-73 (C1 shape)
+    d = _make_data(1000, 3)
+    F = Frame(d)
+    r = F.select(col("y").least_squares.ols(*_xs(d), mode="coefficients", solve_method=solve_method))["coefficients"]
+    ref = S.least_squares(d["y"], *_oracle_cols(d, _xs(d)), mode="coefficients", kwargs=S.OLSKwargs(solve_method=solve_method))
+    _close(r.to_numpy()[0], _ref(ref))
+    p = F.select(col("y").least_squares.ols(*_xs(d), solve_method=solve_method))["y"]
+    _close(p.to_numpy(), _ref(S.least_squares(d["y"], *_oracle_cols(d, _xs(d)), kwargs=S.OLSKwargs(solve_method=solve_method))))
+    e = F.select(col("y").least_squares.ols(*_xs(d), mode="residuals"))["y"]
+    _close(e.to_numpy(), _ref(S.least_squares(d["y"], *_oracle_cols(d, _xs(d)), mode="residuals")))
+
+
+def test_svd_is_a_loud_unsupported_error():
+    d = _make_data(100, 2)
+    with pytest.raises(pls.B200OLSError) as ei:
+        Frame(d).select(col("y").least_squares.ols("x1", "x2", solve_method="svd"))
+    assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("k,n_groups,n", [(8, 300, 60000), (3, 7, 5000), (16, 50, 20000)])
+def test_ridge_coefficients_over_random_groups(k, n_groups, n):           # C2 shape, tests/test_ols.py:380-401,475-503
+    d = _make_data(n, k, n_groups=n_groups, seed=3)
+    F = Frame(d)
+    r = F.select(col("y").least_squares.ridge(*_xs(d), alpha=1e-3, mode="coefficients").over("group"))["coefficients"]
+    keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), per_group=True, mode="coefficients",
+                        kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.0))
+    assert (r.keys == keys).all()
+    _close(r.to_numpy(), c)
+    for mode in ("predictions", "residuals"):
+        p = F.select(col("y").least_squares.ridge(*_xs(d), alpha=1e-3, mode=mode).over("group"))["y"]
+        ref = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), mode=mode,
+                     kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.0))
+        _close(p.to_numpy(), _ref(ref))
+
+
+def test_contiguous_equal_groups_c2_small():
+    G, n, k = 500, 1000, 8
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(G * n, k))
+    beta = 1 + 0.25 * rng.normal(size=(G, k))
+    y = (x.reshape(G, n, k) * beta[:, None, :]).sum(-1).reshape(-1) + 0.1 * rng.normal(size=G * n)
+    d = {f"x{i}": np.ascontiguousarray(x[:, i]) for i in range(k)}
+    d["y"] = y
+    d["group"] = np.repeat(np.arange(G), n)
+    r = Frame(d).select(col("y").least_squares.ridge(*[f"x{i}" for i in range(k)], alpha=1e-3, mode="coefficients").over("group"))["coefficients"]
+    xg = x.reshape(G, n, k)
+    ref = np.linalg.solve(np.einsum("gni,gnj->gij", xg, xg) + 1e-3 * np.eye(k), np.einsum("gni,gn->gi", xg, y.reshape(G, n)))
+    _close(r.to_numpy(), ref)
+    flags = pls.get_engine(0).last_group_flags(G)
+    assert (flags == 0).all()
+
+
+def test_large_group_is_split_into_segments():
+    d = _make_data(50_000, 5, seed=7)
+    d["group"] = np.concatenate([np.zeros(30_000, int), np.ones(19_999, int), np.full(1, 2)])
+    F = Frame(d)
+    r = F.select(col("y").least_squares.ridge(*_xs(d), alpha=0.5, mode="coefficients", add_intercept=True).over("group"))["coefficients"]
+    keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), per_group=True, mode="coefficients",
+                        add_intercept=True, kwargs=S.OLSKwargs(alpha=0.5, l1_ratio=0.0))
+    _close(r.to_numpy(), c)
+    p = F.select(col("y").least_squares.ridge(*_xs(d), alpha=0.5, add_intercept=True).over("group"))["y"]
+    _close(p.to_numpy(), _ref(S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), add_intercept=True,
+                                     kwargs=S.OLSKwargs(alpha=0.5, l1_ratio=0.0))))
+
+
+@pytest.mark.parametrize("null_policy", ["drop", "drop_zero", "drop_y_zero_x", "zero", "ignore"])
+@pytest.mark.parametrize("mode", ["predictions", "residuals", "coefficients"])
+def test_missing_data(null_policy, mode):                                  # tests/test_ols.py:130-249
+    d = _make_data(4000, 2, n_groups=5, add_missing=True)
+    F = Frame(d)
+    r = F.select(col("y").least_squares.ols("x1", "x2", null_policy=null_policy, mode=mode).over("group"))
+    r = r["coefficients" if mode == "coefficients" else "y"]
+    kw = S.OLSKwargs(null_policy=null_policy)
+    if mode == "coefficients":
+        keys, c, m = S.over(S.least_squares, d["group"], d["y"], d["x1"], d["x2"], per_group=True, mode=mode, kwargs=kw)
+        _close(r.to_numpy(), np.where(m, c, np.nan))
+    else:
+        ref = S.over(S.least_squares, d["group"], d["y"], d["x1"], d["x2"], mode=mode, kwargs=kw)
+        got = r.to_numpy()
+        refv = _ref(ref)
+        if null_policy == "ignore":   # NaN (not null) propagates: whole groups are NaN
+            assert (np.isnan(got) == np.isnan(refv)).all()
+        else:
+            _close(got, refv)
+            assert (r.is_null() == ~ref[1]).all()
+
+
+def test_all_empty_data():                                                 # tests/test_ols.py:252-269
+    F = Frame({"A": (np.array([0.0, 2, 0, 4]), np.array([False, True, False, True])),
+               "B": (np.array([1.0, 0, 3, 0]), np.array([True, False, True, False]))})
+    r = F.select(col("A").least_squares.ols(col("B"), mode="residuals", null_policy="drop", solve_method="chol"))["A"]
+    assert r.is_null().all()
+
+
+def test_wls_intercept_and_f32():                                          # tests/test_ols.py:506-541; C3 dtype
+    d = _make_data(3000, 4, n_groups=6, seed=5)
+    rng = np.random.default_rng(1)
+    d["w"] = rng.uniform(0.05, 1.0, size=3000)
+    d["w"] = (d["w"], rng.random(3000) >= 0.02)                             # null weights -> sqrt_w = 1e-12
+    for mode in ("coefficients", "predictions", "residuals"):
+        r = Frame(d).select(col("y").least_squares.wls(*_xs(d), sample_weights="w", add_intercept=True, mode=mode).over("group"))
+        r = r["coefficients" if mode == "coefficients" else "y"]
+        if mode == "coefficients":
+            keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), sample_weights=d["w"],
+                                per_group=True, add_intercept=True, mode=mode)
+            _close(r.to_numpy(), c)
+        else:
+            ref = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), sample_weights=d["w"],
+                         add_intercept=True, mode=mode)
+            _close(r.to_numpy(), _ref(ref), rtol=1e-6, atol=1e-6)
+    # f32 inputs: arithmetic is f64 on f32-rounded inputs; tolerance 1e-4
+    d32 = {k: (v.astype(np.float32) if k != "group" and not isinstance(v, tuple) else v) for k, v in d.items()}
+    d32["w"] = (d["w"][0].astype(np.float32), d["w"][1])
+    r = Frame(d32).select(col("y").least_squares.elastic_net(*_xs(d), alpha=1e-3, l1_ratio=0.5, sample_weights="w").over("group"))["y"]
+    ref = S.over(S.least_squares, d32["group"], d32["y"], *_oracle_cols(d32, _xs(d)), sample_weights=d32["w"],
+                 kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.5))
+    _close(r.to_numpy(), _ref(ref), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("k,sparsity,alpha,l1_ratio,method,positive", [
+    (10, 0.5, 0.001, 0.5, "cd", False), (10, 0.5, 0.001, 0.5, "cd_active_set", False), (16, 0.5, 0.001, 0.5, None, False),
+    (64, 0.9, 0.0001, 1.0, None, False), (4, 0.0, 0.1, 0.5, None, True), (100, 0.9, 0.01, 0.5, "cd", False)])
+def test_elastic_net(k, sparsity, alpha, l1_ratio, method, positive):      # tests/test_ols.py:561-630; C3/C5 shapes
+    d = _make_data(6000, k, n_groups=3, sparsity=sparsity, seed=11)
+    expr = col("y").least_squares.elastic_net(*_xs(d), alpha=alpha, l1_ratio=l1_ratio, positive=positive,
+                                              solve_method=method, mode="coefficients").over("group")
+    if k > 64:
+        with pytest.raises(pls.B200OLSError) as ei:
+            Frame(d).select(expr)
+        assert ei.value.code == -2
+        return
+    r = Frame(d).select(expr)["coefficients"]
+    keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), per_group=True, mode="coefficients",
+                        kwargs=S.OLSKwargs(alpha=alpha, l1_ratio=l1_ratio, positive=positive, solve_method=method))
+    _close(r.to_numpy(), c, rtol=1e-6, atol=1e-8)
+
+
+def test_ill_conditioned_ols_uses_qr_kernel():                             # tests/test_ols.py:315-360 (qr finite / accurate)
+    rng = np.random.default_rng(0)
+    n = 2000
+    x1 = rng.normal(size=n)
+    x2 = x1 + 1e-5 * rng.normal(size=n)      # cond(X) ~ 1e5 -> cond(G) ~ 1e10: normal equations lose 1e-6
+    x3 = rng.normal(size=n)
+    y = x1 + 2 * x2 - x3 + 0.01 * rng.normal(size=n)
+    d = {"y": y, "x1": x1, "x2": x2, "x3": x3}
+    r = Frame(d).select(col("y").least_squares.ols("x1", "x2", "x3", mode="coefficients"))["coefficients"]
+    ref = np.linalg.lstsq(np.c_[x1, x2, x3], y, rcond=None)[0]
+    _close(r.to_numpy()[0], ref, rtol=1e-6, atol=1e-8)
+    assert pls.get_engine(0).last_group_flags(1)[0] & 4
+
+
+# ----------------------------------------------------------------------------------- moving-window models
+@pytest.mark.parametrize("half_life,p0,mean,policy", [(None, 10.0, None, "drop"), (252.0, 10.0, None, "drop"),
+                                                      (None, 1e6, None, "drop_y_zero_x"), (20.0, 0.01, [0.25, 0.25], "zero")])
+@pytest.mark.parametrize("mode", ["coefficients", "predictions", "residuals"])
+def test_recursive_least_squares(half_life, p0, mean, policy, mode):       # tests/test_ols.py:633-715
+    d = _make_data(6000, 2, n_groups=3, add_missing=True, seed=2)
+    kw = dict(half_life=half_life, initial_state_covariance=p0, initial_state_mean=mean, null_policy=policy)
+    r = Frame(d).select(col("y").least_squares.rls("x1", "x2", mode=mode, **kw).over("group"))
+    r = r["coefficients" if mode == "coefficients" else "y"]
+    ref = S.over(S.recursive_least_squares, d["group"], d["y"], d["x1"], d["x2"], mode=mode, kwargs=S.RLSKwargs(**kw))
+    got, refv = r.to_numpy(), _ref(ref)
+    warm = 8  # rows where the diffuse prior dominates are conditioned like p0*|x|^2
+    _close(got[3 * warm:], refv[3 * warm:], rtol=1e-6, atol=1e-8)
+    assert np.allclose(got[:3 * warm], refv[:3 * warm], rtol=1e-4, atol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize("window,min_periods,policy,alpha", [(21, None, "drop", None), (252, 5, "drop", None),
+                                                             (50, 10, "drop_window", None), (30, 3, "zero", 0.01),
+                                                             (100, None, "drop_zero", None)])
+@pytest.mark.parametrize("mode", ["coefficients", "predictions", "residuals"])
+def test_rolling_least_squares(window, min_periods, policy, alpha, mode):  # tests/test_ols.py:718-841
+    d = _make_data(5000, 3, n_groups=2, add_missing=True, seed=4)
+    kw = dict(window_size=window, min_periods=min_periods, null_policy=policy, alpha=alpha)
+    r = Frame(d).select(col("y").least_squares.rolling_ols("x1", "x2", "x3", mode=mode, **kw).over("group"))
+    r = r["coefficients" if mode == "coefficients" else "y"]
+    ref = S.over(S.rolling_least_squares, d["group"], d["y"], d["x1"], d["x2"], d["x3"], mode=mode, kwargs=S.RollingKwargs(**kw))
+    got, refv = r.to_numpy(), _ref(ref)
+    assert (np.isnan(got) == np.isnan(refv)).all()
+    ok = ~np.isnan(refv) & (np.abs(refv) < 1e6)       # singular warm-up windows are rounding noise in the reference too
+    assert np.allclose(got[ok], refv[ok], rtol=1e-6, atol=1e-7)
+
+
+def test_rolling_insufficient_data():                                      # tests/test_ols.py:775-806
+    d = {"y": np.array([1.0, 2.0, 3.0]), "x": np.array([1.0, 2.0, 4.0])}
+    for mp, n_valid in ((2, 2), (3, 1), (4, 0)):
+        r = Frame(d).select(col("y").least_squares.rolling_ols("x", window_size=10, min_periods=mp, mode="coefficients"))["coefficients"]
+        assert (~np.isnan(r.to_numpy()[:, 0])).sum() == n_valid
+
+
+def test_single_long_series_rls_and_rolling_c4_small():                    # C4 shape (1 group, k=6) at 300k rows
+    d = _make_data(300_000, 6, seed=9)
+    names = _xs(d)
+    r = Frame(d).select(col("y").least_squares.rolling_ols(*names, window_size=252, min_periods=6, mode="coefficients"))["coefficients"]
+    ref = S.rolling_least_squares(d["y"], *_oracle_cols(d, names), mode="coefficients",
+                                  kwargs=S.RollingKwargs(window_size=252, min_periods=6, null_policy="drop"))
+    _close(r.to_numpy(), _ref(ref), rtol=1e-6, atol=1e-8)
+    r = Frame(d).select(col("y").least_squares.rls(*names, half_life=252.0))["y"]
+    ref = S.recursive_least_squares(d["y"], *_oracle_cols(d, names), kwargs=S.RLSKwargs(half_life=252.0))
+    _close(r.to_numpy()[100:], _ref(ref)[100:], rtol=1e-6, atol=1e-8)
+
+
+# ----------------------------------------------------------------------------------- device-resident frames
+def test_device_resident_torch_frame():
+    import torch
+    d = _make_data(40_000, 8, n_groups=None, seed=6)
+    G = 40
+    d["group"] = np.repeat(np.arange(G), 1000)
+    dev = {k: torch.as_tensor(v, device="cuda") for k, v in d.items() if k != "group"}
+    dev["group"] = d["group"]
+    r = Frame(dev).select(col("y").least_squares.ridge(*_xs(d), alpha=1e-3, mode="coefficients").over("group"))["coefficients"]
+    assert r.values.is_cuda
+    keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), per_group=True, mode="coefficients",
+                        kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.0))
+    _close(r.to_numpy(), c)
+    p = Frame(dev).select(col("y").least_squares.ridge(*_xs(d), alpha=1e-3).over("group"))["y"]
+    _close(p.to_numpy(), _ref(S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)),
+                                     kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.0))))
+
+
+def test_full_size_c2_normal_equation_property():
+    """BASELINE.json configs[1] at full size (10k groups x 1k rows x 8 f64, alpha=1e-3): size-independent
+    property instead of the oracle — the ridge normal equations hold per group:
+    X^T (y - X b) - alpha b = 0, evaluated in f64 with torch on the device; plus the oracle on 64 groups."""
+    import torch
+    G, n, k, alpha = 10_000, 1000, 8, 1e-3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(k, G * n, dtype=torch.float64, device="cuda", generator=g)
+    beta = 1 + 0.25 * torch.randn(G, k, dtype=torch.float64, device="cuda", generator=g)
+    y = (x.T.reshape(G, n, k) * beta[:, None, :]).sum(-1).reshape(-1) + 0.1 * torch.randn(G * n, dtype=torch.float64, device="cuda", generator=g)
+    cols = {f"x{i}": x[i] for i in range(k)}
+    cols["y"] = y
+    eng = pls.get_engine(0, torch_stream=True)
+    b = pls.Batch(pls.as_col(y), [pls.as_col(x[i]) for i in range(k)], offsets=np.arange(G + 1, dtype=np.int64) * n)
+    coef, _ = eng.least_squares(b, OLSKwargs(alpha=alpha, l1_ratio=0.0).to_c(), 2)
+    torch.cuda.synchronize()
+    xg = x.T.reshape(G, n, k)
+    resid = y.reshape(G, n) - (xg * coef[:, None, :]).sum(-1)
+    grad = torch.einsum("gnk,gn->gk", xg, resid) - alpha * coef
+    scale = torch.einsum("gnk,gn->gk", xg.abs(), y.reshape(G, n).abs())
+    assert float((grad.abs() / scale).max()) < 1e-12
+    sel = np.arange(0, G, G // 64)
+    xs = x.T.reshape(G, n, k)[sel].cpu().numpy()
+    ys = y.reshape(G, n)[sel].cpu().numpy()
+    ref = np.stack([S.solve_ridge(np.ascontiguousarray(ys[i]), np.ascontiguousarray(xs[i]), alpha, None, None) for i in range(len(sel))])
+    _close(coef[sel].cpu().numpy(), ref)

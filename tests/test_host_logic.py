@@ -1,0 +1,133 @@
+"""CPU tests (`-m "not gpu"`): the C-ABI library loads and exports every symbol include/b200ols.h
+declares, fails loudly without a device, and the host-side mirror (kwargs, grouping, sharding,
+world_size-2 gather over gloo) behaves like the reference's Python layer."""
+import ctypes as C
+import os
+import re
+import socket
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from polars_ols_b200 import _lib
+    header = (ROOT / "include" / "b200ols.h").read_text()
+    declared = set(re.findall(r"B200OLS_API[^;(]*?\b(b200ols_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = C.CDLL(str(_lib.SO_PATH))
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.load().b200ols_version() == 100
+
+
+def test_struct_layouts_match_the_header():
+    from polars_ols_b200 import _lib
+    assert C.sizeof(_lib.Column) == 16
+    assert C.sizeof(_lib.Frame) == 8 + 16 + 16 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.OLSKwargs) == 56 and C.sizeof(_lib.RLSKwargs) == 32 and C.sizeof(_lib.RollingKwargs) == 32
+    assert _lib.Frame.target.offset == 24 and _lib.Frame.group_offsets.offset == 64
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import polars_ols_b200 as pls
+    with pytest.raises(pls.B200OLSError) as ei:
+        pls.Engine(0)
+    assert ei.value.code == -4 and "no CPU fallback" in str(ei.value)
+    d = {"y": np.zeros(4), "x": np.ones(4)}
+    with pytest.raises(pls.B200OLSError):
+        pls.Frame(d).select(pls.col("y").least_squares.ols("x"))
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "polars_ols_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h"):
+            txt = p.read_text()
+            assert "oracle" not in txt.replace("the oracle on a CPU-only box", "").replace("against the oracle", "").lower() or p.name in ("solvers.cuh", "moving_core.cuh"), p
+
+
+def test_kwargs_mirror_reference_defaults_and_validation():
+    import polars_ols_b200 as pls
+    k = pls.OLSKwargs()
+    assert (k.alpha, k.l1_ratio, k.max_iter, k.tol, k.positive, k.solve_method, k.rcond, k.null_policy) == \
+        (0.0, None, 1000, 1e-5, False, None, None, "ignore")
+    assert pls.RLSKwargs().null_policy == "drop" and pls.RLSKwargs().initial_state_covariance == 10.0
+    assert pls.RollingKwargs().null_policy == "drop_window" and pls.RollingKwargs().window_size == 1_000_000
+    with pytest.raises(AssertionError):
+        pls.OLSKwargs(null_policy="drop_window")          # polars_ols/least_squares.py:111-115
+    with pytest.raises(AssertionError):
+        pls.OLSKwargs(solve_method="nope")
+    c = pls.OLSKwargs(alpha=None, l1_ratio=None, max_iter=None, tol=None).to_c()
+    assert np.isnan(c.alpha) and np.isnan(c.l1_ratio) and c.max_iter == -1 and np.isnan(c.tol)
+    ns = pls.col("y").least_squares
+    assert ns.ridge("x", alpha=1.0).kwargs.l1_ratio == 0.0      # polars_ols/__init__.py:123
+    assert ns.lasso("x", alpha=1.0).kwargs.l1_ratio == 1.0      # :132
+    assert ns.elastic_net("x", alpha=1.0).kwargs.l1_ratio == 0.5
+    assert ns.rls("x").kwargs.null_policy == "drop" and ns.rolling_ols("x", window_size=5).kwargs.null_policy == "drop"
+    assert ns.expanding_ols("x").kwargs.half_life is None
+
+
+def test_group_plan_matches_polars_over_semantics():
+    from polars_ols_b200.least_squares import _group_plan
+    g = np.array([2, 0, 2, 1, 0, 2])
+    keys, offs, ridx, inv = _group_plan([g])
+    assert keys.tolist() == [0, 1, 2] and offs.tolist() == [0, 2, 3, 6]
+    assert ridx.tolist() == [1, 4, 3, 0, 2, 5]                  # stable: frame order inside each group
+    keys, offs, ridx, inv = _group_plan([np.array([0, 0, 1, 1, 1])])
+    assert ridx is None and offs.tolist() == [0, 2, 5]          # contiguous slices need no gather
+
+
+def test_columns_from_arrow_and_masks():
+    import pyarrow as pa
+    from polars_ols_b200 import as_col
+    c = as_col(pa.array([1.0, None, 3.0, 4.0, None, 6.0, 7.0, 8.0, 9.0]))
+    assert c.values.dtype == np.float64 and c.validity is not None
+    assert np.unpackbits(c.validity, bitorder="little")[:9].tolist() == [1, 0, 1, 1, 0, 1, 1, 1, 1]
+    c = as_col((np.arange(4.0), np.array([True, True, True, True])))
+    assert c.validity is None
+    c = as_col(np.arange(5))
+    assert c.values.dtype == np.float64
+
+
+def test_shard_groups_balances_rows():
+    from polars_ols_b200.parallel import shard_groups
+    offs = np.concatenate([[0], np.cumsum([10, 1000, 10, 10, 1000, 970])])
+    sh = shard_groups(offs, 2)
+    assert sh[0][0] == 0 and sh[-1][1] == 6 and sh[0][1] == sh[1][0]
+    rows = [offs[b] - offs[a] for a, b in sh]
+    assert abs(rows[0] - rows[1]) <= 1000
+    assert shard_groups(np.array([0, 5]), 4)[-1] == (1, 1) or sum(b - a for a, b in shard_groups(np.array([0, 5]), 4)) == 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from polars_ols_b200.parallel import gather_group_results, shard_groups
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    offs = np.concatenate([[0], np.cumsum([5, 50, 5, 40, 7])])
+    shards = shard_groups(offs, world)
+    a, b = shards[rank]
+    local = torch.arange(a, b, dtype=torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64)  # "coefficients" = group id
+    full = gather_group_results(local, shards)
+    q.put((rank, full[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gather_over_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(60) for p in ps]
+    for rank, vals in res:
+        assert vals == [0.0, 1.0, 2.0, 3.0, 4.0]
