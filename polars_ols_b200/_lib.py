@@ -25,7 +25,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 EXPORTS = [
     "b200ols_create", "b200ols_create_on_stream", "b200ols_destroy", "b200ols_synchronize",
     "b200ols_last_error", "b200ols_version", "b200ols_launch_count", "b200ols_host_alloc",
-    "b200ols_host_free", "b200ols_set_tuning", "b200ols_set_profiling", "b200ols_profile_drain", "b200ols_least_squares",
+    "b200ols_host_free", "b200ols_set_tuning", "b200ols_set_variant", "b200ols_set_profiling", "b200ols_profile_drain", "b200ols_least_squares",
     "b200ols_least_squares_coefficients", "b200ols_recursive_least_squares",
     "b200ols_recursive_least_squares_coefficients", "b200ols_rolling_least_squares",
     "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags",
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
     L.b200ols_host_free.argtypes = [vp]
     L.b200ols_host_free.restype = None
     L.b200ols_set_tuning.argtypes = [vp, i32, i32, i32]
+    L.b200ols_set_variant.argtypes = [vp, i32, i32]
     L.b200ols_set_profiling.argtypes = [vp, i32]
     L.b200ols_profile_drain.argtypes = [vp, vp, i32]
     L.b200ols_least_squares.argtypes = [vp, C.POINTER(Frame), C.POINTER(OLSKwargs), i32, C.POINTER(Output)]

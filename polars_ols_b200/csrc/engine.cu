@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/b200ols.h"
+#include "gram_ldg.cuh"
 #include "gram_stream.cuh"
 #include "moving.cuh"
 #include "predict.cuh"
@@ -72,6 +73,7 @@ struct b200ols_ctx {
     int smem_optin = 0;
     int64_t launches = 0;
     int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
+    int variant = 0, unroll = 0;  // Gram kernel variant: 0 = TMA-staged, 1 = direct loads
     // bump arena in device memory, reset at the start of every call
     char *arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
@@ -243,6 +245,14 @@ extern "C" int b200ols_set_tuning(b200ols_ctx *c, int tile_rows, int warps_per_c
     c->tile_rows = tile_rows;
     c->warps_per_cta = warps_per_cta;
     c->ctas_per_sm = ctas_per_sm;
+    return 0;
+}
+
+extern "C" int b200ols_set_variant(b200ols_ctx *c, int variant, int unroll) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (variant < 0 || variant > 1) return fail(B200OLS_ERR_INVALID, "variant must be 0 (TMA-staged) or 1 (direct loads)");
+    c->variant = variant;
+    c->unroll = unroll;
     return 0;
 }
 
@@ -536,6 +546,18 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     const int F = gp.F;
     const int KB = (F + 7) / 8;
     const int NC = gp.kd + 1 + gp.has_w + gp.has_mask;
+    if (c->variant == 1 && KB <= 2) {  // direct-load variant
+        int warps = c->warps_per_cta > 0 ? c->warps_per_cta : 16;
+        const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 1;
+        int64_t grid = std::min<int64_t>(static_cast<int64_t>(c->sm_count) * ctas, (gp.nseg + warps - 1) / warps);
+        grid = std::max<int64_t>(grid, 1);
+        const int U = c->unroll > 0 ? c->unroll : (KB == 1 ? 8 : 4);
+        ProfScope prof(c);
+        CU(sizeof(T) == 8 ? gram_ldg_launch_f64(KB, U, gp, static_cast<unsigned>(grid), warps, c->stream)
+                          : gram_ldg_launch_f32(KB, U, gp, static_cast<unsigned>(grid), warps, c->stream));
+        c->launches++;
+        return 0;
+    }
     const size_t budget = static_cast<size_t>(c->smem_optin) - 2048;  // static mbarriers + slack
     const int KBT = KB <= 1 ? 1 : (KB <= 2 ? 2 : (KB <= 4 ? 4 : 8));  // instantiated block counts
     int warps = c->warps_per_cta > 0 ? c->warps_per_cta : 8;

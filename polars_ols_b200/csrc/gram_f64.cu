@@ -1,7 +1,11 @@
 // gram_f64.cu — f64 instantiations of the row-streaming Gram kernel (see gram_stream.cuh)
+#include "gram_ldg.cuh"
 #include "gram_stream.cuh"
 namespace b200 {
 cudaError_t gram_launch_f64(int KB, const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s) {
     return gram_launch_any<double>(KB, p, grid, warps, smem, s);
+}
+cudaError_t gram_ldg_launch_f64(int KB, int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
+    return gram_ldg_launch_any<double>(KB, U, p, grid, warps, s);
 }
 }  // namespace b200

@@ -74,6 +74,84 @@ __host__ __device__ inline uint32_t gram_scratch_bytes(int F, int fused) {
     return static_cast<uint32_t>((FP * FP + 2 * FP) * sizeof(double));  // G, c, diag scratch
 }
 
+// Epilogue shared by the TMA-staged and the direct-load kernels: reduce X^T y over the 4 lanes that share
+// a feature, then either solve in shared memory (fused) or write the raw Gram partial.
+template <int KB>
+__device__ __forceinline__ void gram_epilogue(const GramParams &p, double (&acc)[KB * (KB + 1) / 2][2], double (&cy)[KB],
+                                              int nfit, int64_t seg, double *Gs, int lane) {
+    constexpr int FP = 8 * KB;
+    const int fb = lane >> 2, q = lane & 3;
+    const int F = p.F;
+    // reduce X^T y and the row count over the 4 lanes that share a feature
+#pragma unroll
+    for (int bk = 0; bk < KB; ++bk) {
+        cy[bk] += __shfl_xor_sync(0xffffffffu, cy[bk], 1);
+        cy[bk] += __shfl_xor_sync(0xffffffffu, cy[bk], 2);
+    }
+    nfit += __shfl_xor_sync(0xffffffffu, nfit, 1);
+    nfit += __shfl_xor_sync(0xffffffffu, nfit, 2);
+    nfit = __shfl_sync(0xffffffffu, nfit, 0);
+    const int64_t g = p.seg_group ? p.seg_group[seg] : seg;
+
+    if (p.fused) {
+        double *cs = Gs + FP * FP;
+        double *ds = cs + FP;
+        int idx = 0;
+#pragma unroll
+        for (int bi = 0; bi < KB; ++bi) {
+#pragma unroll
+            for (int bj = bi; bj < KB; ++bj) {
+                const int rr = 8 * bi + fb, cc = 8 * bj + 2 * q;
+                Gs[rr * FP + cc] = acc[idx][0];
+                Gs[rr * FP + cc + 1] = acc[idx][1];
+                if (bi != bj) {
+                    Gs[cc * FP + rr] = acc[idx][0];
+                    Gs[(cc + 1) * FP + rr] = acc[idx][1];
+                }
+                ++idx;
+            }
+            if (q == 0) cs[8 * bi + fb] = cy[bi];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int fl = 0;
+            if (nfit == 0) {  // src/expressions.rs:357-359: no rows -> zeros
+                for (int i = 0; i < F; ++i) cs[i] = 0.0;
+                fl = FLAG_EMPTY;
+            } else {
+                for (int i = 0; i < F; ++i) Gs[i * FP + i] += p.alpha;
+                fl = normal_equations_solve(Gs, FP, F, cs, p.use_lu, ds, p.illcond_ratio);
+            }
+            p.flags[g] = fl;
+        }
+        __syncwarp();
+        if (lane < F) p.beta[g * F + lane] = cs[lane];
+        if (lane + 32 < F) p.beta[g * F + lane + 32] = cs[lane + 32];
+        __syncwarp();
+    } else {
+        double *out = p.partial + static_cast<size_t>(seg) * (static_cast<size_t>(F) * F + F + 1);
+        int idx = 0;
+#pragma unroll
+        for (int bi = 0; bi < KB; ++bi) {
+#pragma unroll
+            for (int bj = bi; bj < KB; ++bj) {
+                const int rr = 8 * bi + fb, cc = 8 * bj + 2 * q;
+                if (rr < F) {
+                    if (cc < F) out[rr * F + cc] = acc[idx][0];
+                    if (cc + 1 < F) out[rr * F + cc + 1] = acc[idx][1];
+                    if (bi != bj) {
+                        if (cc < F) out[cc * F + rr] = acc[idx][0];
+                        if (cc + 1 < F) out[(cc + 1) * F + rr] = acc[idx][1];
+                    }
+                }
+                ++idx;
+            }
+            if (q == 0 && 8 * bi + fb < F) out[F * F + 8 * bi + fb] = cy[bi];
+        }
+        if (lane == 0) out[F * F + F] = static_cast<double>(nfit);
+    }
+}
+
 template <typename T, int KB, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramParams p) {
     using Vec = typename V2<T>::type;
@@ -222,75 +300,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramPar
             }
         }
 
-        // ---- epilogue -------------------------------------------------------------------------------
-        // reduce X^T y and the row count over the 4 lanes that share a feature
-#pragma unroll
-        for (int bk = 0; bk < KB; ++bk) {
-            cy[bk] += __shfl_xor_sync(0xffffffffu, cy[bk], 1);
-            cy[bk] += __shfl_xor_sync(0xffffffffu, cy[bk], 2);
-        }
-        nfit += __shfl_xor_sync(0xffffffffu, nfit, 1);
-        nfit += __shfl_xor_sync(0xffffffffu, nfit, 2);
-        nfit = __shfl_sync(0xffffffffu, nfit, 0);
-        const int64_t g = p.seg_group ? p.seg_group[seg] : seg;
-
-        if (p.fused) {
-            double *cs = Gs + FP * FP;
-            double *ds = cs + FP;
-            int idx = 0;
-#pragma unroll
-            for (int bi = 0; bi < KB; ++bi) {
-#pragma unroll
-                for (int bj = bi; bj < KB; ++bj) {
-                    const int rr = 8 * bi + fb, cc = 8 * bj + 2 * q;
-                    Gs[rr * FP + cc] = acc[idx][0];
-                    Gs[rr * FP + cc + 1] = acc[idx][1];
-                    if (bi != bj) {
-                        Gs[cc * FP + rr] = acc[idx][0];
-                        Gs[(cc + 1) * FP + rr] = acc[idx][1];
-                    }
-                    ++idx;
-                }
-                if (q == 0) cs[8 * bi + fb] = cy[bi];
-            }
-            __syncwarp();
-            if (lane == 0) {
-                int fl = 0;
-                if (nfit == 0) {  // src/expressions.rs:357-359: no rows -> zeros
-                    for (int i = 0; i < F; ++i) cs[i] = 0.0;
-                    fl = FLAG_EMPTY;
-                } else {
-                    for (int i = 0; i < F; ++i) Gs[i * FP + i] += p.alpha;
-                    fl = normal_equations_solve(Gs, FP, F, cs, p.use_lu, ds, p.illcond_ratio);
-                }
-                p.flags[g] = fl;
-            }
-            __syncwarp();
-            if (lane < F) p.beta[g * F + lane] = cs[lane];
-            if (lane + 32 < F) p.beta[g * F + lane + 32] = cs[lane + 32];
-            __syncwarp();
-        } else {
-            double *out = p.partial + static_cast<size_t>(seg) * (static_cast<size_t>(F) * F + F + 1);
-            int idx = 0;
-#pragma unroll
-            for (int bi = 0; bi < KB; ++bi) {
-#pragma unroll
-                for (int bj = bi; bj < KB; ++bj) {
-                    const int rr = 8 * bi + fb, cc = 8 * bj + 2 * q;
-                    if (rr < F) {
-                        if (cc < F) out[rr * F + cc] = acc[idx][0];
-                        if (cc + 1 < F) out[rr * F + cc + 1] = acc[idx][1];
-                        if (bi != bj) {
-                            if (cc < F) out[cc * F + rr] = acc[idx][0];
-                            if (cc + 1 < F) out[(cc + 1) * F + rr] = acc[idx][1];
-                        }
-                    }
-                    ++idx;
-                }
-                if (q == 0 && 8 * bi + fb < F) out[F * F + 8 * bi + fb] = cy[bi];
-            }
-            if (lane == 0) out[F * F + F] = static_cast<double>(nfit);
-        }
+        gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane);
     }
 }
 

@@ -168,6 +168,9 @@ class Engine:
     def set_tuning(self, tile_rows: int = 0, warps_per_cta: int = 0, ctas_per_sm: int = 0):
         L.check(self._lib.b200ols_set_tuning(self._ctx, tile_rows, warps_per_cta, ctas_per_sm))
 
+    def set_variant(self, variant: int = 0, unroll: int = 0):
+        L.check(self._lib.b200ols_set_variant(self._ctx, variant, unroll))
+
     def set_profiling(self, enabled: bool):
         L.check(self._lib.b200ols_set_profiling(self._ctx, 1 if enabled else 0))
 

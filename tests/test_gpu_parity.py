@@ -126,7 +126,7 @@ def test_contiguous_equal_groups_c2_small():
     d["group"] = np.repeat(np.arange(G), n)
     r = Frame(d).select(col("y").least_squares.ridge(*[f"x{i}" for i in range(k)], alpha=1e-3, mode="coefficients").over("group"))["coefficients"]
     xg = x.reshape(G, n, k)
-    ref = np.linalg.solve(np.einsum("gni,gnj->gij", xg, xg) + 1e-3 * np.eye(k), np.einsum("gni,gn->gi", xg, y.reshape(G, n)))
+    ref = np.linalg.solve(np.einsum("gni,gnj->gij", xg, xg) + 1e-3 * np.eye(k), np.einsum("gni,gn->gi", xg, y.reshape(G, n))[..., None])[..., 0]
     _close(r.to_numpy(), ref)
     flags = pls.get_engine(0).last_group_flags(G)
     assert (flags == 0).all()
