@@ -547,11 +547,11 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     const int KB = (F + 7) / 8;
     const int NC = gp.kd + 1 + gp.has_w + gp.has_mask;
     if (c->variant == 1 && KB <= 2) {  // direct-load variant
-        int warps = c->warps_per_cta > 0 ? c->warps_per_cta : 16;
-        const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 1;
+        int warps = std::min(c->warps_per_cta > 0 ? c->warps_per_cta : 8, 8);
+        const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 3;
         int64_t grid = std::min<int64_t>(static_cast<int64_t>(c->sm_count) * ctas, (gp.nseg + warps - 1) / warps);
         grid = std::max<int64_t>(grid, 1);
-        const int U = c->unroll > 0 ? c->unroll : (KB == 1 ? 8 : 4);
+        const int U = c->unroll > 0 ? c->unroll : 2;
         ProfScope prof(c);
         CU(sizeof(T) == 8 ? gram_ldg_launch_f64(KB, U, gp, static_cast<unsigned>(grid), warps, c->stream)
                           : gram_ldg_launch_f32(KB, U, gp, static_cast<unsigned>(grid), warps, c->stream));

@@ -71,7 +71,63 @@ template <typename T>
 __host__ __device__ inline uint32_t gram_scratch_bytes(int F, int fused) {
     if (!fused) return 0;
     const int FP = (F + 7) & ~7;
-    return static_cast<uint32_t>((FP * FP + 2 * FP) * sizeof(double));  // G, c, diag scratch
+    return static_cast<uint32_t>(((FP * (FP + 1) + 2 * FP + 1) / 2 * 2) * sizeof(double));  // G (row stride FP+1), c, scratch
+}
+
+// Warp-cooperative Cholesky solve in registers (k <= FP <= 16): lane i holds row i of the SPD matrix in
+// g[0..FP) and the right-hand side c_i.  Right-looking LL^T with full symmetric trailing updates, so that
+// afterwards lane i holds row i of L in g[0..i] and COLUMN i of L in g[i+1..) — exactly what the forward
+// (L z = c) and backward (L^T x = z) substitutions need without any transposition.  Values are exchanged
+// with warp shuffles; one rsqrt per column replaces the divisions (results agree with the reference's
+// faer LL^T to rounding).  Returns false on a non-positive / NaN pivot (-> LU fallback); mn / mx are the
+// extreme squared pivots.  On success lane i returns beta_i in c.
+template <int FP>
+__device__ __forceinline__ bool warp_chol_solve(double (&g)[FP], double &c, int F, int lane, double &mn, double &mx) {
+    constexpr unsigned FULL = 0xffffffffu;
+    bool ok = true;
+    mn = INFINITY;
+    mx = 0.0;
+    double inv[FP];
+#pragma unroll
+    for (int j = 0; j < FP; ++j) {
+        inv[j] = 1.0;
+        if (j < F) {
+            const double d = __shfl_sync(FULL, g[j], j);
+            ok = ok && (d > 0.0);
+            mn = fmin(mn, d);
+            mx = fmax(mx, d);
+            const double r = rsqrt(d);
+            inv[j] = r;  // 1 / L_jj
+            const double lij = (lane == j) ? d * r : g[j] * r;
+            if (lane >= j) g[j] = lij;
+#pragma unroll
+            for (int cc = j + 1; cc < FP; ++cc) {
+                if (cc < F) {
+                    const double lcj = __shfl_sync(FULL, lij, cc);
+                    if (lane > j) g[cc] = fma(-lij, lcj, g[cc]);
+                    else if (lane == j) g[cc] = lcj;
+                }
+            }
+        }
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int j = 0; j < FP; ++j) {
+        if (j < F) {
+            const double zj = __shfl_sync(FULL, c * inv[j], j);
+            if (lane == j) c = zj;
+            else if (lane > j) c = fma(-g[j], zj, c);
+        }
+    }
+#pragma unroll
+    for (int j = FP - 1; j >= 0; --j) {
+        if (j < F) {
+            const double xj = __shfl_sync(FULL, c * inv[j], j);
+            if (lane == j) c = xj;
+            else if (lane < j) c = fma(-g[j], xj, c);
+        }
+    }
+    return true;
 }
 
 // Epilogue shared by the TMA-staged and the direct-load kernels: reduce X^T y over the 4 lanes that share
@@ -94,39 +150,62 @@ __device__ __forceinline__ void gram_epilogue(const GramParams &p, double (&acc)
     const int64_t g = p.seg_group ? p.seg_group[seg] : seg;
 
     if (p.fused) {
-        double *cs = Gs + FP * FP;
-        double *ds = cs + FP;
+        constexpr int LD = FP + 1;  // odd row stride: conflict-free row reads
+        double *cs = Gs + FP * LD;
         int idx = 0;
 #pragma unroll
         for (int bi = 0; bi < KB; ++bi) {
 #pragma unroll
             for (int bj = bi; bj < KB; ++bj) {
                 const int rr = 8 * bi + fb, cc = 8 * bj + 2 * q;
-                Gs[rr * FP + cc] = acc[idx][0];
-                Gs[rr * FP + cc + 1] = acc[idx][1];
+                Gs[rr * LD + cc] = acc[idx][0];
+                Gs[rr * LD + cc + 1] = acc[idx][1];
                 if (bi != bj) {
-                    Gs[cc * FP + rr] = acc[idx][0];
-                    Gs[(cc + 1) * FP + rr] = acc[idx][1];
+                    Gs[cc * LD + rr] = acc[idx][0];
+                    Gs[(cc + 1) * LD + rr] = acc[idx][1];
                 }
                 ++idx;
             }
             if (q == 0) cs[8 * bi + fb] = cy[bi];
         }
         __syncwarp();
-        if (lane == 0) {
-            int fl = 0;
-            if (nfit == 0) {  // src/expressions.rs:357-359: no rows -> zeros
-                for (int i = 0; i < F; ++i) cs[i] = 0.0;
-                fl = FLAG_EMPTY;
-            } else {
-                for (int i = 0; i < F; ++i) Gs[i * FP + i] += p.alpha;
-                fl = normal_equations_solve(Gs, FP, F, cs, p.use_lu, ds, p.illcond_ratio);
+        // lane i takes row i of the (ridge) matrix and c_i into registers
+        double grow[FP];
+        const int li = (lane < FP) ? lane : 0;
+#pragma unroll
+        for (int c = 0; c < FP; ++c) grow[c] = Gs[li * LD + c];
+        double ci = (lane < FP) ? cs[lane] : 0.0;
+#pragma unroll
+        for (int c = 0; c < FP; ++c)
+            if (c == lane && lane < F) grow[c] += p.alpha;  // + alpha I, NOT scaled by n (src/least_squares.rs:352-356)
+        int fl = 0;
+        if (nfit == 0) {  // src/expressions.rs:357-359: no rows -> zeros
+            ci = 0.0;
+            fl = FLAG_EMPTY;
+        } else {
+            bool solved = false;
+            if (!p.use_lu) {
+                double mn, mx;
+                const bool ok = warp_chol_solve<FP>(grow, ci, F, lane, mn, mx);
+                if (ok) {
+                    solved = true;
+                    if (mx > p.illcond_ratio * mn) fl |= FLAG_ILLCOND;
+                } else {
+                    fl |= FLAG_LU_FALLBACK;
+                }
             }
-            p.flags[g] = fl;
+            if (!solved) {  // "lu", or Cholesky hit a non-positive pivot: LU with partial pivoting (rare; lane 0)
+                __syncwarp();
+                if (lane == 0) {
+                    for (int i = 0; i < F; ++i) Gs[i * LD + i] += p.alpha;
+                    lu_solve_inplace(Gs, LD, F, cs);
+                }
+                __syncwarp();
+                ci = (lane < FP) ? cs[lane] : 0.0;
+            }
         }
-        __syncwarp();
-        if (lane < F) p.beta[g * F + lane] = cs[lane];
-        if (lane + 32 < F) p.beta[g * F + lane + 32] = cs[lane + 32];
+        if (lane == 0) p.flags[g] = fl;
+        if (lane < F) p.beta[g * F + lane] = ci;
         __syncwarp();
     } else {
         double *out = p.partial + static_cast<size_t>(seg) * (static_cast<size_t>(F) * F + F + 1);
@@ -226,13 +305,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramPar
 
     for (int64_t seg = wg; seg < nseg; seg += nwarps) {
         const int64_t r0 = p.seg_off[seg], r1 = p.seg_off[seg + 1];
-        double acc[NPAIR][2];
+        constexpr bool DUAL = KB <= 2;  // two independent DMMA chains while the accumulators are few
+        double acc[NPAIR][2], acc2[DUAL ? NPAIR : 1][2];
         double cy[KB];
 #pragma unroll
         for (int i = 0; i < NPAIR; ++i) acc[i][0] = acc[i][1] = 0.0;
 #pragma unroll
+        for (int i = 0; i < (DUAL ? NPAIR : 1); ++i) acc2[i][0] = acc2[i][1] = 0.0;
+#pragma unroll
         for (int i = 0; i < KB; ++i) cy[i] = 0.0;
         int nfit = 0;
+        const bool plain = !p.has_mask && !p.has_w;  // warp-uniform: mask-free interior loop allowed
 
         for (int64_t row = r0; row < r1; row += R) {
             const int64_t b = (row + R < r1) ? row + R : r1;
@@ -240,13 +323,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramPar
             const int hi = o + static_cast<int>(b - row);  // valid local rows are [o, hi)
             mbar_wait(&bar[cstage], phase);
             const unsigned char *sb = wbase + static_cast<size_t>(cstage) * stage_bytes;
-            const int noct = (hi + 7) >> 3;
-#pragma unroll 2
-            for (int j = 0; j < noct; ++j) {
+            const unsigned char *xs[KB];
+#pragma unroll
+            for (int bk = 0; bk < KB; ++bk) xs[bk] = sb + static_cast<size_t>(8 * bk + fb) * stride + 2 * q * sizeof(T);
+            const unsigned char *ys = sb + static_cast<size_t>(ycol) * stride + 2 * q * sizeof(T);
+
+            // predicated octet (segment edges, weights, row mask)
+            auto masked_octet = [&](int j) {
                 const int lr = 8 * j + 2 * q;
                 bool v0 = (lr >= o) && (lr < hi);
                 bool v1 = (lr + 1 >= o) && (lr + 1 < hi);
-                const Vec y2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(ycol) * stride + lr * sizeof(T));
+                const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
                 T s0 = T(1), s1 = T(1);
                 if (p.has_mask) {
                     const Vec m2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(mcol) * stride + lr * sizeof(T));
@@ -269,7 +356,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramPar
                     const int f = 8 * bk + fb;
                     T x0 = T(0), x1 = T(0);
                     if (f < kd) {
-                        const Vec x2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(f) * stride + lr * sizeof(T));
+                        const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
                         x0 = x2.x;
                         x1 = x2.y;
                     } else if (f == kd && p.intercept) {
@@ -285,12 +372,56 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramPar
 #pragma unroll
                     for (int bj = bi; bj < KB; ++bj) {
                         dmma_m8n8k4(acc[idx][0], acc[idx][1], f0[bi], f0[bj]);
-                        dmma_m8n8k4(acc[idx][0], acc[idx][1], f1[bi], f1[bj]);
+                        if (DUAL) dmma_m8n8k4(acc2[idx][0], acc2[idx][1], f1[bi], f1[bj]);
+                        else dmma_m8n8k4(acc[idx][0], acc[idx][1], f1[bi], f1[bj]);
                         ++idx;
                     }
                     cy[bi] = fma(f0[bi], y0, cy[bi]);
                     cy[bi] = fma(f1[bi], y1, cy[bi]);
                 }
+            };
+
+            const int noct = (hi + 7) >> 3;
+            if (!plain) {
+                for (int j = 0; j < noct; ++j) masked_octet(j);
+            } else {
+                int j = 0;
+                if (o != 0) {
+                    masked_octet(0);
+                    j = 1;
+                }
+                const int jfull = hi >> 3;  // octets [j, jfull) lie entirely inside [o, hi)
+#pragma unroll 4
+                for (; j < jfull; ++j) {
+                    const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
+                    double f0[KB], f1[KB];
+#pragma unroll
+                    for (int bk = 0; bk < KB; ++bk) {
+                        const int f = 8 * bk + fb;
+                        if (f < kd) {
+                            const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
+                            f0[bk] = static_cast<double>(x2.x);
+                            f1[bk] = static_cast<double>(x2.y);
+                        } else {
+                            f0[bk] = f1[bk] = (f == kd && p.intercept) ? 1.0 : 0.0;
+                        }
+                    }
+                    const double y0 = static_cast<double>(y2.x), y1 = static_cast<double>(y2.y);
+                    int idx = 0;
+#pragma unroll
+                    for (int bi = 0; bi < KB; ++bi) {
+#pragma unroll
+                        for (int bj = bi; bj < KB; ++bj) {
+                            dmma_m8n8k4(acc[idx][0], acc[idx][1], f0[bi], f0[bj]);
+                            if (DUAL) dmma_m8n8k4(acc2[idx][0], acc2[idx][1], f1[bi], f1[bj]);
+                        else dmma_m8n8k4(acc[idx][0], acc[idx][1], f1[bi], f1[bj]);
+                            ++idx;
+                        }
+                        cy[bi] = fma(f0[bi], y0, cy[bi]);
+                        cy[bi] = fma(f1[bi], y1, cy[bi]);
+                    }
+                }
+                if (j < noct) masked_octet(j);
             }
             __syncwarp();
             issue();  // refill the stage we just drained
@@ -299,6 +430,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramPar
                 phase ^= 1u;
             }
         }
+#pragma unroll
+        for (int i = 0; i < (DUAL ? NPAIR : 0); ++i) {
+            acc[i][0] += acc2[i][0];
+            acc[i][1] += acc2[i][1];
+        }
+        if (plain) nfit = (lane == 0) ? static_cast<int>(r1 - r0) : 0;
 
         gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane);
     }

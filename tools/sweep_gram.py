@@ -24,7 +24,7 @@ step = eng.prepare_least_squares(batch, kw, L.COEFFICIENTS, coef)
 res = []
 alg = bench.G * bench.ALG_BYTES_PER_REGRESSION
 configs = [(0, 0, t, w, c) for t, w, c in itertools.product([32, 64, 96, 128, 192, 256], [4, 6, 8, 12, 16], [1, 2])]
-configs += [(1, u, 0, w, c) for u, w, c in itertools.product([2, 4, 8], [4, 8, 16], [1, 2, 3, 4]) if w * c <= 64]
+configs += [(1, u, 0, w, c) for u, w, c in itertools.product([1, 2, 4, 8], [4, 8], [1, 2, 3, 4, 6, 8]) if w * c <= 64]
 for variant, unroll, tile, warps, cps in configs:
     try:
         eng.set_variant(variant, unroll)
