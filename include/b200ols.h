@@ -177,8 +177,10 @@ B200OLS_API int b200ols_profile_drain(b200ols_ctx *ctx, float *ms, int max);
 /* tuning knobs (0 = default): rows per shared-memory tile and consumer warps per CTA of the
  * row-streaming Gram kernel */
 B200OLS_API int b200ols_set_tuning(b200ols_ctx *ctx, int tile_rows, int warps_per_cta, int ctas_per_sm);
-/* Gram kernel variant: 0 = TMA-staged shared-memory pipeline (default), 1 = direct 16-byte global loads
- * (k <= 16 only; `unroll` row octets in flight per lane, 0 = default) */
+/* Gram kernel variant: 0 = TMA-staged shared-memory pipeline + DMMA, 1 = direct 16-byte global loads +
+ * DMMA (k <= 16), 2 = direct loads + FP64 FMA, one row per lane (k <= 8).  `unroll` = row blocks in flight
+ * per lane (0 = default).  Variants that do not cover a shape fall back to variant 0.
+ * The environment variable B200OLS_VARIANT sets the initial variant of new contexts (test hook). */
 B200OLS_API int b200ols_set_variant(b200ols_ctx *ctx, int variant, int unroll);
 
 /* ---- the six entry points (one per reference plugin symbol), batched over groups ------------------ */

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -18,6 +19,7 @@
 
 #include "../../include/b200ols.h"
 #include "gram_ldg.cuh"
+#include "gram_simt.cuh"
 #include "gram_stream.cuh"
 #include "moving.cuh"
 #include "predict.cuh"
@@ -180,6 +182,8 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
+    if (const char *v = std::getenv("B200OLS_VARIANT")) c->variant = std::atoi(v);  // test hook: force a Gram kernel variant
+    if (c->variant < 0 || c->variant > 2) c->variant = 0;
     *out = c;
     return 0;
 }
@@ -250,7 +254,8 @@ extern "C" int b200ols_set_tuning(b200ols_ctx *c, int tile_rows, int warps_per_c
 
 extern "C" int b200ols_set_variant(b200ols_ctx *c, int variant, int unroll) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
-    if (variant < 0 || variant > 1) return fail(B200OLS_ERR_INVALID, "variant must be 0 (TMA-staged) or 1 (direct loads)");
+    if (variant < 0 || variant > 2)
+        return fail(B200OLS_ERR_INVALID, "variant must be 0 (TMA-staged DMMA), 1 (direct-load DMMA) or 2 (direct-load FMA, k <= 8)");
     c->variant = variant;
     c->unroll = unroll;
     return 0;
@@ -546,6 +551,19 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     const int F = gp.F;
     const int KB = (F + 7) / 8;
     const int NC = gp.kd + 1 + gp.has_w + gp.has_mask;
+    if (c->variant == 2 && KB == 1) {  // direct-load FP64-FMA variant (k <= 8)
+        int warps = std::min(c->warps_per_cta > 0 ? c->warps_per_cta : 8, 16);
+        const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 2;
+        int64_t grid = std::min<int64_t>(static_cast<int64_t>(c->sm_count) * ctas, (gp.nseg + warps - 1) / warps);
+        grid = std::max<int64_t>(grid, 1);
+        const int U = c->unroll > 0 ? c->unroll : 1;
+        if (U > 1) warps = std::min(warps, 8);
+        ProfScope prof(c);
+        CU(sizeof(T) == 8 ? gram_simt_launch_f64(U, gp, static_cast<unsigned>(grid), warps, c->stream)
+                          : gram_simt_launch_f32(U, gp, static_cast<unsigned>(grid), warps, c->stream));
+        c->launches++;
+        return 0;
+    }
     if (c->variant == 1 && KB <= 2) {  // direct-load variant
         int warps = std::min(c->warps_per_cta > 0 ? c->warps_per_cta : 8, 8);
         const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 3;
@@ -568,8 +586,10 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         return (static_cast<size_t>(s) * NC * gram_col_stride<T>(r) + gram_scratch_bytes<T>(F, gp.fused)) * w;
     };
     while (need(R, S, warps) > budget) {
-        if (R > 16) R -= 8;
+        if (S > 3) --S;
+        else if (R > 64) R -= 8;
         else if (S > 2) --S;
+        else if (R > 16) R -= 8;
         else if (warps > 1) --warps;
         else return fail(B200OLS_ERR_UNSUPPORTED, "Gram tile does not fit in shared memory (%d columns)", NC);
     }

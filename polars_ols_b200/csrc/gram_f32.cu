@@ -1,5 +1,6 @@
 // gram_f32.cu — f32-input instantiations of the row-streaming Gram kernel (see gram_stream.cuh)
 #include "gram_ldg.cuh"
+#include "gram_simt.cuh"
 #include "gram_stream.cuh"
 namespace b200 {
 cudaError_t gram_launch_f32(int KB, const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s) {
@@ -7,5 +8,8 @@ cudaError_t gram_launch_f32(int KB, const GramParams &p, unsigned grid, int warp
 }
 cudaError_t gram_ldg_launch_f32(int KB, int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
     return gram_ldg_launch_any<float>(KB, U, p, grid, warps, s);
+}
+cudaError_t gram_simt_launch_f32(int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
+    return gram_simt_launch_any<float>(U, p, grid, warps, s);
 }
 }  // namespace b200

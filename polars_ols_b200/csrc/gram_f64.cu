@@ -1,5 +1,6 @@
 // gram_f64.cu — f64 instantiations of the row-streaming Gram kernel (see gram_stream.cuh)
 #include "gram_ldg.cuh"
+#include "gram_simt.cuh"
 #include "gram_stream.cuh"
 namespace b200 {
 cudaError_t gram_launch_f64(int KB, const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s) {
@@ -7,5 +8,8 @@ cudaError_t gram_launch_f64(int KB, const GramParams &p, unsigned grid, int warp
 }
 cudaError_t gram_ldg_launch_f64(int KB, int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
     return gram_ldg_launch_any<double>(KB, U, p, grid, warps, s);
+}
+cudaError_t gram_simt_launch_f64(int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
+    return gram_simt_launch_any<double>(U, p, grid, warps, s);
 }
 }  // namespace b200

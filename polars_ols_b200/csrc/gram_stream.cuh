@@ -130,6 +130,64 @@ __device__ __forceinline__ bool warp_chol_solve(double (&g)[FP], double &c, int 
     return true;
 }
 
+// Second half of the epilogue: the per-warp scratch holds the symmetric Gram matrix (row stride FP + 1)
+// followed by X^T y.  Fused mode: solve and write beta; otherwise (direct-FMA kernel only) dump the raw
+// partial record for the standalone solve kernel.  nfit must be warp-uniform.
+template <int KB>
+__device__ __forceinline__ void gram_finish(const GramParams &p, int nfit, int64_t seg, double *Gs, int lane) {
+    constexpr int FP = 8 * KB;
+    constexpr int LD = FP + 1;
+    const int F = p.F;
+    double *cs = Gs + FP * LD;
+    const int64_t g = p.seg_group ? p.seg_group[seg] : seg;
+    if (!p.fused) {
+        double *out = p.partial + static_cast<size_t>(seg) * (static_cast<size_t>(F) * F + F + 1);
+        for (int e = lane; e < F * F; e += 32) out[e] = Gs[(e / F) * LD + (e % F)];
+        if (lane < F) out[F * F + lane] = cs[lane];
+        if (lane == 0) out[F * F + F] = static_cast<double>(nfit);
+        __syncwarp();
+        return;
+    }
+    // lane i takes row i of the (ridge) matrix and c_i into registers
+    double grow[FP];
+    const int li = (lane < FP) ? lane : 0;
+#pragma unroll
+    for (int c = 0; c < FP; ++c) grow[c] = Gs[li * LD + c];
+    double ci = (lane < FP) ? cs[lane] : 0.0;
+#pragma unroll
+    for (int c = 0; c < FP; ++c)
+        if (c == lane && lane < F) grow[c] += p.alpha;  // + alpha I, NOT scaled by n (src/least_squares.rs:352-356)
+    int fl = 0;
+    if (nfit == 0) {  // src/expressions.rs:357-359: no rows -> zeros
+        ci = 0.0;
+        fl = FLAG_EMPTY;
+    } else {
+        bool solved = false;
+        if (!p.use_lu) {
+            double mn, mx;
+            const bool ok = warp_chol_solve<FP>(grow, ci, F, lane, mn, mx);
+            if (ok) {
+                solved = true;
+                if (mx > p.illcond_ratio * mn) fl |= FLAG_ILLCOND;
+            } else {
+                fl |= FLAG_LU_FALLBACK;
+            }
+        }
+        if (!solved) {  // "lu", or Cholesky hit a non-positive pivot: LU with partial pivoting (rare; lane 0)
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < F; ++i) Gs[i * LD + i] += p.alpha;
+                lu_solve_inplace(Gs, LD, F, cs);
+            }
+            __syncwarp();
+            ci = (lane < FP) ? cs[lane] : 0.0;
+        }
+    }
+    if (lane == 0) p.flags[g] = fl;
+    if (lane < F) p.beta[g * F + lane] = ci;
+    __syncwarp();
+}
+
 // Epilogue shared by the TMA-staged and the direct-load kernels: reduce X^T y over the 4 lanes that share
 // a feature, then either solve in shared memory (fused) or write the raw Gram partial.
 template <int KB>
@@ -169,44 +227,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams &p, double (&acc)
             if (q == 0) cs[8 * bi + fb] = cy[bi];
         }
         __syncwarp();
-        // lane i takes row i of the (ridge) matrix and c_i into registers
-        double grow[FP];
-        const int li = (lane < FP) ? lane : 0;
-#pragma unroll
-        for (int c = 0; c < FP; ++c) grow[c] = Gs[li * LD + c];
-        double ci = (lane < FP) ? cs[lane] : 0.0;
-#pragma unroll
-        for (int c = 0; c < FP; ++c)
-            if (c == lane && lane < F) grow[c] += p.alpha;  // + alpha I, NOT scaled by n (src/least_squares.rs:352-356)
-        int fl = 0;
-        if (nfit == 0) {  // src/expressions.rs:357-359: no rows -> zeros
-            ci = 0.0;
-            fl = FLAG_EMPTY;
-        } else {
-            bool solved = false;
-            if (!p.use_lu) {
-                double mn, mx;
-                const bool ok = warp_chol_solve<FP>(grow, ci, F, lane, mn, mx);
-                if (ok) {
-                    solved = true;
-                    if (mx > p.illcond_ratio * mn) fl |= FLAG_ILLCOND;
-                } else {
-                    fl |= FLAG_LU_FALLBACK;
-                }
-            }
-            if (!solved) {  // "lu", or Cholesky hit a non-positive pivot: LU with partial pivoting (rare; lane 0)
-                __syncwarp();
-                if (lane == 0) {
-                    for (int i = 0; i < F; ++i) Gs[i * LD + i] += p.alpha;
-                    lu_solve_inplace(Gs, LD, F, cs);
-                }
-                __syncwarp();
-                ci = (lane < FP) ? cs[lane] : 0.0;
-            }
-        }
-        if (lane == 0) p.flags[g] = fl;
-        if (lane < F) p.beta[g * F + lane] = ci;
-        __syncwarp();
+        gram_finish<KB>(p, nfit, seg, Gs, lane);
     } else {
         double *out = p.partial + static_cast<size_t>(seg) * (static_cast<size_t>(F) * F + F + 1);
         int idx = 0;

@@ -23,8 +23,9 @@ batch = pls.Batch(pls.Col(yd), [pls.Col(xd[i]) for i in range(bench.K)], offsets
 step = eng.prepare_least_squares(batch, kw, L.COEFFICIENTS, coef)
 res = []
 alg = bench.G * bench.ALG_BYTES_PER_REGRESSION
-configs = [(0, 0, t, w, c) for t, w, c in itertools.product([32, 64, 96, 128, 192, 256], [4, 6, 8, 12, 16], [1, 2])]
-configs += [(1, u, 0, w, c) for u, w, c in itertools.product([1, 2, 4, 8], [4, 8], [1, 2, 3, 4, 6, 8]) if w * c <= 64]
+configs = [(0, 0, t, w, c) for t, w, c in itertools.product([64, 128, 256], [4, 6, 8, 12], [1, 2])]
+configs += [(1, u, 0, w, c) for u, w, c in itertools.product([1, 2], [8], [2, 3, 4])]
+configs += [(2, u, 0, w, c) for u, w, c in itertools.product([1, 2, 4], [4, 8, 16], [1, 2, 3, 4]) if not (u > 1 and w > 8) and w * c <= 32]
 for variant, unroll, tile, warps, cps in configs:
     try:
         eng.set_variant(variant, unroll)
@@ -45,5 +46,5 @@ Path(a.out).parent.mkdir(exist_ok=True)
 Path(a.out).write_text(json.dumps(res, indent=1))
 best = min((r for r in res if "ms" in r), key=lambda r: r["ms"])
 print("BEST", best)
-for v in (0, 1):
+for v in (0, 1, 2):
     print("BEST variant", v, min((r for r in res if "ms" in r and r["variant"] == v), key=lambda r: r["ms"]))
