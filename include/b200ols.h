@@ -178,7 +178,8 @@ B200OLS_API int b200ols_profile_drain(b200ols_ctx *ctx, float *ms, int max);
  * row-streaming Gram kernel */
 B200OLS_API int b200ols_set_tuning(b200ols_ctx *ctx, int tile_rows, int warps_per_cta, int ctas_per_sm);
 /* Gram kernel variant: 0 = TMA-staged shared-memory pipeline + DMMA, 1 = direct 16-byte global loads +
- * DMMA (k <= 16), 2 = direct loads + FP64 FMA, one row per lane (k <= 8).  `unroll` = row blocks in flight
+ * DMMA (k <= 16), 2 = direct loads + FP64 FMA, one row per lane (k <= 8), 3 = CTA-cooperative
+ * warp-specialised TMA pipeline (producer / 8 consumer / solver warps, k <= 16).  `unroll` = row blocks in flight
  * per lane (0 = default).  Variants that do not cover a shape fall back to variant 0.
  * The environment variable B200OLS_VARIANT sets the initial variant of new contexts (test hook). */
 B200OLS_API int b200ols_set_variant(b200ols_ctx *ctx, int variant, int unroll);

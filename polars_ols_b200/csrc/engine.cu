@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/b200ols.h"
+#include "gram_cta.cuh"
 #include "gram_ldg.cuh"
 #include "gram_simt.cuh"
 #include "gram_stream.cuh"
@@ -183,7 +184,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
         c->own_stream = true;
     }
     if (const char *v = std::getenv("B200OLS_VARIANT")) c->variant = std::atoi(v);  // test hook: force a Gram kernel variant
-    if (c->variant < 0 || c->variant > 2) c->variant = 0;
+    if (c->variant < 0 || c->variant > 3) c->variant = 0;
     *out = c;
     return 0;
 }
@@ -254,8 +255,8 @@ extern "C" int b200ols_set_tuning(b200ols_ctx *c, int tile_rows, int warps_per_c
 
 extern "C" int b200ols_set_variant(b200ols_ctx *c, int variant, int unroll) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
-    if (variant < 0 || variant > 2)
-        return fail(B200OLS_ERR_INVALID, "variant must be 0 (TMA-staged DMMA), 1 (direct-load DMMA) or 2 (direct-load FMA, k <= 8)");
+    if (variant < 0 || variant > 3)
+        return fail(B200OLS_ERR_INVALID, "variant must be 0 (per-warp TMA DMMA), 1 (direct-load DMMA), 2 (direct-load FMA, k <= 8) or 3 (CTA-cooperative TMA DMMA)");
     c->variant = variant;
     c->unroll = unroll;
     return 0;
@@ -551,6 +552,29 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     const int F = gp.F;
     const int KB = (F + 7) / 8;
     const int NC = gp.kd + 1 + gp.has_w + gp.has_mask;
+    if (c->variant == 3 && KB <= 2) {  // CTA-cooperative warp-specialised TMA pipeline (k <= 16)
+        const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
+        const size_t fixed = cta_fixed_smem<T>(KB, F);
+        int R = c->tile_rows > 0 ? c->tile_rows : 512;
+        int S = 0;
+        for (;;) {
+            const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(R);
+            S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, (budget - fixed) / sb));
+            if (S >= 2 || R <= 16) break;
+            R -= 8;
+        }
+        if (S < 2) return fail(B200OLS_ERR_UNSUPPORTED, "Gram tile does not fit in shared memory (%d columns)", NC);
+        if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));  // sweep hook: warps_per_cta caps the stages
+        gp.tile_rows = R;
+        gp.stages = S;
+        const size_t smem = static_cast<size_t>(S) * NC * gram_col_stride<T>(R) + fixed;
+        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, gp.nseg));
+        ProfScope prof(c);
+        CU(sizeof(T) == 8 ? gram_cta_launch_f64(KB, gp, static_cast<unsigned>(grid), smem, c->stream)
+                          : gram_cta_launch_f32(KB, gp, static_cast<unsigned>(grid), smem, c->stream));
+        c->launches++;
+        return 0;
+    }
     if (c->variant == 2 && KB == 1) {  // direct-load FP64-FMA variant (k <= 8)
         int warps = std::min(c->warps_per_cta > 0 ? c->warps_per_cta : 8, 16);
         const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 2;

@@ -1,0 +1,287 @@
+// gram_cta.cuh — CTA-cooperative, warp-specialised row-streaming Gram + solve kernel (k <= 16).
+//
+// The canonical Blackwell pipeline shape (producer / consumer / epilogue roles around mbarrier rings),
+// applied to an HBM-bound f64 problem:
+//   warp 0            PRODUCER : waits for a free stage, then every column slice of the next row tile of
+//                                the current segment is fetched by ONE 1-D bulk async copy
+//                                (cp.async.bulk -> UBLKCP, the TMA engine) — k+1(+w)(+mask) copies of up to
+//                                ~8 KB each per tile — completion counted on the stage's `full` mbarrier;
+//   warps 1..W        CONSUMERS: wait on `full`, split the tile's row octets between them, feed
+//                                mma.sync.m8n8k4.f64 (DMMA) with 16-byte LDS fragments (A = X^T tile and
+//                                B = X tile are the same register), release the stage on `empty`; at the
+//                                end of a segment each publishes its accumulator fragments in a
+//                                double-buffered shared-memory slot (`red_full` / `red_empty` mbarriers);
+//   warp W+1          SOLVER   : sums the W partial fragments in a fixed order (deterministic), runs the
+//                                warp-cooperative register Cholesky (LU fallback) of gram_stream.cuh and
+//                                writes beta — overlapped with the consumers' next segment.
+// One persistent CTA per SM; the unit of scheduling is the SM, so 10k groups spread over 148 SMs with
+// < 1 % imbalance (a warp-per-group mapping quantises at 2.8 groups per warp), and up to STAGES whole
+// tiles (~200 KB) are in flight per SM irrespective of occupancy or register pressure.
+#pragma once
+#include "gram_stream.cuh"
+
+namespace b200 {
+
+constexpr int CTA_CONSUMERS = 8;
+constexpr int CTA_THREADS = (CTA_CONSUMERS + 2) * 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KB>
+__host__ __device__ constexpr int cta_red_doubles() { return KB * (KB + 1) + KB + 1; }  // acc frags, cy, nfit
+
+template <typename T>
+__host__ __device__ inline size_t cta_fixed_smem(int KB, int F) {
+    const size_t red = static_cast<size_t>(2) * CTA_CONSUMERS * 32 * (KB * (KB + 1) + KB + 1) * sizeof(double);
+    return red + gram_scratch_bytes<T>(F, 1) + 128;
+}
+
+template <typename T, int KB>
+__global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramParams p) {
+    using Vec = typename V2<T>::type;
+    constexpr int NPAIR = KB * (KB + 1) / 2;
+    constexpr int A = 16 / sizeof(T);
+    constexpr int W = CTA_CONSUMERS;
+    constexpr int RED = cta_red_doubles<KB>();
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES], red_full[2], red_empty[2];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fb = lane >> 2, q = lane & 3;
+    const int kd = p.kd, F = p.F;
+    const int ycol = kd, wcol = kd + 1, mcol = kd + 1 + (p.has_w ? 1 : 0);
+    const int NC = kd + 1 + (p.has_w ? 1 : 0) + (p.has_mask ? 1 : 0);
+    const int R = p.tile_rows, S = p.stages;
+    const uint32_t stride = gram_col_stride<T>(R);
+    const uint32_t stage_bytes = static_cast<uint32_t>(NC) * stride;
+    double *red = reinterpret_cast<double *>(smem + static_cast<size_t>(S) * stage_bytes);
+    double *Gs = red + 2 * W * 32 * RED;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], W);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&red_full[b], W);
+            mbar_init(&red_empty[b], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t nseg = p.nseg;
+    const bool plain = !p.has_mask && !p.has_w;
+
+    if (warp == 0) {
+        // ================================ PRODUCER ================================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+            const int64_t r0 = p.seg_off[seg], r1 = p.seg_off[seg + 1];
+            for (int64_t row = r0; row < r1; row += R) {
+                const int64_t b = (row + R < r1) ? row + R : r1;
+                const int64_t a_al = row & ~static_cast<int64_t>(A - 1);
+                int64_t b_al = (b + (A - 1)) & ~static_cast<int64_t>(A - 1);
+                if (b_al > p.n_rows_pad) b_al = p.n_rows_pad;
+                const uint32_t bytes = static_cast<uint32_t>(b_al - a_al) * sizeof(T);
+                mbar_wait(&empty_bar[stage], phase ^ 1u);  // all consumers released this stage
+                unsigned char *sb = smem + static_cast<size_t>(stage) * stage_bytes;
+                if (lane == 0) {
+                    fence_proxy_async_smem();
+                    mbar_arrive_expect_tx(&full_bar[stage], bytes * static_cast<uint32_t>(NC));
+                }
+                __syncwarp();
+                for (int c = lane; c < NC; c += 32)
+                    bulk_g2s(sb + static_cast<size_t>(c) * stride, static_cast<const T *>(p.cols[c]) + a_al, bytes,
+                             &full_bar[stage]);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp <= W) {
+        // ================================ CONSUMERS ================================
+        const int cw = warp - 1;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t red_i = 0;
+        for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+            const int64_t r0 = p.seg_off[seg], r1 = p.seg_off[seg + 1];
+            constexpr bool DUAL = KB <= 2;
+            double acc[NPAIR][2], acc2[DUAL ? NPAIR : 1][2];
+            double cy[KB];
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < (DUAL ? NPAIR : 1); ++i) acc2[i][0] = acc2[i][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < KB; ++i) cy[i] = 0.0;
+            int nfit = 0;
+
+            for (int64_t row = r0; row < r1; row += R) {
+                const int64_t b = (row + R < r1) ? row + R : r1;
+                const int o = static_cast<int>(row & (A - 1));
+                const int hi = o + static_cast<int>(b - row);  // valid local rows are [o, hi)
+                const int noct = (hi + 7) >> 3;
+                const int per = (noct + W - 1) / W;
+                const int j0 = cw * per;
+                const int j1 = (j0 + per < noct) ? j0 + per : noct;
+                mbar_wait(&full_bar[stage], phase);
+                const unsigned char *sb = smem + static_cast<size_t>(stage) * stage_bytes;
+                const unsigned char *xs[KB];
+#pragma unroll
+                for (int bk = 0; bk < KB; ++bk)
+                    xs[bk] = sb + static_cast<size_t>((8 * bk + fb < kd) ? 8 * bk + fb : 0) * stride + 2 * q * sizeof(T);
+                const unsigned char *ys = sb + static_cast<size_t>(ycol) * stride + 2 * q * sizeof(T);
+                bool has_x[KB];
+                double xconst[KB];
+#pragma unroll
+                for (int bk = 0; bk < KB; ++bk) {
+                    has_x[bk] = 8 * bk + fb < kd;
+                    xconst[bk] = ((8 * bk + fb == kd) && p.intercept) ? 1.0 : 0.0;
+                }
+
+                auto mma_octet = [&](const double (&f0)[KB], const double (&f1)[KB], double y0, double y1) {
+                    int idx = 0;
+#pragma unroll
+                    for (int bi = 0; bi < KB; ++bi) {
+#pragma unroll
+                        for (int bj = bi; bj < KB; ++bj) {
+                            dmma_m8n8k4(acc[idx][0], acc[idx][1], f0[bi], f0[bj]);
+                            if (DUAL) dmma_m8n8k4(acc2[idx][0], acc2[idx][1], f1[bi], f1[bj]);
+                            else dmma_m8n8k4(acc[idx][0], acc[idx][1], f1[bi], f1[bj]);
+                            ++idx;
+                        }
+                        cy[bi] = fma(f0[bi], y0, cy[bi]);
+                        cy[bi] = fma(f1[bi], y1, cy[bi]);
+                    }
+                };
+                auto masked_octet = [&](int j) {
+                    const int lr = 8 * j + 2 * q;
+                    bool v0 = (lr >= o) && (lr < hi);
+                    bool v1 = (lr + 1 >= o) && (lr + 1 < hi);
+                    const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
+                    T s0 = T(1), s1 = T(1);
+                    if (p.has_mask) {
+                        const Vec m2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(mcol) * stride + lr * sizeof(T));
+                        v0 = v0 && (m2.x != T(0));
+                        v1 = v1 && (m2.y != T(0));
+                    }
+                    if (p.has_w) {
+                        const Vec w2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(wcol) * stride + lr * sizeof(T));
+                        s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
+                        s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                    }
+                    const double y0 = v0 ? static_cast<double>(static_cast<T>(y2.x * s0)) : 0.0;
+                    const double y1 = v1 ? static_cast<double>(static_cast<T>(y2.y * s1)) : 0.0;
+                    if (fb == 0) nfit += (v0 ? 1 : 0) + (v1 ? 1 : 0);
+                    double f0[KB], f1[KB];
+#pragma unroll
+                    for (int bk = 0; bk < KB; ++bk) {
+                        const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
+                        const T x0 = has_x[bk] ? x2.x : static_cast<T>(xconst[bk]);
+                        const T x1 = has_x[bk] ? x2.y : static_cast<T>(xconst[bk]);
+                        f0[bk] = v0 ? static_cast<double>(static_cast<T>(x0 * s0)) : 0.0;
+                        f1[bk] = v1 ? static_cast<double>(static_cast<T>(x1 * s1)) : 0.0;
+                    }
+                    mma_octet(f0, f1, y0, y1);
+                };
+
+                if (!plain) {
+                    for (int j = j0; j < j1; ++j) masked_octet(j);
+                } else {
+                    int j = j0;
+                    if (j < j1 && j == 0 && o != 0) {
+                        masked_octet(0);
+                        j = 1;
+                    }
+                    const int jfull = hi >> 3;  // octets below jfull lie entirely inside [o, hi)
+                    const int jend = (j1 < jfull) ? j1 : jfull;
+#pragma unroll 4
+                    for (; j < jend; ++j) {
+                        const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
+                        double f0[KB], f1[KB];
+#pragma unroll
+                        for (int bk = 0; bk < KB; ++bk) {
+                            const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
+                            f0[bk] = has_x[bk] ? static_cast<double>(x2.x) : xconst[bk];
+                            f1[bk] = has_x[bk] ? static_cast<double>(x2.y) : xconst[bk];
+                        }
+                        mma_octet(f0, f1, static_cast<double>(y2.x), static_cast<double>(y2.y));
+                    }
+                    for (; j < j1; ++j) masked_octet(j);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            // ---- publish this warp's partial fragments ----
+            const int buf = red_i & 1;
+            mbar_wait(&red_empty[buf], ((red_i >> 1) & 1u) ^ 1u);
+            double *slot = red + (static_cast<size_t>(buf) * W + cw) * 32 * RED;
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) {
+                slot[(2 * i) * 32 + lane] = DUAL ? acc[i][0] + acc2[i][0] : acc[i][0];
+                slot[(2 * i + 1) * 32 + lane] = DUAL ? acc[i][1] + acc2[i][1] : acc[i][1];
+            }
+#pragma unroll
+            for (int i = 0; i < KB; ++i) slot[(2 * NPAIR + i) * 32 + lane] = cy[i];
+            slot[(2 * NPAIR + KB) * 32 + lane] = static_cast<double>(nfit);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&red_full[buf]);
+            ++red_i;
+        }
+    } else {
+        // ================================ SOLVER ================================
+        uint32_t red_i = 0;
+        for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+            const int buf = red_i & 1;
+            mbar_wait(&red_full[buf], (red_i >> 1) & 1u);
+            double acc[NPAIR][2], cy[KB];
+            double nf = 0.0;
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < KB; ++i) cy[i] = 0.0;
+            for (int cw = 0; cw < W; ++cw) {  // fixed order: deterministic sums
+                const double *slot = red + (static_cast<size_t>(buf) * W + cw) * 32 * RED;
+#pragma unroll
+                for (int i = 0; i < NPAIR; ++i) {
+                    acc[i][0] += slot[(2 * i) * 32 + lane];
+                    acc[i][1] += slot[(2 * i + 1) * 32 + lane];
+                }
+#pragma unroll
+                for (int i = 0; i < KB; ++i) cy[i] += slot[(2 * NPAIR + i) * 32 + lane];
+                nf += slot[(2 * NPAIR + KB) * 32 + lane];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&red_empty[buf]);
+            int nfit = static_cast<int>(nf);
+            if (plain) nfit = (lane == 0) ? static_cast<int>(p.seg_off[seg + 1] - p.seg_off[seg]) : 0;
+            gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane);
+            ++red_i;
+        }
+    }
+}
+
+template <typename T, int KB>
+cudaError_t gram_cta_launch_t(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    auto kern = gram_cta_kernel<T, KB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<grid, CTA_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t gram_cta_launch_f64(int KB, const GramParams &p, unsigned grid, size_t smem, cudaStream_t s);
+cudaError_t gram_cta_launch_f32(int KB, const GramParams &p, unsigned grid, size_t smem, cudaStream_t s);
+
+}  // namespace b200

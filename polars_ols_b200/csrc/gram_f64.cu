@@ -1,4 +1,5 @@
 // gram_f64.cu — f64 instantiations of the row-streaming Gram kernel (see gram_stream.cuh)
+#include "gram_cta.cuh"
 #include "gram_ldg.cuh"
 #include "gram_simt.cuh"
 #include "gram_stream.cuh"
@@ -11,5 +12,8 @@ cudaError_t gram_ldg_launch_f64(int KB, int U, const GramParams &p, unsigned gri
 }
 cudaError_t gram_simt_launch_f64(int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
     return gram_simt_launch_any<double>(U, p, grid, warps, s);
+}
+cudaError_t gram_cta_launch_f64(int KB, const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    return KB == 1 ? gram_cta_launch_t<double, 1>(p, grid, smem, s) : gram_cta_launch_t<double, 2>(p, grid, smem, s);
 }
 }  // namespace b200

@@ -23,7 +23,8 @@ batch = pls.Batch(pls.Col(yd), [pls.Col(xd[i]) for i in range(bench.K)], offsets
 step = eng.prepare_least_squares(batch, kw, L.COEFFICIENTS, coef)
 res = []
 alg = bench.G * bench.ALG_BYTES_PER_REGRESSION
-configs = [(0, 0, t, w, c) for t, w, c in itertools.product([64, 128, 256], [4, 6, 8, 12], [1, 2])]
+configs = [(3, 0, t, w, 1) for t, w in itertools.product([256, 336, 504, 512, 1000, 1024], [0, 2, 3, 4])]
+configs += [(0, 0, t, w, c) for t, w, c in itertools.product([64, 128, 256], [4, 6, 8, 12], [1, 2])]
 configs += [(1, u, 0, w, c) for u, w, c in itertools.product([1, 2], [8], [2, 3, 4])]
 configs += [(2, u, 0, w, c) for u, w, c in itertools.product([1, 2, 4], [4, 8, 16], [1, 2, 3, 4]) if not (u > 1 and w > 8) and w * c <= 32]
 for variant, unroll, tile, warps, cps in configs:
@@ -46,5 +47,5 @@ Path(a.out).parent.mkdir(exist_ok=True)
 Path(a.out).write_text(json.dumps(res, indent=1))
 best = min((r for r in res if "ms" in r), key=lambda r: r["ms"])
 print("BEST", best)
-for v in (0, 1, 2):
+for v in (0, 1, 2, 3):
     print("BEST variant", v, min((r for r in res if "ms" in r and r["variant"] == v), key=lambda r: r["ms"]))
