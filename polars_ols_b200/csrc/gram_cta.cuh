@@ -11,7 +11,7 @@
 //                                B = X tile are the same register), release the stage on `empty`; at the
 //                                end of a segment each publishes its accumulator fragments in a
 //                                double-buffered shared-memory slot (`red_full` / `red_empty` mbarriers);
-//   warp W+1          SOLVER   : sums the W partial fragments in a fixed order (deterministic), runs the
+//   warps W+1..W+4    SOLVERS  : (round-robin over segments) each sums the W partial fragments in a fixed order (deterministic), runs the
 //                                warp-cooperative register Cholesky (LU fallback) of gram_stream.cuh and
 //                                writes beta — overlapped with the consumers' next segment.
 // One persistent CTA per SM; the unit of scheduling is the SM, so 10k groups spread over 148 SMs with
@@ -23,7 +23,9 @@
 namespace b200 {
 
 constexpr int CTA_CONSUMERS = 8;
-constexpr int CTA_THREADS = (CTA_CONSUMERS + 2) * 32;
+constexpr int CTA_SOLVERS = 4;   // the k x k solve is a long dependent chain: several groups are solved concurrently
+constexpr int CTA_RED_DEPTH = 6; // ring of published partial-fragment buffers (consumers may run this far ahead)
+constexpr int CTA_THREADS = (CTA_CONSUMERS + CTA_SOLVERS + 1) * 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -34,8 +36,8 @@ __host__ __device__ constexpr int cta_red_doubles() { return KB * (KB + 1) + KB 
 
 template <typename T>
 __host__ __device__ inline size_t cta_fixed_smem(int KB, int F) {
-    const size_t red = static_cast<size_t>(2) * CTA_CONSUMERS * 32 * (KB * (KB + 1) + KB + 1) * sizeof(double);
-    return red + gram_scratch_bytes<T>(F, 1) + 128;
+    const size_t red = static_cast<size_t>(CTA_RED_DEPTH) * CTA_CONSUMERS * 32 * (KB * (KB + 1) + KB + 1) * sizeof(double);
+    return red + CTA_SOLVERS * gram_scratch_bytes<T>(F, 1) + 128;
 }
 
 template <typename T, int KB>
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     constexpr int RED = cta_red_doubles<KB>();
 
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES], red_full[2], red_empty[2];
+    __shared__ uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES], red_full[CTA_RED_DEPTH], red_empty[CTA_RED_DEPTH];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fb = lane >> 2, q = lane & 3;
@@ -58,14 +60,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     const uint32_t stride = gram_col_stride<T>(R);
     const uint32_t stage_bytes = static_cast<uint32_t>(NC) * stride;
     double *red = reinterpret_cast<double *>(smem + static_cast<size_t>(S) * stage_bytes);
-    double *Gs = red + 2 * W * 32 * RED;
+    double *Gs_base = red + CTA_RED_DEPTH * W * 32 * RED;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], W);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < CTA_RED_DEPTH; ++b) {
             mbar_init(&red_full[b], W);
             mbar_init(&red_empty[b], 1);
         }
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                 }
             }
             // ---- publish this warp's partial fragments ----
-            const int buf = red_i & 1;
-            mbar_wait(&red_empty[buf], ((red_i >> 1) & 1u) ^ 1u);
+            const int buf = red_i % CTA_RED_DEPTH;
+            mbar_wait(&red_empty[buf], ((red_i / CTA_RED_DEPTH) & 1u) ^ 1u);
             double *slot = red + (static_cast<size_t>(buf) * W + cw) * 32 * RED;
 #pragma unroll
             for (int i = 0; i < NPAIR; ++i) {
@@ -240,11 +242,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
             ++red_i;
         }
     } else {
-        // ================================ SOLVER ================================
-        uint32_t red_i = 0;
-        for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-            const int buf = red_i & 1;
-            mbar_wait(&red_full[buf], (red_i >> 1) & 1u);
+        // ================================ SOLVERS ================================
+        // solver s takes the segments whose CTA-local index is congruent to s (mod CTA_SOLVERS)
+        const int sw = warp - (W + 1);
+        double *Gs = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(Gs_base) + static_cast<size_t>(sw) * gram_scratch_bytes<T>(F, 1));
+        uint32_t red_i = sw;
+        for (int64_t seg = blockIdx.x + static_cast<int64_t>(sw) * gridDim.x; seg < nseg;
+             seg += static_cast<int64_t>(CTA_SOLVERS) * gridDim.x, red_i += CTA_SOLVERS) {
+            const int buf = red_i % CTA_RED_DEPTH;
+            mbar_wait(&red_full[buf], (red_i / CTA_RED_DEPTH) & 1u);
             double acc[NPAIR][2], cy[KB];
             double nf = 0.0;
 #pragma unroll
@@ -267,7 +273,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
             int nfit = static_cast<int>(nf);
             if (plain) nfit = (lane == 0) ? static_cast<int>(p.seg_off[seg + 1] - p.seg_off[seg]) : 0;
             gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane);
-            ++red_i;
         }
     }
 }

@@ -12,6 +12,7 @@ import bench
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default="gpurun_out/sweep.json")
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--variants", default="0,1,2,3")
 a = ap.parse_args()
 x, y, offsets = bench.make_data(0)
 dev = torch.device("cuda", 0)
@@ -27,6 +28,8 @@ configs = [(3, 0, t, w, 1) for t, w in itertools.product([256, 336, 504, 512, 10
 configs += [(0, 0, t, w, c) for t, w, c in itertools.product([64, 128, 256], [4, 6, 8, 12], [1, 2])]
 configs += [(1, u, 0, w, c) for u, w, c in itertools.product([1, 2], [8], [2, 3, 4])]
 configs += [(2, u, 0, w, c) for u, w, c in itertools.product([1, 2, 4], [4, 8, 16], [1, 2, 3, 4]) if not (u > 1 and w > 8) and w * c <= 32]
+VARS = [int(v) for v in a.variants.split(',')]
+configs = [c for c in configs if c[0] in VARS]
 for variant, unroll, tile, warps, cps in configs:
     try:
         eng.set_variant(variant, unroll)
@@ -47,5 +50,5 @@ Path(a.out).parent.mkdir(exist_ok=True)
 Path(a.out).write_text(json.dumps(res, indent=1))
 best = min((r for r in res if "ms" in r), key=lambda r: r["ms"])
 print("BEST", best)
-for v in (0, 1, 2, 3):
+for v in VARS:
     print("BEST variant", v, min((r for r in res if "ms" in r and r["variant"] == v), key=lambda r: r["ms"]))
