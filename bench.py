@@ -266,7 +266,7 @@ def main():
     if tp.exists():
         traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "gram_stream_kernel<double,1> (fused Gram + Cholesky solve)",
+                "traffic": traffic, "kernel": "gram_cta_kernel<double,1> (TMA bulk-copy pipeline + DMMA Gram + fused warp Cholesky solve)",
                 "kernel_ms_avg": k_avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": k_avg_ms * a.steps / ms if ms > 0 else None}
 

@@ -76,7 +76,7 @@ struct b200ols_ctx {
     int smem_optin = 0;
     int64_t launches = 0;
     int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
-    int variant = 0, unroll = 0;  // Gram kernel variant: 0 = TMA-staged, 1 = direct loads
+    int variant = 3, unroll = 0;  // Gram kernel variant (b200ols_set_variant); 3 = CTA-cooperative TMA pipeline
     // bump arena in device memory, reset at the start of every call
     char *arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
@@ -184,7 +184,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
         c->own_stream = true;
     }
     if (const char *v = std::getenv("B200OLS_VARIANT")) c->variant = std::atoi(v);  // test hook: force a Gram kernel variant
-    if (c->variant < 0 || c->variant > 3) c->variant = 0;
+    if (c->variant < 0 || c->variant > 3) c->variant = 3;
     *out = c;
     return 0;
 }
@@ -555,7 +555,10 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     if (c->variant == 3 && KB <= 2) {  // CTA-cooperative warp-specialised TMA pipeline (k <= 16)
         const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
         const size_t fixed = cta_fixed_smem<T>(KB, F);
-        int R = c->tile_rows > 0 ? c->tile_rows : 512;
+        // default tile = the longest segment (whole groups per stage: fewest, largest bulk copies), shrunk until
+        // at least two stages fit
+        int R = c->tile_rows > 0 ? c->tile_rows
+                                 : static_cast<int>(std::min<int64_t>(std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, 64), 4096));
         int S = 0;
         for (;;) {
             const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(R);
@@ -747,6 +750,7 @@ static int run_static(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_
     gp.has_mask = st.mask ? 1 : 0;
     gp.n_rows_pad = st.n_pad;
     gp.nseg = pl.nseg;
+    gp.max_seg_rows = pl.split ? SEG_MAX_ROWS : st.max_group_rows;
     gp.seg_off = pl.seg_off;
     gp.seg_group = pl.seg_group;
     gp.alpha = rt.alpha;

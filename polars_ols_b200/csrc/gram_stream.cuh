@@ -43,6 +43,7 @@ struct GramParams {
     int64_t nseg;
     const int64_t *seg_off;           // [nseg+1] packed row offsets
     const int32_t *seg_group;         // [nseg] group of each segment, or nullptr (segment == group)
+    int64_t max_seg_rows;             // host-side hint: longest segment (tile sizing)
     int tile_rows;                    // R, multiple of 8
     int stages;                       // tiles in flight per warp
     // outputs
