@@ -83,11 +83,20 @@ struct b200ols_ctx {
     bool arena_overflow = false;
     std::vector<void *> retired;  // old arenas, freed after the next synchronise
     // pinned host staging for small metadata (offsets, segment tables)
+    // two halves used by alternating calls; a half is recycled only after the event recorded at the end of the
+    // call that used it has completed (device-memspace calls return before their copies ran)
     char *pinned = nullptr;
-    size_t pinned_cap = 0, pinned_off = 0;
+    size_t pinned_cap = 0, pinned_off = 0, pinned_base = 0;
+    int pinned_half = 0;
+    cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
+    bool pinned_ev_set[2] = {false, false};
     // diagnostics of the last static call
     int32_t *last_flags = nullptr;  // device pointer inside the arena
     int64_t last_flags_n = 0;
+    // last uploaded group-offset table (steady-state loops re-use it instead of re-copying every call)
+    std::vector<int64_t> plan_offsets;
+    int64_t *plan_dev = nullptr;
+    size_t plan_cap = 0;
     // optional device-side timing of the dominant kernel
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
@@ -136,15 +145,47 @@ static U *arena_alloc(b200ols_ctx *c, size_t count) {
         }                                                                                               \
     } while (0)
 
+// `bytes` = end offset needed (c->pinned_off based).  Offsets handed out are absolute inside the buffer.
 static int pinned_reserve(b200ols_ctx *c, size_t bytes) {
-    if (bytes <= c->pinned_cap) return 0;
+    const size_t need = bytes - c->pinned_base;  // bytes needed inside the current half
+    if (need <= c->pinned_cap / 2) return 0;
     CU(cudaStreamSynchronize(c->stream));
-    if (c->pinned) cudaFreeHost(c->pinned);
-    c->pinned = nullptr;
-    c->pinned_cap = 0;
-    size_t cap = std::max(bytes + (bytes >> 1), static_cast<size_t>(4) << 20);
-    CU(cudaMallocHost(reinterpret_cast<void **>(&c->pinned), cap));
-    c->pinned_cap = cap;
+    char *old = c->pinned;
+    const size_t used = c->pinned_off - c->pinned_base;
+    size_t half = std::max(need + (need >> 1), static_cast<size_t>(2) << 20);
+    half = (half + 4095) & ~static_cast<size_t>(4095);
+    char *fresh = nullptr;
+    CU(cudaMallocHost(reinterpret_cast<void **>(&fresh), 2 * half));
+    const size_t new_base = c->pinned_half ? half : 0;
+    if (old && used) std::memcpy(fresh + new_base, old + c->pinned_base, used);
+    if (old) cudaFreeHost(old);
+    c->pinned = fresh;
+    c->pinned_cap = 2 * half;
+    c->pinned_base = new_base;
+    c->pinned_off = new_base + used;
+    c->pinned_ev_set[0] = c->pinned_ev_set[1] = false;  // everything was synchronised above
+    return 0;
+}
+
+// start of a call: switch to the other half of the pinned staging buffer
+static int pinned_begin(b200ols_ctx *c) {
+    c->pinned_half ^= 1;
+    const int h = c->pinned_half;
+    if (c->pinned_ev_set[h]) {
+        CU(cudaEventSynchronize(c->pinned_ev[h]));
+        c->pinned_ev_set[h] = false;
+    }
+    c->pinned_base = h ? c->pinned_cap / 2 : 0;
+    c->pinned_off = c->pinned_base;
+    return 0;
+}
+
+// end of a call: everything staged in this half has been enqueued
+static int pinned_end(b200ols_ctx *c) {
+    const int h = c->pinned_half;
+    if (!c->pinned_ev[h]) CU(cudaEventCreateWithFlags(&c->pinned_ev[h], cudaEventDisableTiming));
+    CU(cudaEventRecord(c->pinned_ev[h], c->stream));
+    c->pinned_ev_set[h] = true;
     return 0;
 }
 
@@ -197,7 +238,10 @@ extern "C" void b200ols_destroy(b200ols_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (void *p : c->retired) cudaFree(p);
     if (c->arena) cudaFree(c->arena);
+    if (c->plan_dev) cudaFree(c->plan_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int h = 0; h < 2; ++h)
+        if (c->pinned_ev[h]) cudaEventDestroy(c->pinned_ev[h]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -490,13 +534,28 @@ static int build_plan(b200ols_ctx *c, const Staged &st, int64_t seg_max, Plan *p
     if (!pl->split) {
         pl->nseg = G;
         const size_t bytes = sizeof(int64_t) * (G + 1);
+        if (c->plan_dev && c->plan_offsets.size() == st.offsets.size() &&
+            std::memcmp(c->plan_offsets.data(), st.offsets.data(), bytes) == 0) {
+            pl->seg_off = c->plan_dev;  // identical grouping as the previous call: table is already on the device
+            return 0;
+        }
+        if (bytes > c->plan_cap) {
+            if (c->plan_dev) c->retired.push_back(c->plan_dev);
+            c->plan_dev = nullptr;
+            c->plan_cap = 0;
+            void *q = nullptr;
+            CU(cudaMalloc(&q, bytes + 4096));
+            c->plan_dev = static_cast<int64_t *>(q);
+            c->plan_cap = bytes + 4096;
+        }
+        c->plan_offsets.clear();  // invalid until the copy below is enqueued
         TRY(pinned_reserve(c, c->pinned_off + bytes + 256));
         char *h = c->pinned + c->pinned_off;
         std::memcpy(h, st.offsets.data(), bytes);
         c->pinned_off += round_up(bytes, 256);
-        int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(G) + 1);
-        CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
-        pl->seg_off = d;
+        CU(cudaMemcpyAsync(c->plan_dev, h, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->plan_offsets = st.offsets;
+        pl->seg_off = c->plan_dev;
         return 0;
     }
     gso.resize(G + 1);
@@ -688,7 +747,7 @@ static int resolve_route(const b200ols_ols_kwargs *kw, StaticRoute *r) {
 static constexpr int64_t SEG_MAX_ROWS = 4096;
 static constexpr double ILLCOND_RATIO = 1.0e7;  // squared-pivot ratio above which OLS is re-solved by QR
 
-static int run_static(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
+static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
     if (!kw || !out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
     TRY(validate_frame(f));
@@ -712,7 +771,7 @@ static int run_static(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_
     bytes += 1 << 20;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
-    c->pinned_off = 0;
+    TRY(pinned_begin(c));
 
     Staged st;
     TRY(stage_frame(c, f, kw->null_policy, false, &st));
@@ -884,6 +943,12 @@ static int run_static(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_
     return 0;
 }
 
+static int run_static(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
+    const int rc = run_static_impl(c, f, kw, mode, out);
+    if (c && c->pinned) pinned_end(c);
+    return rc;
+}
+
 extern "C" int b200ols_least_squares(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode,
                                      b200ols_output *out) {
     if (mode == B200OLS_COEFFICIENTS) return fail(B200OLS_ERR_INVALID, "use b200ols_least_squares_coefficients for mode=coefficients");
@@ -939,8 +1004,8 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     return 0;
 }
 
-static int run_moving(b200ols_ctx *c, const b200ols_frame *f, int kind, const b200ols_rls_kwargs *rk,
-                      const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out) {
+static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, const b200ols_rls_kwargs *rk,
+                           const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
     if (!out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
     TRY(validate_frame(f));
@@ -979,7 +1044,7 @@ static int run_moving(b200ols_ctx *c, const b200ols_frame *f, int kind, const b2
     if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * (static_cast<size_t>(F) * 9 + 16) + 4096;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
-    c->pinned_off = 0;
+    TRY(pinned_begin(c));
     c->last_flags = nullptr;
 
     Staged st;
@@ -1031,6 +1096,13 @@ static int run_moving(b200ols_ctx *c, const b200ols_frame *f, int kind, const b2
         CU(cudaStreamSynchronize(c->stream));
     }
     return 0;
+}
+
+static int run_moving(b200ols_ctx *c, const b200ols_frame *f, int kind, const b200ols_rls_kwargs *rk,
+                      const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out) {
+    const int rc = run_moving_impl(c, f, kind, rk, wk, mode, out);
+    if (c && c->pinned) pinned_end(c);
+    return rc;
 }
 
 extern "C" int b200ols_recursive_least_squares(b200ols_ctx *c, const b200ols_frame *f, const b200ols_rls_kwargs *kw, int mode,
