@@ -1,0 +1,163 @@
+// cd_solve.cuh — elastic-net / lasso coordinate descent on the per-group Gram matrices, warp-cooperative.
+//
+// Restates solve_elastic_net (src/least_squares.rs:386-492 of /root/reference) in its Gram form — the
+// reference's residual-form update  w_j <- S(x_j^T (r + x_j w_j), a l1) / (|x_j|^2 + a (1 - l1))  with
+// q = X^T y - G w maintained incrementally: x_j^T (r + x_j w_j) = q_j + G_jj w_j.  Same cyclic order,
+// alpha * n scaling (:419), active-set pruning (:472-476) and stop rule ||w - w_old||_2 < tol (:436-444)
+// as cd_gram_solve() in solvers.cuh (the host-checked serial version); here a sub-warp of WIDTH lanes
+// owns one group: lane l holds coordinates l, l + WIDTH, .. (q, w, G_ll in registers), G sits in shared
+// memory and each coordinate step is: owner computes the new w_j, one shuffle broadcasts the step
+// delta, every lane updates its q entries from row j of G (conflict-free).  32 / WIDTH groups per warp
+// run concurrently, so the latency-bound sweeps of 100k small groups (C3) overlap.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "small_solve.cuh"
+#include "solvers.cuh"
+
+namespace b200 {
+
+template <int WIDTH, int NPL>
+__global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
+    extern __shared__ __align__(16) unsigned char cd_smem[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int F = p.F;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / WIDTH, sl = lane % WIDTH;          // sub-warp inside the warp, lane inside the sub-warp
+    constexpr int SUBS_PER_WARP = 32 / WIDTH;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int subs_per_block = (blockDim.x >> 5) * SUBS_PER_WARP;
+    double *Gs = reinterpret_cast<double *>(cd_smem) + static_cast<size_t>(warp_in_block * SUBS_PER_WARP + sub) * F * F;
+    const size_t P = static_cast<size_t>(F) * F + F + 1;
+    const bool active_set = p.route == ROUTE_CD_ACTIVE;
+    const bool positive = p.positive != 0;
+    const int64_t n_iters = (p.n_groups + static_cast<int64_t>(gridDim.x) * subs_per_block - 1) / (static_cast<int64_t>(gridDim.x) * subs_per_block);
+
+    for (int64_t it = 0; it < n_iters; ++it) {
+        // every sub-warp of a warp runs the same number of iterations (shuffles need the full warp)
+        const int64_t g = (it * gridDim.x + blockIdx.x) * subs_per_block + warp_in_block * SUBS_PER_WARP + sub;
+        const bool live = g < p.n_groups;
+        const int64_t s0 = live ? (p.group_seg_off ? p.group_seg_off[g] : g) : 0;
+        const int64_t s1 = live ? (p.group_seg_off ? p.group_seg_off[g + 1] : g + 1) : 0;
+        // ---- gather the group's Gram matrix (fixed-order sum over its segments) ----
+        for (int e = sl; e < F * F; e += WIDTH) {
+            double s = 0.0;
+            for (int64_t sg = s0; sg < s1; ++sg) s += p.partial[static_cast<size_t>(sg) * P + e];
+            Gs[e] = s;
+        }
+        double q[NPL], w[NPL], w_old[NPL], gd[NPL];
+        double nfit = 0.0;
+        for (int64_t sg = s0; sg < s1; ++sg) nfit += p.partial[static_cast<size_t>(sg) * P + F * F + F];
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) {
+            const int l = sl + WIDTH * t;
+            double s = 0.0;
+            if (l < F)
+                for (int64_t sg = s0; sg < s1; ++sg) s += p.partial[static_cast<size_t>(sg) * P + F * F + l];
+            q[t] = s;
+            w[t] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) {
+            const int l = sl + WIDTH * t;
+            gd[t] = (l < F) ? Gs[l * F + l] : 1.0;
+        }
+        const double a = p.alpha * nfit;  // alpha *= n_samples (src/least_squares.rs:419)
+        const double l1 = a * p.l1_ratio, l2 = a * (1.0 - p.l1_ratio);
+        // sub-warps diverge freely (different sweep counts / active sets): shuffles use the sub-warp's own mask
+        const unsigned submask = (WIDTH == 32) ? FULL : (((1u << WIDTH) - 1u) << (sub * WIDTH));
+        if (live) {
+            if (nfit == 0.0) {  // src/expressions.rs:357-359: no rows -> zeros
+#pragma unroll
+                for (int t = 0; t < NPL; ++t) {
+                    const int l = sl + WIDTH * t;
+                    if (l < F) p.beta[g * F + l] = 0.0;
+                }
+                if (sl == 0) p.flags[g] = FLAG_EMPTY;
+            } else {
+                uint64_t active = (F >= 64) ? ~0ull : ((1ull << F) - 1ull);
+                for (int64_t sweep = 0; sweep < p.max_iter; ++sweep) {
+#pragma unroll
+                    for (int t = 0; t < NPL; ++t) w_old[t] = w[t];
+                    const uint64_t loop_set = active;  // the reference iterates over a clone of the active list (:459)
+                    for (int j = 0; j < F; ++j) {
+                        if (!((loop_set >> j) & 1ull)) continue;
+                        const int owner = j % WIDTH, tj = j / WIDTH;
+                        double qj = q[0], wj = w[0], gj = gd[0];
+#pragma unroll
+                        for (int t = 1; t < NPL; ++t)
+                            if (t == tj) { qj = q[t]; wj = w[t]; gj = gd[t]; }
+                        const double rho = fma(gj, wj, qj);
+                        const double wn_own = soft_threshold(rho, l1, positive) / (gj + l2);
+                        const double wn = __shfl_sync(submask, wn_own, owner, WIDTH);
+                        const double wo = __shfl_sync(submask, wj, owner, WIDTH);
+                        const double delta = wn - wo;
+                        if (sl == owner) {
+#pragma unroll
+                            for (int t = 0; t < NPL; ++t)
+                                if (t == tj) w[t] = wn;
+                        }
+                        if (delta != 0.0) {
+#pragma unroll
+                            for (int t = 0; t < NPL; ++t) {
+                                const int l = sl + WIDTH * t;
+                                if (l < F) q[t] = fma(-Gs[j * F + l], delta, q[t]);  // G symmetric: row j == column j
+                            }
+                        }
+                        if (active_set && fabs(wn) < p.tol) active &= ~(1ull << j);  // never re-admitted (:472-476)
+                    }
+                    double d2 = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NPL; ++t) {
+                        const double d = w[t] - w_old[t];
+                        d2 = fma(d, d, d2);
+                    }
+#pragma unroll
+                    for (int o = WIDTH / 2; o > 0; o >>= 1) d2 += __shfl_xor_sync(submask, d2, o, WIDTH);
+                    if (sqrt(d2) < p.tol) break;
+                }
+#pragma unroll
+                for (int t = 0; t < NPL; ++t) {
+                    const int l = sl + WIDTH * t;
+                    if (l < F) p.beta[g * F + l] = w[t];
+                }
+                if (sl == 0) p.flags[g] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, int sm_count) {
+    const int F = sp.F;
+    int width, npl;
+    if (F <= 8) { width = 8; npl = 1; }
+    else if (F <= 16) { width = 16; npl = 1; }
+    else if (F <= 32) { width = 32; npl = 1; }
+    else { width = 32; npl = 2; }
+    const int subs_per_warp = 32 / width;
+    const size_t per_sub = static_cast<size_t>(F) * F * sizeof(double);
+    int warps = 4;
+    while (warps > 1 && per_sub * subs_per_warp * warps > 200 * 1024) --warps;
+    const size_t smem = per_sub * subs_per_warp * warps;
+    const int64_t subs_per_block = static_cast<int64_t>(warps) * subs_per_warp;
+    int64_t blocks = (sp.n_groups + subs_per_block - 1) / subs_per_block;
+    const int64_t max_blocks = static_cast<int64_t>(sm_count) * std::max<int64_t>(1, std::min<int64_t>(16, (200 * 1024) / std::max<size_t>(smem, 1)));
+    blocks = std::max<int64_t>(1, std::min(blocks, max_blocks));
+    cudaError_t e = cudaSuccess;
+#define B200_CD_LAUNCH(WD, NP)                                                                                      \
+    e = cudaFuncSetAttribute(cd_solve_kernel<WD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+    if (e == cudaSuccess) cd_solve_kernel<WD, NP><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(sp);
+    if (width == 8) { B200_CD_LAUNCH(8, 1) }
+    else if (width == 16) { B200_CD_LAUNCH(16, 1) }
+    else if (npl == 1) { B200_CD_LAUNCH(32, 1) }
+    else { B200_CD_LAUNCH(32, 2) }
+#undef B200_CD_LAUNCH
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace b200

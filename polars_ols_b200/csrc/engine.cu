@@ -27,6 +27,7 @@
 #include "prep.cuh"
 #include "qr_fallback.cuh"
 #include "small_solve.cuh"
+#include "cd_solve.cuh"
 
 using namespace b200;
 
@@ -841,10 +842,14 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         sp.illcond_ratio = ILLCOND_RATIO;
         sp.max_iter = rt.max_iter;
         sp.positive = rt.positive;
-        const unsigned blocks = static_cast<unsigned>((G + 63) / 64);
-        small_solve_kernel<<<blocks, 64, 0, c->stream>>>(sp);
+        if (cd) {
+            CU(launch_cd_solve(c->stream, sp, c->sm_count));
+        } else {
+            const unsigned blocks = static_cast<unsigned>((G + 63) / 64);
+            small_solve_kernel<<<blocks, 64, 0, c->stream>>>(sp);
+            CU(cudaGetLastError());
+        }
         c->launches++;
-        CU(cudaGetLastError());
     }
 
     if (rt.ols_qr_guard) {
@@ -914,6 +919,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     pr.target_validity = st.y_validity;
     pr.mask = (kw->null_policy == B200OLS_NULL_DROP) ? st.mask : nullptr;
     pr.nseg = pl.nseg;
+    pr.n_rows = N;
     pr.seg_off = pl.seg_off;
     pr.seg_group = pl.seg_group;
     pr.beta = beta;
@@ -928,7 +934,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     pr.out = dout;
     pr.out_valid = dval;
     {
-        const int64_t warps_needed = pl.nseg;
+        const int64_t warps_needed = (N + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
         const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
         if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
         else predict_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);

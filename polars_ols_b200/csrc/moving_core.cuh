@@ -65,7 +65,7 @@ struct NormalState {   // S = sum x x^T (+ alpha I), v = sum x y   (lower triang
 // pivoting on a local copy (solve_normal_equations(.., None, Some(LU)), src/least_squares.rs:732-734).
 template <int K>
 B200_HD void solve_normal(const NormalState<K> &st, double (&beta)[K]) {
-    double L[K][K];
+    double L[K][K], inv[K];
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -73,14 +73,21 @@ B200_HD void solve_normal(const NormalState<K> &st, double (&beta)[K]) {
 #pragma unroll
         for (int p = 0; p < j; ++p) d = fma(-L[j][p], L[j][p], d);
         if (!(d > 0.0)) ok = false;
-        const double sd = sqrt(d);
-        L[j][j] = sd;
+        // one reciprocal square root per column instead of K divisions (f64 division and sqrt are ~25-instruction
+        // sequences on the GPU and this runs once per row); results agree with the reference's LL^T to rounding
+#if defined(__CUDA_ARCH__)
+        const double r = rsqrt(d);
+#else
+        const double r = 1.0 / sqrt(d);
+#endif
+        inv[j] = r;
+        L[j][j] = d * r;
 #pragma unroll
         for (int i = j + 1; i < K; ++i) {
             double s = st.S[i][j];
 #pragma unroll
             for (int p = 0; p < j; ++p) s = fma(-L[i][p], L[j][p], s);
-            L[i][j] = s / sd;
+            L[i][j] = s * r;
         }
     }
     if (ok) {
@@ -89,14 +96,14 @@ B200_HD void solve_normal(const NormalState<K> &st, double (&beta)[K]) {
             double s = st.v[i];
 #pragma unroll
             for (int p = 0; p < i; ++p) s = fma(-L[i][p], beta[p], s);
-            beta[i] = s / L[i][i];
+            beta[i] = s * inv[i];
         }
 #pragma unroll
         for (int i = K - 1; i >= 0; --i) {
             double s = beta[i];
 #pragma unroll
             for (int p = i + 1; p < K; ++p) s = fma(-L[p][i], beta[p], s);
-            beta[i] = s / L[i][i];
+            beta[i] = s * inv[i];
         }
         return;
     }
@@ -362,7 +369,7 @@ B200_HD void rls_summarise(const Src &src, const RlsCfg &cfg, int64_t c0, int64_
 
 // One covariance-form update (src/least_squares.rs:531-540), operation order as in the reference.
 template <int K>
-B200_HD void rls_update(double (&P)[K][K], double (&theta)[K], const double (&x)[K], double y, double lam) {
+B200_HD void rls_update(double (&P)[K][K], double (&theta)[K], const double (&x)[K], double y, double lam, double inv_lam) {
     double xp[K], px[K], kg[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -382,9 +389,9 @@ B200_HD void rls_update(double (&P)[K][K], double (&theta)[K], const double (&x)
         for (int j = 0; j < K; ++j) s = fma(P[i][j], x[j], s);
         px[i] = s;
     }
-    const double rl = r * lam;
+    const double irl = 1.0 / (r * lam);  // one division per row; K = P x / (r lambda)
 #pragma unroll
-    for (int i = 0; i < K; ++i) kg[i] = px[i] / rl;
+    for (int i = 0; i < K; ++i) kg[i] = px[i] * irl;
     double pred = 0.0;
 #pragma unroll
     for (int j = 0; j < K; ++j) pred = fma(x[j], theta[j], pred);
@@ -394,7 +401,7 @@ B200_HD void rls_update(double (&P)[K][K], double (&theta)[K], const double (&x)
 #pragma unroll
     for (int i = 0; i < K; ++i)
 #pragma unroll
-        for (int j = 0; j < K; ++j) P[i][j] = P[i][j] / lam - (kg[i] * kg[j]) * r;
+        for (int j = 0; j < K; ++j) P[i][j] = fma(P[i][j], inv_lam, -(kg[i] * kg[j]) * r);  // P / lambda - K K^T r
 }
 
 // Runs rows [c0, c1).  `first_chunk`: the series starts here -> P = p0 I, theta = theta0 exactly as the
@@ -424,11 +431,12 @@ B200_HD void rls_chunk(const Src &src, const RlsCfg &cfg, bool first_chunk, cons
             for (int i = 0; i < K; ++i) P[i][c] = col[i];
         }
     }
+    const double inv_lam = 1.0 / cfg.lambda;  // exact (1.0) for the expanding case
     double x[K], y;
     for (int64_t r = c0; r < c1; ++r) {
         if (src.valid(r)) {
             src.load(r, x, y);
-            rls_update<K>(P, theta, x, y, cfg.lambda);
+            rls_update<K>(P, theta, x, y, cfg.lambda, inv_lam);
         }
         emit(r, theta, false);
     }
