@@ -985,6 +985,19 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     }
     gco[G] = static_cast<int64_t>(r0.size());
     const size_t nc = r0.size();
+    // super-chunks for the rls scan: runs of <= SCAN_SUPER chunks inside one series
+    std::vector<int64_t> s0, s1, gso(static_cast<size_t>(G) + 1);
+    if (p.kind == MOVING_RLS) {
+        for (int64_t g = 0; g < G; ++g) {
+            gso[g] = static_cast<int64_t>(s0.size());
+            for (int64_t c = gco[g]; c < gco[g + 1]; c += SCAN_SUPER) {
+                s0.push_back(c);
+                s1.push_back(std::min<int64_t>(c + SCAN_SUPER, gco[g + 1]));
+            }
+        }
+        gso[G] = static_cast<int64_t>(s0.size());
+    }
+    const size_t ns = s0.size();
     p.n_chunks = static_cast<int64_t>(nc);
     size_t off = 0;
     auto take = [&](size_t bytes) { char *q = ws + off; off += (bytes + 255) & ~static_cast<size_t>(255); return q; };
@@ -994,6 +1007,14 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     int64_t *d_gco = reinterpret_cast<int64_t *>(take((G + 1) * 8));
     p.series_info = reinterpret_cast<int64_t *>(take(static_cast<size_t>(G) * 24 + 8));
     p.summaries = reinterpret_cast<double *>(take(p.kind == MOVING_RLS ? nc * MOVING_REC * 8 + 8 : 8));
+    int64_t *d_s0 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
+    int64_t *d_s1 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
+    int64_t *d_gso = reinterpret_cast<int64_t *>(take((G + 1) * 8));
+    p.sup = reinterpret_cast<double *>(take(ns * MOVING_REC * 8 + 8));
+    p.n_super = static_cast<int64_t>(ns);
+    p.sup_c0 = d_s0;
+    p.sup_c1 = d_s1;
+    p.group_sup_off = d_gso;
     if (off > moving_workspace_bytes(p.n_rows, G, p.F)) return fail(B200OLS_ERR_CUDA, "internal: moving workspace under-sized");
     // pageable -> device async copies are staged by the driver before the call returns
     if (nc) {
@@ -1002,6 +1023,11 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
         CU(cudaMemcpyAsync(d_cg, cg.data(), nc * 4, cudaMemcpyHostToDevice, stream));
     }
     CU(cudaMemcpyAsync(d_gco, gco.data(), (G + 1) * 8, cudaMemcpyHostToDevice, stream));
+    if (ns) {
+        CU(cudaMemcpyAsync(d_s0, s0.data(), ns * 8, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(d_s1, s1.data(), ns * 8, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(d_gso, gso.data(), (G + 1) * 8, cudaMemcpyHostToDevice, stream));
+    }
     CU(cudaStreamSynchronize(stream));  // host vectors go out of scope; tables are tiny
     p.chunk_r0 = d_r0;
     p.chunk_r1 = d_r1;

@@ -49,6 +49,9 @@ struct MovingParams {
     const int64_t *chunk_r0, *chunk_r1;
     const int32_t *chunk_group;
     double *summaries;                // [n_chunks][REC]  rls
+    int64_t n_super;                  // rls scan: runs of <= SCAN_SUPER chunks of one series
+    const int64_t *sup_c0, *sup_c1, *group_sup_off;
+    double *sup;                      // [n_super][REC]
     int64_t *series_info;             // [G][3] rolling: mpv, n_valid, all_nan
 };
 
@@ -171,40 +174,94 @@ __global__ void __launch_bounds__(128) rls_summary_kernel(const MovingParams p) 
 }
 
 // Exclusive scan over the chunks of each series: rec[c] <- information state ENTERING chunk c.
-// One warp per series, lanes over the K*K+K elements; the chunk loop is sequential (a few 10^4 steps at
-// most, each an FMA on coalesced 8-byte loads).
+// The per-chunk summaries are affine maps  s -> D s + A  (associative), so the scan is hierarchical:
+//   phase 0: one warp per super-chunk (run of <= 256 chunks of one series) composes its chunks
+//            (lanes = the K*K+K matrix elements) -> sup[sc] = (D, A) of the run;
+//   phase 1: one warp per series walks its super-chunks: sup[sc] <- state entering the run, starting from
+//            the prior A0 = I/p0, b0 = A0 theta0;
+//   phase 2: one warp per super-chunk replays its chunks from that state and overwrites rec[c] in place.
+// Records are prefetched SCAN_PF at a time (the addresses do not depend on the carry), so no phase is a
+// chain of dependent HBM round trips.
+constexpr int SCAN_SUPER = 256;
+constexpr int SCAN_PF = 8;
+
 template <int K>
-__global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, const int64_t *group_chunk_off) {
+__global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int phase, int64_t n_super,
+                                                       const int64_t *__restrict__ sup_c0, const int64_t *__restrict__ sup_c1,
+                                                       const int64_t *__restrict__ group_sup_off, double *__restrict__ sup) {
     const int lane = threadIdx.x & 31;
-    const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (g >= p.n_groups) return;
+    const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     constexpr int NE = K * K + K;
-    const int64_t c0 = group_chunk_off[g], c1 = group_chunk_off[g + 1];
-    double carry[(NE + 31) / 32];
+    constexpr int NT = (NE + 31) / 32;
+    double carry[NT];
+    if (phase == 1) {
+        if (wid >= p.n_groups) return;
 #pragma unroll
-    for (int t = 0; t < (NE + 31) / 32; ++t) {
-        const int e = lane + 32 * t;
-        double v = 0.0;
-        if (e < K * K) {
-            const int i = e / K, j = e % K;
-            v = (i == j) ? 1.0 / p.p0 : 0.0;            // A0 = I / p0
-        } else if (e < NE) {
-            v = (p.has_mean ? p.mean[e - K * K] : 0.0) / p.p0;  // b0 = A0 theta0
-        }
-        carry[t] = v;
-    }
-    for (int64_t c = c0; c < c1; ++c) {
-        double *rec = p.summaries + c * MOVING_REC;
-        const double D = rec[NE];
-#pragma unroll
-        for (int t = 0; t < (NE + 31) / 32; ++t) {
+        for (int t = 0; t < NT; ++t) {
             const int e = lane + 32 * t;
-            if (e < NE) {
-                const double add = rec[e];
-                rec[e] = carry[t];
-                carry[t] = fma(D, carry[t], add);
+            double v = 0.0;
+            if (e < K * K) v = ((e / K) == (e % K)) ? 1.0 / p.p0 : 0.0;                  // A0 = I / p0
+            else if (e < NE) v = (p.has_mean ? p.mean[e - K * K] : 0.0) / p.p0;         // b0 = A0 theta0
+            carry[t] = v;
+        }
+        for (int64_t sc = group_sup_off[wid]; sc < group_sup_off[wid + 1]; ++sc) {
+            double *rec = sup + sc * MOVING_REC;
+            const double D = rec[NE];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int e = lane + 32 * t;
+                if (e < NE) {
+                    const double add = rec[e];
+                    rec[e] = carry[t];
+                    carry[t] = fma(D, carry[t], add);
+                }
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    if (wid >= n_super) return;
+    const int64_t c0 = sup_c0[wid], c1 = sup_c1[wid];
+    double Dtot = 1.0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int e = lane + 32 * t;
+        carry[t] = (phase == 2 && e < NE) ? sup[wid * MOVING_REC + e] : 0.0;  // phase 0 starts from the zero map offset
+    }
+    for (int64_t cb = c0; cb < c1; cb += SCAN_PF) {
+        double add[SCAN_PF][NT], Dv[SCAN_PF];
+#pragma unroll
+        for (int u = 0; u < SCAN_PF; ++u) {
+            const int64_t c = (cb + u < c1) ? cb + u : c1 - 1;
+            const double *rec = p.summaries + c * MOVING_REC;
+            Dv[u] = rec[NE];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int e = lane + 32 * t;
+                add[u][t] = (e < NE) ? rec[e] : 0.0;
             }
         }
+#pragma unroll
+        for (int u = 0; u < SCAN_PF; ++u) {
+            if (cb + u < c1) {
+                double *rec = p.summaries + (cb + u) * MOVING_REC;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const int e = lane + 32 * t;
+                    if (phase == 2 && e < NE) rec[e] = carry[t];
+                    carry[t] = fma(Dv[u], carry[t], add[u][t]);
+                }
+                Dtot *= Dv[u];
+            }
+        }
+    }
+    if (phase == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int e = lane + 32 * t;
+            if (e < NE) sup[wid * MOVING_REC + e] = carry[t];
+        }
+        if (lane == 0) sup[wid * MOVING_REC + NE] = Dtot;
     }
 }
 
@@ -245,7 +302,9 @@ inline int64_t moving_chunk_len(int64_t n_rows, int sm_count, int kind, int64_t 
 
 inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int /*F*/) {
     const size_t max_chunks = static_cast<size_t>(n_rows / 64 + n_groups + 2);
-    return max_chunks * (MOVING_REC * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (3 * 8 + 8) + 8192;
+    const size_t max_super = max_chunks / 256 + static_cast<size_t>(n_groups) + 2;
+    return max_chunks * (MOVING_REC * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (3 * 8 + 8 + 8) +
+           max_super * (MOVING_REC * 8 + 16) + 16384;
 }
 
 template <typename T, int K>
@@ -264,9 +323,12 @@ static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const i
         ++*launches;
     } else {
         rls_summary_kernel<T, K><<<cb, 128, 0, stream>>>(p);
-        rls_scan_kernel<K><<<static_cast<unsigned>((p.n_groups * 32 + 127) / 128), 128, 0, stream>>>(p, group_chunk_off_dev);
+        const unsigned sb = static_cast<unsigned>((p.n_super * 32 + 127) / 128);
+        rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 0, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
+        rls_scan_kernel<K><<<static_cast<unsigned>((p.n_groups * 32 + 127) / 128), 128, 0, stream>>>(p, 1, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
+        rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 2, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
         rls_main_kernel<T, K><<<cb, 128, 0, stream>>>(p);
-        *launches += 3;
+        *launches += 5;
     }
     return cudaGetLastError();
 }
