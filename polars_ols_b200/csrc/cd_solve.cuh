@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
             for (int64_t sg = s0; sg < s1; ++sg) s += p.partial[static_cast<size_t>(sg) * P + e];
             Gs[e] = s;
         }
-        double q[NPL], w[NPL], w_old[NPL], gd[NPL];
+        double q[NPL], w[NPL], w_old[NPL], gd[NPL], rinv[NPL];
         double nfit = 0.0;
         for (int64_t sg = s0; sg < s1; ++sg) nfit += p.partial[static_cast<size_t>(sg) * P + F * F + F];
 #pragma unroll
@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
         }
         const double a = p.alpha * nfit;  // alpha *= n_samples (src/least_squares.rs:419)
         const double l1 = a * p.l1_ratio, l2 = a * (1.0 - p.l1_ratio);
+        // 1 / (|x_j|^2 + a (1 - l1)) once per coordinate: the per-update division of the reference (:431) becomes
+        // a multiplication (f64 division is a ~20-instruction sequence and this loop is instruction bound)
+#pragma unroll
+        for (int t = 0; t < NPL; ++t) rinv[t] = 1.0 / (gd[t] + l2);
         // sub-warps diverge freely (different sweep counts / active sets): shuffles use the sub-warp's own mask
         const unsigned submask = (WIDTH == 32) ? FULL : (((1u << WIDTH) - 1u) << (sub * WIDTH));
         if (live) {
@@ -86,12 +90,12 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
                     for (int j = 0; j < F; ++j) {
                         if (!((loop_set >> j) & 1ull)) continue;
                         const int owner = j % WIDTH, tj = j / WIDTH;
-                        double qj = q[0], wj = w[0], gj = gd[0];
+                        double qj = q[0], wj = w[0], gj = gd[0], rj = rinv[0];
 #pragma unroll
                         for (int t = 1; t < NPL; ++t)
-                            if (t == tj) { qj = q[t]; wj = w[t]; gj = gd[t]; }
+                            if (t == tj) { qj = q[t]; wj = w[t]; gj = gd[t]; rj = rinv[t]; }
                         const double rho = fma(gj, wj, qj);
-                        const double wn_own = soft_threshold(rho, l1, positive) / (gj + l2);
+                        const double wn_own = soft_threshold(rho, l1, positive) * rj;
                         const double wn = __shfl_sync(submask, wn_own, owner, WIDTH);
                         const double wo = __shfl_sync(submask, wj, owner, WIDTH);
                         const double delta = wn - wo;

@@ -19,6 +19,7 @@
 
 #include "../../include/b200ols.h"
 #include "gram_cta.cuh"
+#include "gram_wide.cuh"
 #include "gram_ldg.cuh"
 #include "gram_simt.cuh"
 #include "gram_stream.cuh"
@@ -612,6 +613,28 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     const int F = gp.F;
     const int KB = (F + 7) / 8;
     const int NC = gp.kd + 1 + gp.has_w + gp.has_mask;
+    if (c->variant == 3 && KB > 2 && !gp.fused) {  // 17 <= k <= 64: block pairs split across the consumer warps
+        const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
+        int R = c->tile_rows > 0 ? c->tile_rows : 96;
+        int S = 0;
+        for (;;) {
+            const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(R);
+            S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, budget / sb));
+            if (S >= 2 || R <= 16) break;
+            R -= 8;
+        }
+        if (S < 2) return fail(B200OLS_ERR_UNSUPPORTED, "Gram tile does not fit in shared memory (%d columns)", NC);
+        if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));
+        gp.tile_rows = R;
+        gp.stages = S;
+        const size_t smem = static_cast<size_t>(S) * NC * gram_col_stride<T>(R);
+        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, gp.nseg));
+        ProfScope prof(c);
+        CU(sizeof(T) == 8 ? gram_wide_launch_f64(gp, static_cast<unsigned>(grid), smem, c->stream)
+                          : gram_wide_launch_f32(gp, static_cast<unsigned>(grid), smem, c->stream));
+        c->launches++;
+        return 0;
+    }
     if (c->variant == 3 && KB <= 2) {  // CTA-cooperative warp-specialised TMA pipeline (k <= 16)
         const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
         const size_t fixed = cta_fixed_smem<T>(KB, F);
@@ -746,6 +769,17 @@ static int resolve_route(const b200ols_ols_kwargs *kw, StaticRoute *r) {
 }
 
 static constexpr int64_t SEG_MAX_ROWS = 4096;
+
+// Groups are cut into segments only to create parallelism: the CTA-level Gram kernels walk a group of any
+// length tile by tile, so with at least ~2 groups per SM nothing is split (and the solve stays fused).
+// With few groups the segment length is chosen to give ~4 segments per SM (never below 1024 rows).
+static int64_t choose_seg_max(const b200ols_ctx *c, int64_t n_groups, int64_t n_rows) {
+    if (c->variant != 3) return SEG_MAX_ROWS;  // warp-per-segment kernels: bound the work of one warp
+    if (n_groups >= 2 * static_cast<int64_t>(c->sm_count)) return INT64_MAX / 4;
+    int64_t s = n_rows / (4 * static_cast<int64_t>(c->sm_count)) + 1;
+    s = (s + 15) & ~static_cast<int64_t>(15);
+    return std::max<int64_t>(s, 1024);
+}
 static constexpr double ILLCOND_RATIO = 1.0e7;  // squared-pivot ratio above which OLS is re-solved by QR
 
 static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
@@ -763,8 +797,9 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     const int64_t G = f->n_groups, N = f->n_rows;
     const size_t P = static_cast<size_t>(F) * F + F + 1;
     // arena budget
-    size_t bytes = stage_bytes_bound(f) + plan_bytes_bound(f, SEG_MAX_ROWS);
-    const size_t nseg_bound = static_cast<size_t>(G) + static_cast<size_t>(N / (SEG_MAX_ROWS / 2)) + 2;
+    const int64_t seg_max = choose_seg_max(c, G, N);
+    size_t bytes = stage_bytes_bound(f) + plan_bytes_bound(f, seg_max);
+    const size_t nseg_bound = static_cast<size_t>(G) + static_cast<size_t>(N / std::max<int64_t>(seg_max / 2, 1)) + 2;
     bytes += nseg_bound * P * 8 + static_cast<size_t>(G) * (static_cast<size_t>(F) * F + 4 * F) * 8;  // partials + work
     bytes += static_cast<size_t>(G) * F * 8 + static_cast<size_t>(G) * 4 + 4096;                     // beta + flags
     if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * 9 + 4096;                         // out + validity
@@ -777,7 +812,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     Staged st;
     TRY(stage_frame(c, f, kw->null_policy, false, &st));
     Plan pl;
-    TRY(build_plan(c, st, SEG_MAX_ROWS, &pl));
+    TRY(build_plan(c, st, seg_max, &pl));
 
     double *beta = arena_alloc<double>(c, static_cast<size_t>(G) * F);
     int32_t *flags = arena_alloc<int32_t>(c, static_cast<size_t>(G));
@@ -810,7 +845,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     gp.has_mask = st.mask ? 1 : 0;
     gp.n_rows_pad = st.n_pad;
     gp.nseg = pl.nseg;
-    gp.max_seg_rows = pl.split ? SEG_MAX_ROWS : st.max_group_rows;
+    gp.max_seg_rows = pl.split ? std::min<int64_t>(seg_max, st.max_group_rows) : st.max_group_rows;
     gp.seg_off = pl.seg_off;
     gp.seg_group = pl.seg_group;
     gp.alpha = rt.alpha;

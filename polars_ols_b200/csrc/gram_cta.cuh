@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     __syncthreads();
 
     const int64_t nseg = p.nseg;
-    const bool plain = !p.has_mask && !p.has_w;
+    const bool plain = !p.has_mask;  // no row mask: interior octets need no predication (weights only scale)
 
     if (warp == 0) {
         // ================================ PRODUCER ================================
@@ -204,17 +204,36 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                     }
                     const int jfull = hi >> 3;  // octets below jfull lie entirely inside [o, hi)
                     const int jend = (j1 < jfull) ? j1 : jfull;
+                    if (!p.has_w) {
 #pragma unroll 4
-                    for (; j < jend; ++j) {
-                        const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
-                        double f0[KB], f1[KB];
+                        for (; j < jend; ++j) {
+                            const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
+                            double f0[KB], f1[KB];
 #pragma unroll
-                        for (int bk = 0; bk < KB; ++bk) {
-                            const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
-                            f0[bk] = has_x[bk] ? static_cast<double>(x2.x) : xconst[bk];
-                            f1[bk] = has_x[bk] ? static_cast<double>(x2.y) : xconst[bk];
+                            for (int bk = 0; bk < KB; ++bk) {
+                                const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
+                                f0[bk] = has_x[bk] ? static_cast<double>(x2.x) : xconst[bk];
+                                f1[bk] = has_x[bk] ? static_cast<double>(x2.y) : xconst[bk];
+                            }
+                            mma_octet(f0, f1, static_cast<double>(y2.x), static_cast<double>(y2.y));
                         }
-                        mma_octet(f0, f1, static_cast<double>(y2.x), static_cast<double>(y2.y));
+                    } else {
+                        const unsigned char *ws = sb + static_cast<size_t>(wcol) * stride + 2 * q * sizeof(T);
+#pragma unroll 2
+                        for (; j < jend; ++j) {
+                            const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
+                            const Vec w2 = *reinterpret_cast<const Vec *>(ws + 8 * j * sizeof(T));
+                            const T s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
+                            const T s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                            double f0[KB], f1[KB];
+#pragma unroll
+                            for (int bk = 0; bk < KB; ++bk) {
+                                const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
+                                f0[bk] = static_cast<double>(static_cast<T>((has_x[bk] ? x2.x : static_cast<T>(xconst[bk])) * s0));
+                                f1[bk] = static_cast<double>(static_cast<T>((has_x[bk] ? x2.y : static_cast<T>(xconst[bk])) * s1));
+                            }
+                            mma_octet(f0, f1, static_cast<double>(static_cast<T>(y2.x * s0)), static_cast<double>(static_cast<T>(y2.y * s1)));
+                        }
                     }
                     for (; j < j1; ++j) masked_octet(j);
                 }

@@ -1,5 +1,6 @@
 // gram_f64.cu — f64 instantiations of the row-streaming Gram kernel (see gram_stream.cuh)
 #include "gram_cta.cuh"
+#include "gram_wide.cuh"
 #include "gram_ldg.cuh"
 #include "gram_simt.cuh"
 #include "gram_stream.cuh"
@@ -15,5 +16,8 @@ cudaError_t gram_simt_launch_f64(int U, const GramParams &p, unsigned grid, int 
 }
 cudaError_t gram_cta_launch_f64(int KB, const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     return KB == 1 ? gram_cta_launch_t<double, 1>(p, grid, smem, s) : gram_cta_launch_t<double, 2>(p, grid, smem, s);
+}
+cudaError_t gram_wide_launch_f64(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    return gram_wide_launch_t<double>(p, grid, smem, s);
 }
 }  // namespace b200

@@ -33,21 +33,12 @@ struct PredictParams {
     uint8_t *out_valid;               // bytes or nullptr
 };
 
+template <typename T> struct PV;
+template <> struct PV<double> { using type = double2; static constexpr int N = 2; };
+template <> struct PV<float> { using type = float4; static constexpr int N = 4; };
+
 template <typename T>
-__device__ __forceinline__ void predict_row(const PredictParams &p, int64_t r, const double *beta) {
-    const int kd = p.kd;
-    T s = T(1);
-    if (p.has_w) {
-        const T w = static_cast<const T *>(p.cols[kd])[r];
-        s = p.w_is_sqrt ? w : static_cast<T>(sqrt(w));
-    }
-    double acc = 0.0;
-#pragma unroll 8
-    for (int j = 0; j < kd; ++j) {
-        const T x = static_cast<const T *>(p.cols[j])[r];
-        acc = fma(static_cast<double>(static_cast<T>(x * s)), __ldg(beta + j), acc);
-    }
-    if (p.intercept) acc = fma(static_cast<double>(s), __ldg(beta + kd), acc);
+__device__ __forceinline__ void predict_store(const PredictParams &p, int64_t r, double acc, T s) {
     if (p.has_w) acc *= static_cast<double>(T(1) / s);  // predictions *= 1.0 / sqrt_w
     const int64_t orow = p.row_index ? p.row_index[r] : r;
     bool valid = true;
@@ -62,16 +53,39 @@ __device__ __forceinline__ void predict_row(const PredictParams &p, int64_t r, c
 }
 
 template <typename T>
+__device__ __forceinline__ T predict_scale(const PredictParams &p, T w) {
+    return p.w_is_sqrt ? w : static_cast<T>(sqrt(w));
+}
+
+// one row (vector tails and rows of a vector that straddle a group boundary)
+template <typename T>
+__device__ __forceinline__ void predict_row(const PredictParams &p, int64_t r, const double *beta) {
+    const int kd = p.kd;
+    T s = T(1);
+    if (p.has_w) s = predict_scale<T>(p, static_cast<const T *>(p.cols[kd])[r]);
+    double acc = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < kd; ++j) {
+        const T x = static_cast<const T *>(p.cols[j])[r];
+        acc = fma(static_cast<double>(static_cast<T>(x * s)), __ldg(beta + j), acc);
+    }
+    if (p.intercept) acc = fma(static_cast<double>(s), __ldg(beta + kd), acc);
+    predict_store<T>(p, r, acc, s);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
+    using Vec = typename PV<T>::type;
+    constexpr int VN = PV<T>::N;  // rows per lane and iteration: one 16-byte load per column
     const int lane = threadIdx.x & 31;
     const int64_t wg = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const int64_t nchunks = (p.n_rows + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
-    const int F = p.F;
+    const int F = p.F, kd = p.kd;
     for (int64_t ch = wg; ch < nchunks; ch += nwarps) {
         const int64_t c0 = ch * PREDICT_CHUNK;
         const int64_t c1 = (c0 + PREDICT_CHUNK < p.n_rows) ? c0 + PREDICT_CHUNK : p.n_rows;
-        int64_t r = c0 + lane;
+        int64_t r = c0 + static_cast<int64_t>(lane) * VN;
         if (r >= c1) continue;
         // segment of row r: largest s with seg_off[s] <= r (empty segments are skipped by the search)
         int64_t lo = 0, hi = p.nseg;  // invariant: seg_off[lo] <= r < seg_off[hi]
@@ -82,13 +96,51 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
         int64_t seg = lo;
         int64_t seg_end = p.seg_off[seg + 1];
         const double *beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * F;
-        for (; r < c1; r += 32) {
+        for (; r < c1; r += 32 * VN) {
             while (r >= seg_end) {
                 ++seg;
                 seg_end = p.seg_off[seg + 1];
                 beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * F;
             }
-            predict_row<T>(p, r, beta);
+            if (r + VN <= c1 && r + VN <= seg_end) {
+                // whole vector inside one group: 16-byte loads, beta_j loaded once for the VN rows
+                T sv[VN];
+                double acc[VN];
+#pragma unroll
+                for (int v = 0; v < VN; ++v) { sv[v] = T(1); acc[v] = 0.0; }
+                if (p.has_w) {
+                    const Vec w4 = *reinterpret_cast<const Vec *>(static_cast<const T *>(p.cols[kd]) + r);
+                    const T *wp = reinterpret_cast<const T *>(&w4);
+#pragma unroll
+                    for (int v = 0; v < VN; ++v) sv[v] = predict_scale<T>(p, wp[v]);
+                }
+#pragma unroll 4
+                for (int j = 0; j < kd; ++j) {
+                    const Vec x4 = *reinterpret_cast<const Vec *>(static_cast<const T *>(p.cols[j]) + r);
+                    const T *xp = reinterpret_cast<const T *>(&x4);
+                    const double b = __ldg(beta + j);
+#pragma unroll
+                    for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(static_cast<T>(xp[v] * sv[v])), b, acc[v]);
+                }
+                if (p.intercept) {
+                    const double b = __ldg(beta + kd);
+#pragma unroll
+                    for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(sv[v]), b, acc[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < VN; ++v) predict_store<T>(p, r + v, acc[v], sv[v]);
+            } else {
+                int64_t sg = seg, se = seg_end;
+                const double *bb = beta;
+                for (int v = 0; v < VN && r + v < c1; ++v) {
+                    while (r + v >= se) {
+                        ++sg;
+                        se = p.seg_off[sg + 1];
+                        bb = p.beta + (p.seg_group ? p.seg_group[sg] : sg) * F;
+                    }
+                    predict_row<T>(p, r + v, bb);
+                }
+            }
         }
     }
 }
