@@ -21,7 +21,9 @@ constexpr int WIDE_SB = WIDE_KB / 2;                          // super-blocks pe
 constexpr int WIDE_ITEMS = WIDE_SB + WIDE_SB * (WIDE_SB - 1) / 2;  // 4 diagonal + 6 off-diagonal = 10 consumer warps
 constexpr int WIDE_THREADS = (WIDE_ITEMS + 1) * 32;
 
-template <typename T>
+// EXTRA = weights and/or a row mask are present (predicated, scaled path); otherwise the loop body is
+// 2-4 LDS.128 + 6-8 DMMA per 8 rows and warp.
+template <typename T, bool EXTRA>
 __global__ void __launch_bounds__(WIDE_THREADS, 1) gram_wide_kernel(const GramParams p) {
     using Vec = typename V2<T>::type;
     constexpr int A = 16 / sizeof(T);
@@ -101,15 +103,19 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) gram_wide_kernel(const GramPa
     const bool active = blk[0] < nblk && (diag || blk[2] < nblk);  // super-blocks beyond F have nothing to do
     bool has_x[4];
     double xconst[4];
-    int xcolidx[4];
+    uint32_t xoff[4];  // byte offset of this lane's element pair inside a stage, per feature block
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int f = 8 * blk[t] + fb;
         has_x[t] = f < kd;
-        xcolidx[t] = has_x[t] ? f : 0;
+        xoff[t] = static_cast<uint32_t>(has_x[t] ? f : 0) * stride + 2 * q * sizeof(T);  // padding lanes alias column 0
         xconst[t] = (f == kd && p.intercept) ? 1.0 : 0.0;
     }
-    const bool plain = !p.has_mask;
+    const uint32_t yoff = static_cast<uint32_t>(ycol) * stride + 2 * q * sizeof(T);
+    const uint32_t woff = static_cast<uint32_t>(wcol) * stride + 2 * q * sizeof(T);
+    const uint32_t moff = static_cast<uint32_t>(mcol) * stride + 2 * q * sizeof(T);
+    const bool has_w = EXTRA && p.has_w, has_mask = EXTRA && p.has_mask;
+    const bool plain = !has_mask;
 
     int stage = 0;
     uint32_t phase = 0;
@@ -128,44 +134,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) gram_wide_kernel(const GramPa
             mbar_wait(&full_bar[stage], phase);
             if (active) {
                 const unsigned char *sbp = smem + static_cast<size_t>(stage) * stage_bytes;
-                const unsigned char *xs[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) xs[t] = sbp + static_cast<size_t>(xcolidx[t]) * stride + 2 * q * sizeof(T);
-                const unsigned char *ys = sbp + static_cast<size_t>(ycol) * stride + 2 * q * sizeof(T);
-                const unsigned char *wsp = sbp + static_cast<size_t>(wcol) * stride + 2 * q * sizeof(T);
-                const unsigned char *msp = sbp + static_cast<size_t>(mcol) * stride + 2 * q * sizeof(T);
-                for (int j = 0; j < noct; ++j) {
-                    const int lr = 8 * j + 2 * q;
-                    bool v0 = true, v1 = true;
-                    const bool edge = !plain || (j == 0 && o != 0) || (8 * j + 8 > hi);
-                    if (edge) {
-                        v0 = (lr >= o) && (lr < hi);
-                        v1 = (lr + 1 >= o) && (lr + 1 < hi);
-                        if (p.has_mask) {
-                            const Vec m2 = *reinterpret_cast<const Vec *>(msp + 8 * j * sizeof(T));
-                            v0 = v0 && (m2.x != T(0));
-                            v1 = v1 && (m2.y != T(0));
-                        }
-                    }
-                    T s0 = T(1), s1 = T(1);
-                    if (p.has_w) {
-                        const Vec w2 = *reinterpret_cast<const Vec *>(wsp + 8 * j * sizeof(T));
-                        s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                        s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
-                    }
-                    double f0[4], f1[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (t < 2 || !diag) {
-                            const Vec x2 = *reinterpret_cast<const Vec *>(xs[t] + 8 * j * sizeof(T));
-                            const T x0 = has_x[t] ? x2.x : static_cast<T>(xconst[t]);
-                            const T x1 = has_x[t] ? x2.y : static_cast<T>(xconst[t]);
-                            f0[t] = v0 ? static_cast<double>(static_cast<T>(x0 * s0)) : 0.0;
-                            f1[t] = v1 ? static_cast<double>(static_cast<T>(x1 * s1)) : 0.0;
-                        } else {
-                            f0[t] = f1[t] = 0.0;
-                        }
-                    }
+                auto mma_all = [&](const double (&f0)[4], const double (&f1)[4]) {
                     if (diag) {
                         dmma_m8n8k4(acc[0][0], acc[0][1], f0[0], f0[0]);
                         dmma_m8n8k4(acc[1][0], acc[1][1], f0[0], f0[1]);
@@ -183,14 +152,97 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) gram_wide_kernel(const GramPa
                         dmma_m8n8k4(acc[2][0], acc[2][1], f1[1], f1[2]);
                         dmma_m8n8k4(acc[3][0], acc[3][1], f1[1], f1[3]);
                     }
+                };
+                // predicated / scaled octet (segment edges, weights, row mask)
+                auto masked_octet = [&](int j) {
+                    const int lr = 8 * j + 2 * q;
+                    bool v0 = (lr >= o) && (lr < hi);
+                    bool v1 = (lr + 1 >= o) && (lr + 1 < hi);
+                    const uint32_t jo = 8 * j * sizeof(T);
+                    if (has_mask) {
+                        const Vec m2 = *reinterpret_cast<const Vec *>(sbp + moff + jo);
+                        v0 = v0 && (m2.x != T(0));
+                        v1 = v1 && (m2.y != T(0));
+                    }
+                    T s0 = T(1), s1 = T(1);
+                    if (has_w) {
+                        const Vec w2 = *reinterpret_cast<const Vec *>(sbp + woff + jo);
+                        s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
+                        s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                    }
+                    double f0[4], f1[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        f0[t] = f1[t] = 0.0;
+                        if (t < 2 || !diag) {
+                            const Vec x2 = *reinterpret_cast<const Vec *>(sbp + xoff[t] + jo);
+                            const T x0 = has_x[t] ? x2.x : static_cast<T>(xconst[t]);
+                            const T x1 = has_x[t] ? x2.y : static_cast<T>(xconst[t]);
+                            f0[t] = v0 ? static_cast<double>(static_cast<T>(x0 * s0)) : 0.0;
+                            f1[t] = v1 ? static_cast<double>(static_cast<T>(x1 * s1)) : 0.0;
+                        }
+                    }
+                    mma_all(f0, f1);
                     if (diag) {
-                        const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
+                        const Vec y2 = *reinterpret_cast<const Vec *>(sbp + yoff + jo);
                         const double y0 = v0 ? static_cast<double>(static_cast<T>(y2.x * s0)) : 0.0;
                         const double y1 = v1 ? static_cast<double>(static_cast<T>(y2.y * s1)) : 0.0;
                         cy[0] = fma(f0[0], y0, fma(f1[0], y1, cy[0]));
                         cy[1] = fma(f0[1], y0, fma(f1[1], y1, cy[1]));
                         if (item == 0 && fb == 0) nfit += (v0 ? 1 : 0) + (v1 ? 1 : 0);
                     }
+                };
+                if (EXTRA) {
+                    for (int j = 0; j < noct; ++j) masked_octet(j);
+                } else {
+                    int j = 0;
+                    if (o != 0) {
+                        masked_octet(0);
+                        j = 1;
+                    }
+                    const int jfull = hi >> 3;
+                    if (diag) {
+#pragma unroll 2
+                        for (; j < jfull; ++j) {
+                            const uint32_t jo = 8 * j * sizeof(T);
+                            const Vec a2 = *reinterpret_cast<const Vec *>(sbp + xoff[0] + jo);
+                            const Vec b2 = *reinterpret_cast<const Vec *>(sbp + xoff[1] + jo);
+                            const Vec y2 = *reinterpret_cast<const Vec *>(sbp + yoff + jo);
+                            const double a0 = has_x[0] ? static_cast<double>(a2.x) : xconst[0], a1 = has_x[0] ? static_cast<double>(a2.y) : xconst[0];
+                            const double b0 = has_x[1] ? static_cast<double>(b2.x) : xconst[1], b1 = has_x[1] ? static_cast<double>(b2.y) : xconst[1];
+                            dmma_m8n8k4(acc[0][0], acc[0][1], a0, a0);
+                            dmma_m8n8k4(acc[1][0], acc[1][1], a0, b0);
+                            dmma_m8n8k4(acc[2][0], acc[2][1], b0, b0);
+                            dmma_m8n8k4(acc[0][0], acc[0][1], a1, a1);
+                            dmma_m8n8k4(acc[1][0], acc[1][1], a1, b1);
+                            dmma_m8n8k4(acc[2][0], acc[2][1], b1, b1);
+                            const double y0 = static_cast<double>(y2.x), y1 = static_cast<double>(y2.y);
+                            cy[0] = fma(a0, y0, fma(a1, y1, cy[0]));
+                            cy[1] = fma(b0, y0, fma(b1, y1, cy[1]));
+                        }
+                    } else {
+#pragma unroll 2
+                        for (; j < jfull; ++j) {
+                            const uint32_t jo = 8 * j * sizeof(T);
+                            const Vec a2 = *reinterpret_cast<const Vec *>(sbp + xoff[0] + jo);
+                            const Vec b2 = *reinterpret_cast<const Vec *>(sbp + xoff[1] + jo);
+                            const Vec c2 = *reinterpret_cast<const Vec *>(sbp + xoff[2] + jo);
+                            const Vec d2 = *reinterpret_cast<const Vec *>(sbp + xoff[3] + jo);
+                            const double a0 = has_x[0] ? static_cast<double>(a2.x) : xconst[0], a1 = has_x[0] ? static_cast<double>(a2.y) : xconst[0];
+                            const double b0 = has_x[1] ? static_cast<double>(b2.x) : xconst[1], b1 = has_x[1] ? static_cast<double>(b2.y) : xconst[1];
+                            const double c0 = has_x[2] ? static_cast<double>(c2.x) : xconst[2], c1 = has_x[2] ? static_cast<double>(c2.y) : xconst[2];
+                            const double d0 = has_x[3] ? static_cast<double>(d2.x) : xconst[3], d1 = has_x[3] ? static_cast<double>(d2.y) : xconst[3];
+                            dmma_m8n8k4(acc[0][0], acc[0][1], a0, c0);
+                            dmma_m8n8k4(acc[1][0], acc[1][1], a0, d0);
+                            dmma_m8n8k4(acc[2][0], acc[2][1], b0, c0);
+                            dmma_m8n8k4(acc[3][0], acc[3][1], b0, d0);
+                            dmma_m8n8k4(acc[0][0], acc[0][1], a1, c1);
+                            dmma_m8n8k4(acc[1][0], acc[1][1], a1, d1);
+                            dmma_m8n8k4(acc[2][0], acc[2][1], b1, c1);
+                            dmma_m8n8k4(acc[3][0], acc[3][1], b1, d1);
+                        }
+                    }
+                    for (; j < noct; ++j) masked_octet(j);
                 }
             }
             __syncwarp();
@@ -243,13 +295,18 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) gram_wide_kernel(const GramPa
     }
 }
 
-template <typename T>
-cudaError_t gram_wide_launch_t(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
-    auto kern = gram_wide_kernel<T>;
+template <typename T, bool EXTRA>
+cudaError_t gram_wide_launch_e(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    auto kern = gram_wide_kernel<T, EXTRA>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     kern<<<grid, WIDE_THREADS, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t gram_wide_launch_t(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    return (p.has_w || p.has_mask) ? gram_wide_launch_e<T, true>(p, grid, smem, s) : gram_wide_launch_e<T, false>(p, grid, smem, s);
 }
 
 cudaError_t gram_wide_launch_f64(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s);
