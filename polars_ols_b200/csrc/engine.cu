@@ -1007,7 +1007,15 @@ extern "C" int b200ols_least_squares_coefficients(b200ols_ctx *c, const b200ols_
 int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets, bool f64, int sm_count, char *ws,
                          int64_t *launches) {
     const int64_t G = p.n_groups;
-    const int64_t L = moving_chunk_len(p.n_rows, sm_count, p.kind, p.window);
+    int64_t L = moving_chunk_len(p.n_rows, sm_count, p.kind, p.window);
+    // the chunk-interleaved copies take L * n_chunks elements per column: with many series much shorter than
+    // L that pads badly, so shrink L until the padded size is at most 2N + 64G (always true at L = 64)
+    for (;;) {
+        int64_t nch = 0;
+        for (int64_t g = 0; g < G; ++g) nch += (offsets[g + 1] - offsets[g] + L - 1) / L;
+        if (L <= 64 || L * nch <= 2 * p.n_rows + 64 * G) break;
+        L >>= 1;
+    }
     std::vector<int64_t> r0, r1, gco(static_cast<size_t>(G) + 1);
     std::vector<int32_t> cg;
     for (int64_t g = 0; g < G; ++g) {
@@ -1047,6 +1055,16 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     int64_t *d_gso = reinterpret_cast<int64_t *>(take((G + 1) * 8));
     p.sup = reinterpret_cast<double *>(take(ns * MOVING_REC * 8 + 8));
     p.n_super = static_cast<int64_t>(ns);
+    {   // chunk-interleaved column copies (filled by chunk_transpose_kernel)
+        p.chunk_len = L;
+        p.chunk_shift = 0;
+        while ((int64_t{1} << p.chunk_shift) < L) ++p.chunk_shift;
+        const size_t esz = f64 ? 8 : 4;
+        const size_t col_bytes = static_cast<size_t>(L) * nc * esz + 256;
+        for (int j = 0; j <= p.kd; ++j) p.tcols[j] = take(col_bytes);
+        p.tw = p.w ? take(col_bytes) : nullptr;
+        p.tmask = p.mask ? take(col_bytes) : nullptr;
+    }
     p.sup_c0 = d_s0;
     p.sup_c1 = d_s1;
     p.group_sup_off = d_gso;

@@ -49,6 +49,13 @@ struct MovingParams {
     const int64_t *chunk_r0, *chunk_r1;
     const int32_t *chunk_group;
     double *summaries;                // [n_chunks][REC]  rls
+    // chunk-interleaved ("transposed") copies of the input columns: element (column, row i of chunk ch) at
+    // tcols[column][i * n_chunks + ch], so that the lanes of a warp (consecutive chunks) read consecutive
+    // addresses while every thread walks its own chunk sequentially
+    const void *tcols[GRAM_MAX_COLS];  // [0,kd) features, [kd] target
+    const void *tw, *tmask;
+    int64_t chunk_len;                // L (power of two); every chunk of a series except its last has L rows
+    int chunk_shift;                  // log2(L)
     int64_t n_super;                  // rls scan: runs of <= SCAN_SUPER chunks of one series
     const int64_t *sup_c0, *sup_c1, *group_sup_off;
     double *sup;                      // [n_super][REC]
@@ -89,10 +96,90 @@ __device__ __forceinline__ DevSrc<T, K> make_src(const MovingParams &p) {
     return s;
 }
 
+// Same interface over the chunk-interleaved copies; r is still the packed row index.  Rows of earlier
+// chunks of the same series (window halo, warm-up) resolve to (chunk - back, row inside that chunk).
 template <typename T, int K>
+struct DevSrcT {
+    const T *x[K];
+    const T *y, *w, *mask;
+    int64_t r0, c, nch, L;
+    int shift, kd, w_is_sqrt;
+    __device__ __forceinline__ int64_t at(int64_t r) const {
+        if (r >= r0) return (r - r0) * nch + c;
+        const int64_t d = r0 - r;
+        const int64_t back = (d + L - 1) >> shift;
+        return ((back << shift) - d) * nch + (c - back);
+    }
+    __device__ __forceinline__ bool valid(int64_t r) const { return mask ? (mask[at(r)] != T(0)) : true; }
+    __device__ __forceinline__ T scale_at(int64_t t) const {
+        if (!w) return T(1);
+        const T v = w[t];
+        return w_is_sqrt ? v : static_cast<T>(sqrt(v));
+    }
+    __device__ __forceinline__ T scale(int64_t r) const { return scale_at(at(r)); }
+    __device__ __forceinline__ void load(int64_t r, double (&xo)[K], double &yo) const {
+        const int64_t t = at(r);
+        const T s = scale_at(t);
+#pragma unroll
+        for (int j = 0; j < K; ++j) xo[j] = (j < kd) ? static_cast<double>(static_cast<T>(x[j][t] * s)) : static_cast<double>(s);
+        yo = static_cast<double>(static_cast<T>(y[t] * s));
+    }
+};
+
+template <typename T, int K>
+__device__ __forceinline__ DevSrcT<T, K> make_src_t(const MovingParams &p, int64_t chunk) {
+    DevSrcT<T, K> s;
+#pragma unroll
+    for (int j = 0; j < K; ++j) s.x[j] = (j < p.kd) ? static_cast<const T *>(p.tcols[j]) : nullptr;
+    s.y = static_cast<const T *>(p.tcols[p.kd]);
+    s.w = static_cast<const T *>(p.tw);
+    s.mask = static_cast<const T *>(p.tmask);
+    s.r0 = p.chunk_r0[chunk];
+    s.c = chunk;
+    s.nch = p.n_chunks;
+    s.L = p.chunk_len;
+    s.shift = p.chunk_shift;
+    s.kd = p.kd;
+    s.w_is_sqrt = p.w_is_sqrt;
+    return s;
+}
+
+// dst[i * n_chunks + ch] = src[chunk_r0[ch] + i]: 32 x 32 tiles through shared memory, coalesced on both sides.
+// blockIdx.z = column slot (features, target, weights, mask).
+struct TransposeParams {
+    const void *src[GRAM_MAX_COLS];
+    void *dst[GRAM_MAX_COLS];
+    const int64_t *chunk_r0, *chunk_r1;
+    int64_t n_chunks, chunk_len;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) chunk_transpose_kernel(const TransposeParams p) {
+    __shared__ T tile[32][33];
+    const T *src = static_cast<const T *>(p.src[blockIdx.z]);
+    T *dst = static_cast<T *>(p.dst[blockIdx.z]);
+    const int64_t ch0 = static_cast<int64_t>(blockIdx.x) * 32, i0 = static_cast<int64_t>(blockIdx.y) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+    for (int k = ty; k < 32; k += 8) {  // chunk ch0 + k, rows i0 + tx
+        const int64_t ch = ch0 + k;
+        T v = T(0);
+        if (ch < p.n_chunks) {
+            const int64_t r = p.chunk_r0[ch] + i0 + tx;
+            if (r < p.chunk_r1[ch]) v = src[r];
+        }
+        tile[k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {  // row i0 + k, chunks ch0 + tx
+        const int64_t ch = ch0 + tx, i = i0 + k;
+        if (ch < p.n_chunks && i < p.chunk_len) dst[i * p.n_chunks + ch] = tile[tx][k];
+    }
+}
+
+template <typename T, int K, typename SrcT>
 struct DevEmit {
     const MovingParams &p;
-    const DevSrc<T, K> &src;
+    const SrcT &src;
     __device__ __forceinline__ void operator()(int64_t r, const double (&beta)[K], bool) const {
         const int64_t orow = p.row_index ? p.row_index[r] : r;
         if (p.mode == 2) {
@@ -137,7 +224,7 @@ template <typename T, int K>
 __global__ void __launch_bounds__(128) rolling_main_kernel(const MovingParams p) {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
-    const DevSrc<T, K> src = make_src<T, K>(p);
+    const DevSrcT<T, K> src = make_src_t<T, K>(p, c);
     const int64_t g = p.chunk_group[c];
     const int64_t g0 = p.group_off[g], g1 = p.group_off[g + 1];
     RollingSeries rs;
@@ -151,7 +238,7 @@ __global__ void __launch_bounds__(128) rolling_main_kernel(const MovingParams p)
         rs.all_nan = (g1 - g0) < p.min_periods;
     }
     RollingCfg cfg{p.window, p.min_periods, p.alpha, p.fixed_window};
-    DevEmit<T, K> emit{p, src};
+    DevEmit<T, K, DevSrcT<T, K>> emit{p, src};
     rolling_chunk<K>(src, cfg, rs, g0, g1, p.chunk_r0[c], p.chunk_r1[c], emit);
 }
 
@@ -159,7 +246,7 @@ template <typename T, int K>
 __global__ void __launch_bounds__(128) rls_summary_kernel(const MovingParams p) {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
-    const DevSrc<T, K> src = make_src<T, K>(p);
+    const DevSrcT<T, K> src = make_src_t<T, K>(p, c);
     RlsCfg cfg{p.lambda, p.p0};
     RlsSummary<K> s;
     rls_summarise<K>(src, cfg, p.chunk_r0[c], p.chunk_r1[c], s);
@@ -269,7 +356,7 @@ template <typename T, int K>
 __global__ void __launch_bounds__(128) rls_main_kernel(const MovingParams p) {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
-    const DevSrc<T, K> src = make_src<T, K>(p);
+    const DevSrcT<T, K> src = make_src_t<T, K>(p, c);
     const int64_t g = p.chunk_group[c];
     const int64_t r0 = p.chunk_r0[c];
     const bool first = r0 == p.group_off[g];
@@ -284,27 +371,26 @@ __global__ void __launch_bounds__(128) rls_main_kernel(const MovingParams p) {
             in.v[i] = rec[K * K + i];
         }
     }
-    DevEmit<T, K> emit{p, src};
+    DevEmit<T, K, DevSrcT<T, K>> emit{p, src};
     rls_chunk<K>(src, cfg, first, p.has_mean ? p.mean : nullptr, &in, r0, p.chunk_r1[c], emit);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
 inline int64_t moving_chunk_len(int64_t n_rows, int sm_count, int kind, int64_t window) {
-    int64_t L = (n_rows + static_cast<int64_t>(sm_count) * 1024 - 1) / (static_cast<int64_t>(sm_count) * 1024);
-    L = ((L + 63) / 64) * 64;
-    if (L < 64) L = 64;
-    if (kind == MOVING_ROLLING) {
-        const int64_t w4 = std::min<int64_t>(window, 1 << 16) / 4;
-        if (L < w4) L = ((w4 + 63) / 64) * 64;
-    }
+    int64_t want = (n_rows + static_cast<int64_t>(sm_count) * 1024 - 1) / (static_cast<int64_t>(sm_count) * 1024);
+    if (kind == MOVING_ROLLING) want = std::max<int64_t>(want, std::min<int64_t>(window, 1 << 16) / 4);
+    int64_t L = 64;  // power of two (the chunk-interleaved addressing shifts instead of dividing)
+    while (L < want) L <<= 1;
     return L;
 }
 
-inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int /*F*/) {
+inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int F) {
     const size_t max_chunks = static_cast<size_t>(n_rows / 64 + n_groups + 2);
     const size_t max_super = max_chunks / 256 + static_cast<size_t>(n_groups) + 2;
     return max_chunks * (MOVING_REC * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (3 * 8 + 8 + 8) +
-           max_super * (MOVING_REC * 8 + 16) + 16384;
+           max_super * (MOVING_REC * 8 + 16) + 16384 +
+           // chunk-interleaved column copies: (F + 3) columns x padded rows (every series pads < one chunk)
+           static_cast<size_t>(F + 3) * (static_cast<size_t>(n_rows) * 2 + static_cast<size_t>(n_groups + 1) * 64 + 4096) * 8;
 }
 
 template <typename T, int K>
@@ -312,6 +398,20 @@ static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const i
                                    int64_t *launches) {
     const unsigned cb = static_cast<unsigned>((p.n_chunks + 127) / 128);
     if (p.n_chunks == 0) return cudaSuccess;
+    {   // chunk-interleaved copies of every input column (one coalesced read + write of the data)
+        TransposeParams tp;
+        int nc = 0;
+        for (int j = 0; j <= p.kd; ++j) { tp.src[nc] = p.cols[j]; tp.dst[nc] = const_cast<void *>(p.tcols[j]); ++nc; }
+        if (p.w) { tp.src[nc] = p.w; tp.dst[nc] = const_cast<void *>(p.tw); ++nc; }
+        if (p.mask) { tp.src[nc] = p.mask; tp.dst[nc] = const_cast<void *>(p.tmask); ++nc; }
+        tp.chunk_r0 = p.chunk_r0;
+        tp.chunk_r1 = p.chunk_r1;
+        tp.n_chunks = p.n_chunks;
+        tp.chunk_len = p.chunk_len;
+        const dim3 grid(static_cast<unsigned>((p.n_chunks + 31) / 32), static_cast<unsigned>((p.chunk_len + 31) / 32), static_cast<unsigned>(nc));
+        chunk_transpose_kernel<T><<<grid, 256, 0, stream>>>(tp);
+        ++*launches;
+    }
     if (p.kind == MOVING_ROLLING) {
         if (p.mask) {
             rolling_prepass_kernel<T, K><<<static_cast<unsigned>((p.n_groups + 127) / 128), 128, 0, stream>>>(p);
