@@ -94,7 +94,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_run(x, y, offsets, steps: int, warmup: int, min_seconds: float = 0.0):
+def cpu_port_run(x, y, offsets, steps: int, warmup: int, min_seconds: float = 0.0, tune_threads: bool = True):
     """times the CPU restatement of the reference's per-group path (oracle/ols_oracle.c, OpenMP over groups =
     polars' rayon pool) on the host cores.  Each step = the full 10k-group batch."""
     import ctypes as C
@@ -104,10 +104,26 @@ def cpu_port_run(x, y, offsets, steps: int, warmup: int, min_seconds: float = 0.
     arr = (C.c_void_p * (K + 1))(*[c.ctypes.data for c in cols])
     out = np.empty((G, K))
     threads = L.orc_max_threads()
+    n_threads = [0]  # 0 = the OpenMP default
 
     def step():
-        L.orc_grouped_least_squares_coefficients(arr, K, offsets.ctypes.data, G, 0, ALPHA, 0.0, 1000, 1e-5, 0, 0, out.ctypes.data)
+        L.orc_grouped_least_squares_coefficients(arr, K, offsets.ctypes.data, G, 0, ALPHA, 0.0, 1000, 1e-5, 0, n_threads[0], out.ctypes.data)
 
+    if tune_threads:
+        # give the CPU arm its best thread count: all logical CPUs vs one thread per physical core (SMT rarely helps
+        # this memory-bound loop); 3 untimed batches each, keep the faster
+        ncpu = os.cpu_count() or threads
+        best = None
+        for cand in sorted({ncpu, max(1, ncpu // 2), threads}, reverse=True):
+            n_threads[0] = cand
+            step()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                step()
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, cand)
+        n_threads[0] = threads = best[1]
     for _ in range(warmup):
         step()
     times = []

@@ -205,6 +205,16 @@ B200OLS_API int b200ols_rolling_least_squares(b200ols_ctx *ctx, const b200ols_fr
 B200OLS_API int b200ols_rolling_least_squares_coefficients(b200ols_ctx *ctx, const b200ols_frame *frame,
                                                const b200ols_rolling_kwargs *kwargs, b200ols_output *out);
 
+/* "next" row: replaces _polars_plugin_predict (src/expressions.rs:706-741).
+ * coefficients: n_coef Float64 child arrays of the coefficient struct Series (one value per ROW, e.g. the
+ * broadcast result of `.over()` or the per-row output of rls / rolling); features: n_coef - add_intercept
+ * columns of `dtype`.  predictions[r] = sum_j feature_j[r] * coefficient_j[r] (+ coefficient_last[r] when
+ * add_intercept).  Null features are zero-filled unless null_policy == IGNORE (-> NaN); DROP masks rows with
+ * any null input.  out->values[n_rows] (+ optional validity bytes). */
+B200OLS_API int b200ols_predict(b200ols_ctx *ctx, int64_t n_rows, int32_t n_coef, int32_t dtype, int32_t memspace,
+                                const b200ols_column *coefficients, const b200ols_column *features,
+                                int32_t add_intercept, int32_t null_policy, b200ols_output *out);
+
 /* Per-group diagnostics of the last static call on ctx (host copy): bit 0 = Cholesky failed and the
  * LU fallback ran (src/least_squares.rs:299-316), bit 1 = group had no rows after null filtering
  * (coefficients = 0, src/expressions.rs:357-359), bit 2 = re-solved by the pivoted-QR kernel

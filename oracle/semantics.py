@@ -376,6 +376,26 @@ def rolling_least_squares(target, *features, sample_weights=None, add_intercept=
     return _finish_predictions(plugin_rolling_least_squares([t_fit, *f_fit], kw), target, sqrt_w, mode, True)
 
 
+def predict(coefficients: Sequence, features: Sequence, null_policy: str = "zero", add_intercept: bool = False) -> Col:
+    """predict (src/expressions.rs:706-741 + polars_ols/least_squares.py:455-491): rowwise
+    (features * coefficients).sum(1); features zero-filled unless 'ignore'; 'drop' masks rows with any null input."""
+    coefs = [as_col(c) for c in coefficients]
+    feats = [as_col(f) for f in features]
+    if add_intercept:
+        feats = feats + [(np.ones(len(coefs[0][0])), None)]
+    assert len(coefs) == len(feats), "number of coefficients must match number of features!"
+    fill = np.nan if null_policy == "ignore" else 0.0
+    x = np.stack([_to_f64(f, fill) for f in feats], axis=1)
+    c = np.stack([_to_f64(cc, np.nan) for cc in coefs], axis=1)
+    pred = (x * c).sum(axis=1)
+    if null_policy == "drop":
+        m = np.ones(len(pred), dtype=bool)
+        for col_ in coefs + feats:
+            m &= _is_valid(col_)
+        return pred, m
+    return pred, None
+
+
 # ---------------------------------------------------------------------------------------------
 # polars `.over(group)`: split rows by key (order preserved inside a group), one call per group,
 # scatter back.  Static coefficients (returns_scalar) are broadcast to the group's rows.

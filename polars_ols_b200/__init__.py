@@ -15,6 +15,7 @@ from .least_squares import (  # noqa: F401
     NullPolicy,
     OLSKwargs,
     OutputMode,
+    PredictExpr,
     Result,
     RLSKwargs,
     RollingKwargs,
@@ -23,6 +24,7 @@ from .least_squares import (  # noqa: F401
     compute_least_squares,
     compute_recursive_least_squares,
     compute_rolling_least_squares,
+    predict,
 )
 
 __version__ = "0.1.0"

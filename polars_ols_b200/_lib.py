@@ -28,7 +28,7 @@ EXPORTS = [
     "b200ols_host_free", "b200ols_set_tuning", "b200ols_set_variant", "b200ols_set_profiling", "b200ols_profile_drain", "b200ols_least_squares",
     "b200ols_least_squares_coefficients", "b200ols_recursive_least_squares",
     "b200ols_recursive_least_squares_coefficients", "b200ols_rolling_least_squares",
-    "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags",
+    "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags", "b200ols_predict",
 ]
 
 
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     L.b200ols_rolling_least_squares.argtypes = [vp, C.POINTER(Frame), C.POINTER(RollingKwargs), i32, C.POINTER(Output)]
     L.b200ols_rolling_least_squares_coefficients.argtypes = [vp, C.POINTER(Frame), C.POINTER(RollingKwargs), C.POINTER(Output)]
     L.b200ols_last_group_flags.argtypes = [vp, vp, i64]
+    L.b200ols_predict.argtypes = [vp, i64, i32, i32, i32, C.POINTER(Column), C.POINTER(Column), i32, i32, C.POINTER(Output)]
     _lib = L
     return L
 

@@ -1002,6 +1002,120 @@ extern "C" int b200ols_least_squares_coefficients(b200ols_ctx *c, const b200ols_
 }
 
 // ------------------------------------------------------------------------------------------------
+// predict (src/expressions.rs:706-741): row-wise dot of features with a per-row coefficient struct
+// ------------------------------------------------------------------------------------------------
+struct RowDotParams {
+    const void *feat[GRAM_MAX_COLS];
+    const uint8_t *feat_valid[GRAM_MAX_COLS];
+    const double *coef[GRAM_MAX_COLS];
+    const uint8_t *coef_valid[GRAM_MAX_COLS];
+    int n_coef, n_feat, fill_nan, drop;
+    int64_t n_rows;
+    double *out;
+    uint8_t *out_valid;
+};
+
+template <typename T>
+static __global__ void __launch_bounds__(256) rowdot_kernel(const RowDotParams p) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n_rows; r += stride) {
+        double acc = 0.0;
+        bool all_valid = true;
+        for (int j = 0; j < p.n_coef; ++j) {
+            bool cv = p.coef_valid[j] ? ((p.coef_valid[j][r >> 3] >> (r & 7)) & 1) : true;
+            const double c = cv ? p.coef[j][r] : static_cast<double>(NAN);
+            double x = 1.0;  // the `const` feature appended by add_intercept (polars_ols/least_squares.py:479-483)
+            if (j < p.n_feat) {
+                const bool xv = p.feat_valid[j] ? ((p.feat_valid[j][r >> 3] >> (r & 7)) & 1) : true;
+                all_valid = all_valid && xv;
+                x = xv ? static_cast<double>(static_cast<const T *>(p.feat[j])[r]) : (p.fill_nan ? static_cast<double>(NAN) : 0.0);
+            }
+            all_valid = all_valid && cv;
+            acc += x * c;  // (&features * &coefficients).sum_axis(Axis(1))
+        }
+        p.out[r] = acc;
+        if (p.out_valid) p.out_valid[r] = (!p.drop || all_valid) ? 1 : 0;
+    }
+}
+
+extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, int32_t dtype, int32_t memspace,
+                               const b200ols_column *coefficients, const b200ols_column *features, int32_t add_intercept,
+                               int32_t null_policy, b200ols_output *out) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (!coefficients || !out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    if (n_rows < 0 || n_coef < 1 || n_coef > 64) return fail(B200OLS_ERR_INVALID, "bad shape");
+    const int n_feat = n_coef - (add_intercept ? 1 : 0);
+    // src/expressions.rs:717-721 "number of coefficients must match number of features!"
+    if (n_feat < 0 || (n_feat > 0 && !features)) return fail(B200OLS_ERR_INVALID, "number of coefficients must match number of features!");
+    if (dtype != B200OLS_F64 && dtype != B200OLS_F32) return fail(B200OLS_ERR_INVALID, "bad dtype %d", dtype);
+    if (null_policy < B200OLS_NULL_IGNORE || null_policy > B200OLS_NULL_DROP_WINDOW) return fail(B200OLS_ERR_INVALID, "Invalid null_policy detected!");
+    CU(cudaSetDevice(c->device));
+    TRY(free_retired(c));
+    const size_t esz = dtype == B200OLS_F64 ? 8 : 4;
+    const size_t bm = static_cast<size_t>((n_rows + 7) / 8);
+    size_t bytes = 1 << 20;
+    if (memspace == B200OLS_HOST) bytes += static_cast<size_t>(n_coef) * 2 * (static_cast<size_t>(n_rows) * 8 + bm + 1024) + static_cast<size_t>(n_rows) * 9 + 4096;
+    TRY(arena_reserve(c, bytes));
+    c->arena_off = 0;
+    TRY(pinned_begin(c));
+    c->last_flags = nullptr;
+    RowDotParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.n_coef = n_coef;
+    rp.n_feat = n_feat;
+    rp.fill_nan = null_policy == B200OLS_NULL_IGNORE;
+    rp.drop = null_policy == B200OLS_NULL_DROP;
+    rp.n_rows = n_rows;
+    auto stage = [&](const b200ols_column &col, size_t es, const void **v, const uint8_t **m) -> int {
+        if (memspace == B200OLS_DEVICE) {
+            *v = col.values;
+            *m = col.validity;
+            return 0;
+        }
+        char *d = arena_alloc<char>(c, static_cast<size_t>(n_rows) * es + 16);
+        if (n_rows) CU(cudaMemcpyAsync(d, col.values, static_cast<size_t>(n_rows) * es, cudaMemcpyHostToDevice, c->stream));
+        *v = d;
+        *m = nullptr;
+        if (col.validity) {
+            uint8_t *b = arena_alloc<uint8_t>(c, bm + 16);
+            CU(cudaMemcpyAsync(b, col.validity, bm, cudaMemcpyHostToDevice, c->stream));
+            *m = b;
+        }
+        return 0;
+    };
+    for (int j = 0; j < n_coef; ++j) {
+        const void *v;
+        TRY(stage(coefficients[j], 8, &v, &rp.coef_valid[j]));
+        rp.coef[j] = static_cast<const double *>(v);
+        if (j < n_feat) TRY(stage(features[j], esz, &rp.feat[j], &rp.feat_valid[j]));
+    }
+    double *dout = out->values;
+    uint8_t *dval = out->validity;
+    if (memspace == B200OLS_HOST) {
+        dout = arena_alloc<double>(c, static_cast<size_t>(n_rows));
+        dval = out->validity ? arena_alloc<uint8_t>(c, static_cast<size_t>(n_rows)) : nullptr;
+    }
+    rp.out = dout;
+    rp.out_valid = dval;
+    ARENA_GUARD(c);
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((n_rows + 255) / 256, static_cast<int64_t>(c->sm_count) * 16));
+    {
+        ProfScope prof(c);
+        if (dtype == B200OLS_F64) rowdot_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(rp);
+        else rowdot_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(rp);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    if (memspace == B200OLS_HOST) {
+        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * n_rows, cudaMemcpyDeviceToHost, c->stream));
+        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(n_rows), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (c->pinned) pinned_end(c);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // moving-window models: rls / rolling (moving.cuh)
 // ------------------------------------------------------------------------------------------------
 int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets, bool f64, int sm_count, char *ws,

@@ -82,8 +82,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
         // ================================ PRODUCER ================================
         int stage = 0;
         uint32_t phase = 0;
+        // segment bounds are fetched one segment ahead (their HBM/L2 latency would otherwise sit on the critical
+        // path of every small group)
+        int64_t nr0 = 0, nr1 = 0;
+        if (static_cast<int64_t>(blockIdx.x) < nseg) { nr0 = p.seg_off[blockIdx.x]; nr1 = p.seg_off[blockIdx.x + 1]; }
         for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-            const int64_t r0 = p.seg_off[seg], r1 = p.seg_off[seg + 1];
+            const int64_t r0 = nr0, r1 = nr1;
+            if (seg + gridDim.x < nseg) { nr0 = p.seg_off[seg + gridDim.x]; nr1 = p.seg_off[seg + gridDim.x + 1]; }
             for (int64_t row = r0; row < r1; row += R) {
                 const int64_t b = (row + R < r1) ? row + R : r1;
                 const int64_t a_al = row & ~static_cast<int64_t>(A - 1);
@@ -112,8 +117,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
         int stage = 0;
         uint32_t phase = 0;
         uint32_t red_i = 0;
+        int64_t nr0 = 0, nr1 = 0;
+        if (static_cast<int64_t>(blockIdx.x) < nseg) { nr0 = p.seg_off[blockIdx.x]; nr1 = p.seg_off[blockIdx.x + 1]; }
         for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-            const int64_t r0 = p.seg_off[seg], r1 = p.seg_off[seg + 1];
+            const int64_t r0 = nr0, r1 = nr1;
+            if (seg + gridDim.x < nseg) { nr0 = p.seg_off[seg + gridDim.x]; nr1 = p.seg_off[seg + gridDim.x + 1]; }
             constexpr bool DUAL = KB <= 2;
             double acc[NPAIR][2], acc2[DUAL ? NPAIR : 1][2];
             double cy[KB];

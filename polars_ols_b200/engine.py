@@ -305,6 +305,35 @@ class Engine:
         return v, m
 
 
+    def predict(self, coefficients: List[Col], features: List[Col], add_intercept: bool, null_policy: int):
+        """b200ols_predict: row-wise dot of features with per-row coefficient columns."""
+        n = len(coefficients[0])
+        dev = coefficients[0].is_device
+        for c_ in coefficients:
+            if dev:
+                if c_.values.dtype != torch.float64:
+                    c_.values = c_.values.to(torch.float64)
+            elif c_.values.dtype != np.float64 or not c_.values.flags.c_contiguous:
+                c_.values = np.ascontiguousarray(c_.values, dtype=np.float64)
+        f32 = len(features) > 0 and all((f.values.dtype == (torch.float32 if dev else np.float32)) for f in features)
+        for f in features:
+            if dev:
+                want = torch.float32 if f32 else torch.float64
+                if f.values.dtype != want:
+                    f.values = f.values.to(want)
+            else:
+                want = np.float32 if f32 else np.float64
+                if f.values.dtype != want or not f.values.flags.c_contiguous:
+                    f.values = np.ascontiguousarray(f.values, dtype=want)
+        cc = (L.Column * len(coefficients))(*[L.Column(_ptr(c_.values), _ptr(c_.validity)) for c_ in coefficients])
+        ff = (L.Column * max(len(features), 1))(*[L.Column(_ptr(f.values), _ptr(f.validity)) for f in features])
+        memspace = L.DEVICE if dev else L.HOST
+        o, v, m = self._alloc_out(memspace, (n,), True, coefficients[0].values)
+        L.check(self._lib.b200ols_predict(self._ctx, n, len(coefficients), L.F32 if f32 else L.F64, memspace, cc, ff,
+                                          1 if add_intercept else 0, null_policy, C.byref(o)))
+        return v, m
+
+
 _engines = {}
 
 CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle of the (legacy) default stream

@@ -36,7 +36,7 @@ logger = logging.getLogger(__name__)
 __all__ = [
     "compute_least_squares", "compute_recursive_least_squares", "compute_rolling_least_squares",
     "OLSKwargs", "RLSKwargs", "RollingKwargs", "NullPolicy", "OutputMode", "SolveMethod",
-    "LeastSquares", "Frame", "col", "Expr", "Result",
+    "LeastSquares", "Frame", "col", "Expr", "Result", "predict", "PredictExpr",
 ]
 
 NullPolicy = Literal["zero", "drop", "ignore", "drop_zero", "drop_y_zero_x", "drop_window"]
@@ -284,6 +284,49 @@ class LsExpr:
         return Result(self.output_name, v, m)
 
 
+class PredictExpr:
+    """Pending `predict` expression (reference polars_ols/least_squares.py:455-491)."""
+
+    def __init__(self, coefficients: Expr, features: List[Expr], null_policy: str, add_intercept: bool, name: Optional[str]):
+        self.coefficients, self.features = coefficients, features
+        self.null_policy, self.add_intercept, self.output_name = null_policy, add_intercept, name or "predictions"
+
+    def alias(self, name: str) -> "PredictExpr":
+        self.output_name = name
+        return self
+
+    def evaluate(self, frame: "Frame", engine: Optional[Engine] = None) -> Result:
+        coef = self.coefficients._data if self.coefficients._data is not None else frame[self.coefficients._name]
+        if isinstance(coef, Result):
+            coef = coef.to_numpy(broadcast=True)
+        if isinstance(coef, dict):                      # struct column as {field: array}
+            cols = [as_col(v) for v in coef.values()]
+        elif _is_torch(coef):
+            cols = [as_col(coef[:, j].contiguous()) for j in range(coef.shape[1])]
+        else:
+            a = np.asarray(coef, dtype=np.float64)      # [N, k]; NaN <=> null field (fill_nan(NULL) at src/expressions.rs:137-139)
+            cols = [Col(np.ascontiguousarray(a[:, j])) for j in range(a.shape[1])]
+            cols = [Col(c.values, None if not np.isnan(c.values).any() else np.packbits(~np.isnan(c.values), bitorder="little")) for c in cols]
+        feats = [f.resolve(frame) for f in self.features]
+        add_intercept = self.add_intercept
+        if add_intercept and any(f.output_name == "const" for f in self.features):
+            logger.warning("feature named 'const' already detected, assuming it is the intercept")
+            add_intercept = False
+        assert len(cols) == len(feats) + (1 if add_intercept else 0), "number of coefficients must match number of features!"
+        if engine is None:
+            dev = cols[0].values.device.index if cols[0].is_device else 0
+            engine = get_engine(dev or 0, torch_stream=cols[0].is_device)
+        v, m = engine.predict(cols, feats, add_intercept, L.NULL_POLICY[self.null_policy])
+        return Result(self.output_name, v, m)
+
+
+def predict(coefficients: ExprOrStr, *features: ExprOrStr, null_policy: NullPolicy = "zero", add_intercept: bool = False,
+            name: Optional[str] = None) -> PredictExpr:
+    """reference polars_ols/least_squares.py:455-491"""
+    assert null_policy in _VALID_NULL_POLICIES, "'null_policy' must be one of {drop, ignore, zero}"
+    return PredictExpr(parse_into_expr(coefficients), [parse_into_expr(f) for f in features], null_policy, add_intercept, name)
+
+
 class Frame(dict):
     """Minimal stand-in for ``pl.DataFrame``: a dict of equal-length columns (numpy arrays, pyarrow arrays,
     ``(values, valid_mask)`` pairs, numpy masked arrays or CUDA torch tensors)."""
@@ -387,3 +430,7 @@ class LeastSquares:
 
     def expanding_ols(self, *features: ExprOrStr, **kwargs) -> LsExpr:
         return self.rls(*features, half_life=None, **kwargs)
+
+    def predict(self, *features: ExprOrStr, name: Optional[str] = None, add_intercept: bool = False,
+                null_policy: NullPolicy = "zero") -> "PredictExpr":
+        return predict(self._expr, *features, add_intercept=add_intercept, name=name, null_policy=null_policy)

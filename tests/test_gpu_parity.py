@@ -326,3 +326,34 @@ def test_full_size_c2_normal_equation_property():
     ys = y.reshape(G, n)[sel].cpu().numpy()
     ref = np.stack([S.solve_ridge(np.ascontiguousarray(ys[i]), np.ascontiguousarray(xs[i]), alpha, None, None) for i in range(len(sel))])
     _close(coef[sel].cpu().numpy(), ref)
+
+
+# ----------------------------------------------------------------------------------- predict (§8f rank 1)
+def test_predict_matches_dot_product():                                    # tests/test_ols.py:903-944
+    d = _make_data(5000, 2, n_groups=3)
+    F = Frame(d)
+    coef = F.select(col("y").least_squares.ols("x1", "x2", mode="coefficients").over("group"))["coefficients"]
+    test = _make_data(40, 2, n_groups=3, seed=12)
+    cb = coef.to_numpy()[np.searchsorted(coef.keys, test["group"])]         # the join on "group"
+    Ft = Frame({"coefficients": cb, "x1": test["x1"], "x2": test["x2"]})
+    p = Ft.select(col("coefficients").least_squares.predict(col("x1"), col("x2"), name="predictions", null_policy="zero"))["predictions"]
+    expected = (np.c_[test["x1"], test["x2"]] * cb).sum(1)
+    _close(p.to_numpy(), expected)
+
+
+def test_predict_intercept_and_null_policies():                            # tests/test_ols.py:947-966
+    d = {"y": np.array([1.0, 2, 3, 4]), "x1": np.array([3.0, 4, 5, 6]), "x2": np.array([4.0, 5, 6, 7]), "x3": np.array([5.0, 6, 7, 8])}
+    F = Frame(d)
+    c = F.select(col("y").least_squares.ridge("x1", "x2", "x3", alpha=1e-9, add_intercept=True, mode="coefficients"))["coefficients"]
+    F["coefficients"] = np.broadcast_to(c.to_numpy()[0], (4, 4)).copy()
+    p = F.select(col("coefficients").least_squares.predict("x1", "x2", "x3", add_intercept=True).alias("y_pred"))["y_pred"]
+    ref = S.predict([F["coefficients"][:, j] for j in range(4)], [d["x1"], d["x2"], d["x3"]], "zero", True)
+    _close(p.to_numpy(), _ref(ref))
+    # nulls in the features
+    dm = _make_data(3000, 3, add_missing=True, seed=21)
+    cb = np.random.default_rng(0).normal(size=(3000, 3))
+    Fm = Frame({**dm, "coefficients": cb})
+    for pol in ("zero", "ignore", "drop"):
+        p = Fm.select(col("coefficients").least_squares.predict("x1", "x2", "x3", null_policy=pol))["predictions"]
+        ref = S.predict([cb[:, j] for j in range(3)], [dm["x1"], dm["x2"], dm["x3"]], pol)
+        _close(p.to_numpy(), _ref(ref))
