@@ -97,18 +97,26 @@ struct b200ols_ctx {
     int64_t last_flags_n = 0;
     // last uploaded group-offset table (steady-state loops re-use it instead of re-copying every call)
     std::vector<int64_t> plan_offsets;
+    int64_t plan_max_rows = 0, plan_wide_group = -1;
+    int plan_F = -1;
     int64_t *plan_dev = nullptr;
     size_t plan_cap = 0;
     // optional device-side timing of the dominant kernel
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
+    std::vector<cudaEvent_t> event_pool;
 };
 
 struct ProfScope {  // brackets a launch with events when profiling is on
     b200ols_ctx *c;
     cudaEvent_t a = nullptr, b = nullptr;
     explicit ProfScope(b200ols_ctx *ctx) : c(ctx) {
-        if (c->profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, c->stream);
+        if (!c->profiling) return;
+        auto get = [&](cudaEvent_t *ev) {
+            if (!c->event_pool.empty()) { *ev = c->event_pool.back(); c->event_pool.pop_back(); return true; }
+            return cudaEventCreate(ev) == cudaSuccess;
+        };
+        if (get(&a) && get(&b)) cudaEventRecord(a, c->stream);
     }
     ~ProfScope() {
         if (a && b) {
@@ -282,8 +290,8 @@ extern "C" int b200ols_profile_drain(b200ols_ctx *c, float *ms, int max) {
         float t = 0.f;
         cudaEventElapsedTime(&t, pr.first, pr.second);
         if (ms && n < max) ms[n++] = t;
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        c->event_pool.push_back(pr.first);
+        c->event_pool.push_back(pr.second);
     }
     c->prof.clear();
     return n;
@@ -334,6 +342,7 @@ struct Staged {
     int64_t n_groups = 1;
     std::vector<int64_t> offsets;          // host copy [G+1]
     int64_t max_group_rows = 0;
+    int64_t wide_group = -1;               // first group with 0 < n <= k (needs the min-norm SVD path), or -1
     bool prepped = false;
 };
 
@@ -402,18 +411,34 @@ static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool 
     st->F = kd + st->intercept;
     st->has_w = f->sample_weights ? 1 : 0;
     st->n_groups = f->n_groups;
-    st->offsets.resize(static_cast<size_t>(f->n_groups) + 1);
-    if (f->group_offsets) {
+    if (f->group_offsets && c->plan_offsets.size() == static_cast<size_t>(f->n_groups) + 1 &&
+        std::memcmp(c->plan_offsets.data(), f->group_offsets, sizeof(int64_t) * (f->n_groups + 1)) == 0) {
+        // same grouping as the previous call (steady-state loops): reuse the validated host copy
+        st->offsets = c->plan_offsets;
+        st->max_group_rows = c->plan_max_rows;
+        st->wide_group = c->plan_wide_group;
+        if (c->plan_F != st->F) {  // the "n <= k" test depends on the number of coefficients
+            st->wide_group = -1;
+            for (int64_t g = 0; g < f->n_groups && st->wide_group < 0; ++g) {
+                const int64_t len = st->offsets[g + 1] - st->offsets[g];
+                if (len > 0 && len <= st->F) st->wide_group = g;
+            }
+        }
+    } else if (f->group_offsets) {
+        st->offsets.resize(static_cast<size_t>(f->n_groups) + 1);
         std::memcpy(st->offsets.data(), f->group_offsets, sizeof(int64_t) * (f->n_groups + 1));
         for (int64_t g = 0; g < f->n_groups; ++g) {
             const int64_t len = st->offsets[g + 1] - st->offsets[g];
             if (len < 0) return fail(B200OLS_ERR_INVALID, "group_offsets must be non-decreasing");
             st->max_group_rows = std::max(st->max_group_rows, len);
+            if (len > 0 && len <= st->F && st->wide_group < 0) st->wide_group = g;
         }
     } else {
+        st->offsets.resize(2);
         st->offsets[0] = 0;
         st->offsets[1] = n;
         st->max_group_rows = n;
+        if (n > 0 && n <= st->F) st->wide_group = 0;
     }
 
     const int ncol = kd + 1 + st->has_w;  // features, target, weights
@@ -557,6 +582,9 @@ static int build_plan(b200ols_ctx *c, const Staged &st, int64_t seg_max, Plan *p
         c->pinned_off += round_up(bytes, 256);
         CU(cudaMemcpyAsync(c->plan_dev, h, bytes, cudaMemcpyHostToDevice, c->stream));
         c->plan_offsets = st.offsets;
+        c->plan_max_rows = st.max_group_rows;
+        c->plan_wide_group = st.wide_group;
+        c->plan_F = st.F;
         pl->seg_off = c->plan_dev;
         return 0;
     }
@@ -820,14 +848,11 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     c->last_flags_n = G;
 
     // wide / under-determined groups take the LAPACK SVD path in the reference (src/least_squares.rs:225-229)
-    if (rt.ols_qr_guard && !st.prepped) {
-        for (int64_t g = 0; g < G; ++g) {
-            const int64_t len = st.offsets[g + 1] - st.offsets[g];
-            if (len > 0 && len <= F)
-                return fail(B200OLS_ERR_UNSUPPORTED,
-                            "group %lld has n=%lld <= k=%d rows: the min-norm SVD path is not implemented on the device yet",
-                            (long long)g, (long long)len, F);
-        }
+    if (rt.ols_qr_guard && !st.prepped && st.wide_group >= 0) {
+        const int64_t g = st.wide_group;
+        return fail(B200OLS_ERR_UNSUPPORTED,
+                    "group %lld has n=%lld <= k=%d rows: the min-norm SVD path is not implemented on the device yet",
+                    (long long)g, (long long)(st.offsets[g + 1] - st.offsets[g]), F);
     }
 
     GramParams gp;

@@ -307,8 +307,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
 template <typename T, int KB>
 cudaError_t gram_cta_launch_t(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     auto kern = gram_cta_kernel<T, KB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
+    static size_t attr_set[64] = {};  // per device: the opt-in shared-memory size already granted to this kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem > attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = smem;
+    }
     kern<<<grid, CTA_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
