@@ -209,7 +209,7 @@ def main():
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     ev_done = [torch.cuda.Event() for _ in range(2)]     # kernel i finished writing coefs[i & 1]
     ev_gath = [torch.cuda.Event() for _ in range(2)]     # gather of coefs[i & 1] finished reading it
-    gathered = [None]
+    gathered = [torch.empty((world * G, K), dtype=torch.float64, device=dev) if world > 1 else None]
 
     def full_step(i):
         b = i & 1
@@ -222,7 +222,7 @@ def main():
         ev_done[b].record(cur)
         comm.wait_event(ev_done[b])
         with torch.cuda.stream(comm):
-            gathered[0] = gather_group_results(coefs[b], shards)  # NCCL all-gather of the coefficient chunks
+            gather_group_results(coefs[b], shards, out=gathered[0])  # ONE NCCL all-gather of the coefficient chunks
             ev_gath[b].record(comm)
 
     def drain():

@@ -27,8 +27,9 @@ def shard_groups(offsets: np.ndarray, world_size: int) -> List[Tuple[int, int]]:
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
-def gather_group_results(local, shards: List[Tuple[int, int]], group=None):
+def gather_group_results(local, shards: List[Tuple[int, int]], group=None, out=None):
     """all-gather of per-rank [g_local, k] chunks into the full [G, k] tensor on every rank.
+    Equal shards: ONE all_gather_into_tensor straight into `out` (pre-allocated by steady-state callers).
     Ragged shards are padded to the largest one (a single fixed-size all_gather_into_tensor — over
     NVLink/NVSwitch with NCCL — then compacted)."""
     import torch
@@ -37,6 +38,11 @@ def gather_group_results(local, shards: List[Tuple[int, int]], group=None):
     world = dist.get_world_size(group)
     k = local.shape[1]
     gmax = max(b - a for a, b in shards)
+    if all(b - a == gmax for a, b in shards):
+        if out is None:
+            out = torch.empty((world * gmax, k), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = torch.zeros((gmax, k), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = torch.empty((world * gmax, k), dtype=local.dtype, device=local.device)

@@ -116,6 +116,12 @@ def _gloo_worker(rank, world, port, q):
     a, b = shards[rank]
     local = torch.arange(a, b, dtype=torch.float64)[:, None] * torch.ones(1, 3, dtype=torch.float64)  # "coefficients" = group id
     full = gather_group_results(local, shards)
+    # equal shards take the single-collective path (one all_gather_into_tensor straight into `out`)
+    eq = [(0, 3), (3, 6)]
+    loc = torch.arange(eq[rank][0], eq[rank][1], dtype=torch.float64)[:, None] * torch.ones(1, 2, dtype=torch.float64)
+    out = torch.empty((6, 2), dtype=torch.float64)
+    full_eq = gather_group_results(loc, eq, out=out)
+    assert full_eq.data_ptr() == out.data_ptr() and full_eq[:, 0].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
     q.put((rank, full[:, 0].tolist()))
     dist.destroy_process_group()
 

@@ -253,3 +253,15 @@ def test_grouped_driver_matches_per_group():
         x = d["x"][sl]
         ref = np.linalg.solve(x.T @ x + 1e-3 * np.eye(4), x.T @ d["y"][sl])
         assert np.allclose(out[g], ref, rtol=1e-9)
+
+
+def test_predict_semantics():                                                 # tests/test_ols.py:903-966
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(50, 3)); c = rng.normal(size=(50, 4))
+    mx = rng.random(50) >= 0.2
+    p, m = S.predict([c[:, j] for j in range(4)], [(x[:, 0], mx), x[:, 1], x[:, 2]], "zero", add_intercept=True)
+    assert m is None and np.allclose(p, np.where(mx, x[:, 0], 0) * c[:, 0] + x[:, 1] * c[:, 1] + x[:, 2] * c[:, 2] + c[:, 3])
+    p, m = S.predict([c[:, j] for j in range(3)], [(x[:, 0], mx), x[:, 1], x[:, 2]], "drop")
+    assert (m == mx).all()
+    p, m = S.predict([c[:, j] for j in range(3)], [(x[:, 0], mx), x[:, 1], x[:, 2]], "ignore")
+    assert (np.isnan(p) == ~mx).all()
