@@ -72,7 +72,7 @@ enum {
 enum {
     B200OLS_OK = 0,
     B200OLS_ERR_INVALID = -1,     /* bad argument (the reference's assert!/expect panics) */
-    B200OLS_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented on the device yet */
+    B200OLS_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented on the device yet (k > 64; rls / rolling k > 8) */
     B200OLS_ERR_CUDA = -3,        /* CUDA runtime failure (message has the cudaError string) */
     B200OLS_ERR_NO_DEVICE = -4    /* no CUDA device: there is NO CPU fallback */
 };
@@ -218,7 +218,8 @@ B200OLS_API int b200ols_predict(b200ols_ctx *ctx, int64_t n_rows, int32_t n_coef
 /* Per-group diagnostics of the last static call on ctx (host copy): bit 0 = Cholesky failed and the
  * LU fallback ran (src/least_squares.rs:299-316), bit 1 = group had no rows after null filtering
  * (coefficients = 0, src/expressions.rs:357-359), bit 2 = re-solved by the pivoted-QR kernel
- * (ill-conditioned Gram).  flags must hold n_groups ints. */
+ * (ill-conditioned Gram), bit 4 = 0 < n <= k (the reference's LAPACK min-norm path), bit 5 = solved by the
+ * one-sided Jacobi SVD kernel (solve_method = "svd", or n <= k).  flags must hold n_groups ints. */
 B200OLS_API int b200ols_last_group_flags(b200ols_ctx *ctx, int32_t *flags, int64_t n_groups);
 
 #ifdef __cplusplus

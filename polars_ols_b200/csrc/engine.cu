@@ -28,6 +28,7 @@
 #include "prep.cuh"
 #include "qr_fallback.cuh"
 #include "small_solve.cuh"
+#include "svd_solve.cuh"
 #include "cd_solve.cuh"
 
 using namespace b200;
@@ -752,6 +753,10 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
 struct StaticRoute {
     int route = ROUTE_CHOL;   // ROUTE_*
     bool ols_qr_guard = false;  // OLS branch (QR in the reference): re-solve ill-conditioned groups by QR
+    bool svd_all = false;       // solve_method = "svd": every group by the Jacobi SVD kernel
+    bool svd_wide = false;      // solve_method = None on the OLS branch: groups with n <= k take the SVD path
+    bool svd_ridge = false;     // ridge-SVD formula (solve_ridge_svd)
+    double rcond = NAN;
     double alpha = 0.0, l1_ratio = 0.0, tol = 1e-5;
     int64_t max_iter = 1000;
     int positive = 0;
@@ -771,18 +776,22 @@ static int resolve_route(const b200ols_ols_kwargs *kw, StaticRoute *r) {
     r->max_iter = kw->max_iter < 0 ? 1000 : kw->max_iter;
     r->tol = std::isnan(kw->tol) ? 1e-5 : kw->tol;
     if (alpha == 0.0 && !positive && (m == B200OLS_SOLVE_NONE || m == B200OLS_SOLVE_SVD || m == B200OLS_SOLVE_QR)) {
-        if (m == B200OLS_SOLVE_SVD)
-            return fail(B200OLS_ERR_UNSUPPORTED, "solve_method='svd' (LAPACK dgelsd min-norm) is not implemented on the device yet");
         r->route = ROUTE_CHOL;
-        r->ols_qr_guard = true;
+        r->ols_qr_guard = m != B200OLS_SOLVE_SVD;
+        r->svd_all = m == B200OLS_SOLVE_SVD;          // solve_ols_svd (src/least_squares.rs:183-191)
+        r->svd_wide = m == B200OLS_SOLVE_NONE;        // n <= k -> SVD (src/least_squares.rs:225-229)
         return 0;
     }
     const double l1 = std::isnan(kw->l1_ratio) ? 0.0 : kw->l1_ratio;
     if (alpha >= 0.0 && l1 == 0.0 && !positive) {
         if (m == B200OLS_SOLVE_NONE || m == B200OLS_SOLVE_CHOL) r->route = ROUTE_CHOL;
         else if (m == B200OLS_SOLVE_LU) r->route = ROUTE_LU;
-        else if (m == B200OLS_SOLVE_SVD)
-            return fail(B200OLS_ERR_UNSUPPORTED, "ridge solve_method='svd' is not implemented on the device yet");
+        else if (m == B200OLS_SOLVE_SVD) {  // solve_ridge_svd (src/least_squares.rs:106-168)
+            r->route = ROUTE_CHOL;
+            r->svd_all = true;
+            r->svd_ridge = true;
+            r->rcond = kw->rcond;
+        }
         else return fail(B200OLS_ERR_INVALID, "Only 'Cholesky', 'LU', & 'SVD' are currently supported solver methods for Ridge.");
         return 0;
     }
@@ -831,7 +840,8 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     bytes += nseg_bound * P * 8 + static_cast<size_t>(G) * (static_cast<size_t>(F) * F + 4 * F) * 8;  // partials + work
     bytes += static_cast<size_t>(G) * F * 8 + static_cast<size_t>(G) * 4 + 4096;                     // beta + flags
     if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * 9 + 4096;                         // out + validity
-    if (rt.ols_qr_guard) bytes += static_cast<size_t>(F + 1) * static_cast<size_t>(N) * 8 + 4096;  // QR workspace
+    if (rt.ols_qr_guard || rt.svd_all || rt.svd_wide)
+        bytes += static_cast<size_t>(F + 1) * static_cast<size_t>(N) * 8 + static_cast<size_t>(G) * F * F * 8 + 8192;  // QR / SVD workspace
     bytes += 1 << 20;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
@@ -848,13 +858,6 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     c->last_flags_n = G;
 
     // wide / under-determined groups take the LAPACK SVD path in the reference (src/least_squares.rs:225-229)
-    if (rt.ols_qr_guard && !st.prepped && st.wide_group >= 0) {
-        const int64_t g = st.wide_group;
-        return fail(B200OLS_ERR_UNSUPPORTED,
-                    "group %lld has n=%lld <= k=%d rows: the min-norm SVD path is not implemented on the device yet",
-                    (long long)g, (long long)(st.offsets[g + 1] - st.offsets[g]), F);
-    }
-
     GramParams gp;
     std::memset(&gp, 0, sizeof(gp));
     for (int j = 0; j < st.kd; ++j) gp.cols[j] = st.feat[j];
@@ -912,6 +915,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         c->launches++;
     }
 
+    double *svd_ws = nullptr;  // the QR and SVD kernels share one absolute-row workspace
     if (rt.ols_qr_guard) {
         // groups whose Gram is too ill-conditioned for 1e-6 parity with the reference's QR are re-solved
         // from the data by Householder QR with column pivoting (faer col_piv_qr, src/least_squares.rs:195-205)
@@ -942,8 +946,50 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         qp.flags = flags;
         qp.n_rows = st.n;
         qp.ws = arena_alloc<double>(c, static_cast<size_t>(F + 1) * static_cast<size_t>(st.n) + 8);
+        svd_ws = qp.ws;
         ARENA_GUARD(c);
         CU(launch_qr_fallback_kernel(c->stream, qp, f->dtype == B200OLS_F64));
+        c->launches++;
+    }
+
+    if (rt.svd_all || rt.svd_wide) {
+        // minimum-norm / ridge SVD path (solve_ols_svd, solve_ridge_svd): one-sided Jacobi on the data
+        SvdParams sv;
+        std::memset(&sv, 0, sizeof(sv));
+        QrParams &qp = sv.q;
+        for (int j = 0; j < st.kd; ++j) qp.cols[j] = st.feat[j];
+        qp.cols[st.kd] = st.y;
+        qp.w = st.w;
+        qp.mask = st.mask;
+        qp.kd = st.kd;
+        qp.intercept = st.intercept;
+        qp.F = F;
+        qp.w_is_sqrt = st.w_is_sqrt;
+        qp.n_groups = G;
+        qp.n_rows = st.n;
+        qp.beta = beta;
+        qp.flags = flags;
+        if (!pl.split) {
+            qp.group_off = pl.seg_off;
+        } else {
+            const size_t ob = sizeof(int64_t) * (G + 1);
+            TRY(pinned_reserve(c, c->pinned_off + ob + 256));
+            char *h = c->pinned + c->pinned_off;
+            c->pinned_off += round_up(ob, 256);
+            std::memcpy(h, st.offsets.data(), ob);
+            int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(G) + 1);
+            CU(cudaMemcpyAsync(d, h, ob, cudaMemcpyHostToDevice, c->stream));
+            qp.group_off = d;
+        }
+        qp.ws = svd_ws ? svd_ws : arena_alloc<double>(c, static_cast<size_t>(F + 1) * static_cast<size_t>(st.n) + 8);
+        sv.vws = arena_alloc<double>(c, static_cast<size_t>(G) * F * F + 8);
+        sv.all_groups = rt.svd_all ? 1 : 0;
+        sv.ridge = rt.svd_ridge ? 1 : 0;
+        sv.alpha = rt.alpha;
+        sv.rcond = rt.rcond;
+        sv.max_sweeps = 40;
+        ARENA_GUARD(c);
+        CU(launch_svd_solve(c->stream, sv, f->dtype == B200OLS_F64));
         c->launches++;
     }
 

@@ -184,6 +184,7 @@ __device__ __forceinline__ void gram_finish(const GramParams &p, int nfit, int64
             ci = (lane < FP) ? cs[lane] : 0.0;
         }
     }
+    if (nfit > 0 && nfit <= F) fl |= FLAG_WIDE;
     if (lane == 0) p.flags[g] = fl;
     if (lane < F) p.beta[g * F + lane] = ci;
     __syncwarp();

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) qr_fallback_kernel(const QrParams p) {
     const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (g >= p.n_groups) return;
     const int fl = p.flags[g];
-    if (!(fl & (FLAG_ILLCOND | FLAG_LU_FALLBACK)) || (fl & FLAG_EMPTY)) return;
+    if (!(fl & (FLAG_ILLCOND | FLAG_LU_FALLBACK)) || (fl & (FLAG_EMPTY | FLAG_WIDE))) return;  // wide groups -> SVD kernel
     const int F = p.F, kd = p.kd;
     const int64_t r0 = p.group_off[g], r1 = p.group_off[g + 1], n = r1 - r0;
     const int64_t N = p.n_rows;

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(128) small_solve_kernel(const SolveParams p) {
     if (p.route == ROUTE_CHOL || p.route == ROUTE_LU) {
         for (int i = 0; i < F; ++i) G[i * F + i] += p.alpha;
         fl = normal_equations_solve(G, F, F, c, p.route == ROUTE_LU, scratch, p.illcond_ratio);
+        if (nfit <= static_cast<double>(F)) fl |= FLAG_WIDE;
         for (int i = 0; i < F; ++i) beta[i] = c[i];
     } else {
         // alpha is scaled by the number of fitted samples (src/least_squares.rs:419)

@@ -24,7 +24,9 @@ enum : int {
     FLAG_LU_FALLBACK = 1,  // Cholesky hit a non-positive pivot, LU with partial pivoting ran
     FLAG_EMPTY = 2,        // no rows after null filtering: coefficients = 0
     FLAG_QR = 4,           // ill-conditioned: re-solved by the pivoted-QR kernel
-    FLAG_ILLCOND = 8       // internal: Cholesky pivot ratio says cond(G) is too large for 1e-6 parity
+    FLAG_ILLCOND = 8,      // internal: Cholesky pivot ratio says cond(G) is too large for 1e-6 parity
+    FLAG_WIDE = 16,        // 0 < n <= k: the reference takes the LAPACK min-norm SVD path (src/least_squares.rs:225-229)
+    FLAG_SVD = 32          // solved by the one-sided Jacobi SVD kernel
 };
 
 // In-place LL^T on the lower triangle of the symmetric matrix A (row-major, leading dim ld).

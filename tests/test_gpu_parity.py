@@ -92,11 +92,48 @@ def test_ols(solve_method):                                                # tes
     _close(e.to_numpy(), _ref(S.least_squares(d["y"], *_oracle_cols(d, _xs(d)), mode="residuals")))
 
 
-def test_svd_is_a_loud_unsupported_error():
-    d = _make_data(100, 2)
-    with pytest.raises(pls.B200OLSError) as ei:
-        Frame(d).select(col("y").least_squares.ols("x1", "x2", solve_method="svd"))
-    assert ei.value.code == -2
+def test_ols_svd_matches_lapack():                                          # tests/test_ols.py:54-73 [svd]
+    d = _make_data(1000, 3, n_groups=4)
+    r = Frame(d).select(col("y").least_squares.ols(*_xs(d), mode="coefficients", solve_method="svd").over("group"))["coefficients"]
+    keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), per_group=True, mode="coefficients",
+                        kwargs=S.OLSKwargs(solve_method="svd"))
+    _close(r.to_numpy(), c)
+    assert (pls.get_engine(0).last_group_flags(4) & 32).all()
+
+
+@pytest.mark.parametrize("k", [2, 10, 40, 64])
+def test_fit_wide_takes_the_min_norm_path(k):                              # tests/test_ols.py:272-312 (n = 10 rows)
+    d = _make_data(10, k, seed=k)
+    r = Frame(d).select(col("y").least_squares.ols(*_xs(d), mode="coefficients"))["coefficients"]
+    ref = S.least_squares(d["y"], *_oracle_cols(d, _xs(d)), mode="coefficients")          # lstsq (dgelsd) when n <= k
+    _close(r.to_numpy()[0], _ref(ref), rtol=1e-6, atol=1e-9)
+    p = Frame(d).select(col("y").least_squares.ols(*_xs(d)))["y"].to_numpy()
+    if k >= 10:
+        assert np.corrcoef(p, d["y"])[0, 1] > 1 - 1e-5                      # interpolates exactly
+
+
+def test_fit_multi_collinear_svd_and_qr():                                 # tests/test_ols.py:315-360
+    rng = np.random.default_rng(0)
+    n = 1000
+    x1, x2 = rng.normal(size=n), rng.normal(size=n)
+    x3 = x1 + x2                                                            # exactly collinear
+    y = x1 + x2 + x3 + 0.01 * rng.normal(size=n)
+    d = {"y": y, "x1": x1, "x2": x2, "x3": x3}
+    r = Frame(d).select(col("y").least_squares.ols("x1", "x2", "x3", mode="coefficients", solve_method="svd"))["coefficients"]
+    ref = np.linalg.lstsq(np.c_[x1, x2, x3], y, rcond=None)[0]              # min-norm
+    assert np.allclose(r.to_numpy()[0], ref, rtol=1e-6, atol=1e-8)
+    p = Frame(d).select(col("y").least_squares.ols("x1", "x2", "x3", solve_method="svd"))["y"].to_numpy()
+    assert np.allclose(p, np.c_[x1, x2, x3] @ ref, rtol=1e-6, atol=1e-8)
+    q = Frame(d).select(col("y").least_squares.ols("x1", "x2", "x3", solve_method="qr"))["y"].to_numpy()
+    assert np.isfinite(q).all()                                             # reference: qr predictions stay finite
+
+
+def test_ridge_svd():                                                      # tests/test_ols.py:475-503 [svd]
+    d = _make_data(5000, 3, n_groups=3)
+    r = Frame(d).select(col("y").least_squares.ridge(*_xs(d), alpha=0.01, solve_method="svd", mode="coefficients").over("group"))["coefficients"]
+    keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), per_group=True, mode="coefficients",
+                        kwargs=S.OLSKwargs(alpha=0.01, l1_ratio=0.0, solve_method="svd"))
+    _close(r.to_numpy(), c)
 
 
 @pytest.mark.parametrize("k,n_groups,n", [(8, 300, 60000), (3, 7, 5000), (16, 50, 20000)])
@@ -170,7 +207,7 @@ def test_missing_data(null_policy, mode):                                  # tes
 def test_all_empty_data():                                                 # tests/test_ols.py:252-269
     F = Frame({"A": (np.array([0.0, 2, 0, 4]), np.array([False, True, False, True])),
                "B": (np.array([1.0, 0, 3, 0]), np.array([True, False, True, False]))})
-    r = F.select(col("A").least_squares.ols(col("B"), mode="residuals", null_policy="drop", solve_method="chol"))["A"]
+    r = F.select(col("A").least_squares.ols(col("B"), mode="residuals", null_policy="drop", solve_method="svd"))["A"]
     assert r.is_null().all()
 
 
