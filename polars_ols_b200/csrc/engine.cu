@@ -224,9 +224,11 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
     c->device = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 9)
+    if (prop.major < 9) {
+        delete c;
         return fail(B200OLS_ERR_NO_DEVICE, "device sm_%d%d: this library is built for sm_100a only", prop.major,
                     prop.minor);
+    }
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
     if (cuda_stream) {
