@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused P2P stores from the solver warps (default) or an NCCL all-gather per step")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
 
@@ -181,7 +183,7 @@ def main():
     import torch
     import polars_ols_b200 as pls
     from polars_ols_b200 import _lib as L
-    from polars_ols_b200.parallel import gather_group_results
+    from polars_ols_b200.parallel import PeerGather, gather_group_results
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -204,16 +206,22 @@ def main():
     if a.tile_rows or a.warps or a.ctas_per_sm:
         eng.set_tuning(a.tile_rows, a.warps, a.ctas_per_sm)
     batch = pls.Batch(pls.Col(yd), [pls.Col(xd[i]) for i in range(K)], offsets=offsets)
-    steps_fn = [eng.prepare_least_squares(batch, kw, L.COEFFICIENTS, c_) for c_ in coefs]
+    peer = None
+    if world > 1 and a.gather == "peer":
+        # fused gather: beta goes from the solver warps into every rank's [world*G, K] buffer over NVLink
+        peer = PeerGather(eng, world * G, K, rank * G)
+        peer.attach()
+    # in peer mode the only outputs are the gathered buffers (no local [G, K] copy)
+    steps_fn = [eng.prepare_least_squares(batch, kw, L.COEFFICIENTS, None if peer is not None else c_) for c_ in coefs]
     shards = [(r * G, (r + 1) * G) for r in range(world)]
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if (world > 1 and peer is None) else None
     ev_done = [torch.cuda.Event() for _ in range(2)]     # kernel i finished writing coefs[i & 1]
     ev_gath = [torch.cuda.Event() for _ in range(2)]     # gather of coefs[i & 1] finished reading it
     gathered = [torch.empty((world * G, K), dtype=torch.float64, device=dev) if world > 1 else None]
 
     def full_step(i):
         b = i & 1
-        if world == 1:
+        if world == 1 or peer is not None:
             steps_fn[b]()
             return
         cur = torch.cuda.current_stream(dev)
@@ -252,7 +260,13 @@ def main():
     ms = e0.elapsed_time(e1)
     kern_ms = eng.profile_drain()
     eng.set_profiling(False)
-    launches = eng.launch_count - launches0 + (a.steps if world > 1 else 0)
+    launches = eng.launch_count - launches0 + (a.steps if (world > 1 and peer is None) else 0)
+    if peer is not None:
+        # every rank's shard must have landed in this rank's buffer (all ranks synchronised at the barrier above)
+        full = peer.read()
+        assert np.isfinite(full).all() and (np.abs(full).sum(axis=1) > 0).all(), "peer gather incomplete"
+        coef = torch.as_tensor(full[rank * G:(rank + 1) * G], device=dev)
+        peer.close()
     t_local = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
@@ -323,7 +337,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "inputs 720 MB per step > 126 MB L2 (no flush needed)",
                        "parallelism": f"groups sharded over {world} GPU(s), weak scaling"
-                                      + (", NCCL all-gather of coefficient chunks per step (side stream, overlapped with the next step's kernel)" if world > 1 else ""),
+                                      + ((", coefficient chunks gathered by P2P stores from the solver warps into every rank's buffer (NVLink peer memory, fused into the kernel)" if a.gather == "peer" else ", NCCL all-gather of coefficient chunks per step (side stream, overlapped with the next step's kernel)") if world > 1 else ""),
                        "inputs": "resident in HBM (value) / pinned host memory (e2e)"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + hy.nbytes + offsets.nbytes),

@@ -205,6 +205,29 @@ B200OLS_API int b200ols_rolling_least_squares(b200ols_ctx *ctx, const b200ols_fr
 B200OLS_API int b200ols_rolling_least_squares_coefficients(b200ols_ctx *ctx, const b200ols_frame *frame,
                                                const b200ols_rolling_kwargs *kwargs, b200ols_output *out);
 
+/* ---- multi-GPU: fused coefficient gather over NVLink peer memory ------------------------------------
+ * Groups are independent, so ranks shard by group and the only exchange is the final gather of the
+ * per-rank coefficient chunks.  Instead of a collective after the kernel, every rank's
+ * solver warps store beta straight into EVERY rank's full [total_groups, n_coef] buffer (P2P stores over
+ * NVLink / NVSwitch, peer pointers obtained through CUDA IPC): the gather costs no extra launch.
+ *   b200ols_device_alloc / _free : cudaMalloc'd (IPC-exportable) device memory
+ *   b200ols_ipc_export / _open / _close : cudaIpc{Get,Open,Close}MemHandle (64-byte handles travel between the
+ *                                  ranks by any host channel, e.g. torch.distributed.all_gather_object)
+ *   b200ols_set_peer_gather      : peer_coef[r] = rank r's full buffer (r = 0..n_peers-1, own rank included);
+ *                                  subsequent b200ols_least_squares_coefficients calls on DEVICE frames write
+ *                                  rows [group_base, group_base + n_groups) of every peer buffer
+ *                                  (out->values may then be NULL).  n_peers = 0 switches it off.
+ * Ordering is the caller's: a rank may read its buffer once all ranks have synchronised their streams
+ * (e.g. stream sync + barrier), exactly as after a collective. */
+B200OLS_API void *b200ols_device_alloc(b200ols_ctx *ctx, size_t bytes);
+B200OLS_API void b200ols_device_free(b200ols_ctx *ctx, void *p);
+B200OLS_API int b200ols_ipc_export(b200ols_ctx *ctx, const void *dev_ptr, uint8_t handle[64]);
+B200OLS_API int b200ols_ipc_open(b200ols_ctx *ctx, const uint8_t handle[64], void **dev_ptr);
+B200OLS_API int b200ols_ipc_close(b200ols_ctx *ctx, void *dev_ptr);
+B200OLS_API int b200ols_copy_to_host(b200ols_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+B200OLS_API int b200ols_set_peer_gather(b200ols_ctx *ctx, int n_peers, void *const *peer_coef, int64_t group_base,
+                                        int64_t total_groups);
+
 /* "next" row: replaces _polars_plugin_predict (src/expressions.rs:706-741).
  * coefficients: n_coef Float64 child arrays of the coefficient struct Series (one value per ROW, e.g. the
  * broadcast result of `.over()` or the per-row output of rls / rolling); features: n_coef - add_intercept

@@ -28,7 +28,8 @@ EXPORTS = [
     "b200ols_host_free", "b200ols_set_tuning", "b200ols_set_variant", "b200ols_set_profiling", "b200ols_profile_drain", "b200ols_least_squares",
     "b200ols_least_squares_coefficients", "b200ols_recursive_least_squares",
     "b200ols_recursive_least_squares_coefficients", "b200ols_rolling_least_squares",
-    "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags", "b200ols_predict",
+    "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags", "b200ols_predict", "b200ols_device_alloc", "b200ols_device_free", "b200ols_ipc_export",
+    "b200ols_ipc_open", "b200ols_ipc_close", "b200ols_copy_to_host", "b200ols_set_peer_gather",
 ]
 
 
@@ -115,6 +116,15 @@ def load() -> C.CDLL:
     L.b200ols_rolling_least_squares.argtypes = [vp, C.POINTER(Frame), C.POINTER(RollingKwargs), i32, C.POINTER(Output)]
     L.b200ols_rolling_least_squares_coefficients.argtypes = [vp, C.POINTER(Frame), C.POINTER(RollingKwargs), C.POINTER(Output)]
     L.b200ols_last_group_flags.argtypes = [vp, vp, i64]
+    L.b200ols_device_alloc.argtypes = [vp, C.c_size_t]
+    L.b200ols_device_alloc.restype = vp
+    L.b200ols_device_free.argtypes = [vp, vp]
+    L.b200ols_device_free.restype = None
+    L.b200ols_ipc_export.argtypes = [vp, vp, vp]
+    L.b200ols_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.b200ols_ipc_close.argtypes = [vp, vp]
+    L.b200ols_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
+    L.b200ols_set_peer_gather.argtypes = [vp, i32, C.POINTER(vp), i64, i64]
     L.b200ols_predict.argtypes = [vp, i64, i32, i32, i32, C.POINTER(Column), C.POINTER(Column), i32, i32, C.POINTER(Output)]
     _lib = L
     return L

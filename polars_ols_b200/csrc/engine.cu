@@ -102,6 +102,10 @@ struct b200ols_ctx {
     int plan_F = -1;
     int64_t *plan_dev = nullptr;
     size_t plan_cap = 0;
+    // fused multi-GPU gather (b200ols_set_peer_gather)
+    int n_peers = 0;
+    double *peer_coef[8] = {};
+    int64_t peer_group_base = 0, peer_total_groups = 0;
     // optional device-side timing of the dominant kernel
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
@@ -278,6 +282,80 @@ extern "C" void b200ols_host_free(void *p) {
 }
 
 extern "C" int64_t b200ols_launch_count(const b200ols_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" void *b200ols_device_alloc(b200ols_ctx *c, size_t bytes) {
+    if (!c) return nullptr;
+    void *p = nullptr;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(B200OLS_ERR_CUDA, "cudaMalloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void b200ols_device_free(b200ols_ctx *c, void *p) {
+    if (c && p) {
+        cudaSetDevice(c->device);
+        cudaFree(p);
+    }
+}
+extern "C" int b200ols_ipc_export(b200ols_ctx *c, const void *dev_ptr, uint8_t handle[64]) {
+    if (!c || !dev_ptr || !handle) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    std::memcpy(handle, &h, 64);
+    return 0;
+}
+extern "C" int b200ols_ipc_open(b200ols_ctx *c, const uint8_t handle[64], void **dev_ptr) {
+    if (!c || !dev_ptr || !handle) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int b200ols_ipc_close(b200ols_ctx *c, void *dev_ptr) {
+    if (!c || !dev_ptr) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+extern "C" int b200ols_copy_to_host(b200ols_ctx *c, void *dst_host, const void *src_dev, size_t bytes) {
+    if (!c || !dst_host || !src_dev) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int b200ols_set_peer_gather(b200ols_ctx *c, int n_peers, void *const *peer_coef, int64_t group_base,
+                                       int64_t total_groups) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (n_peers < 0 || n_peers > 8) return fail(B200OLS_ERR_INVALID, "n_peers must be in [0, 8]");
+    if (n_peers > 0 && (!peer_coef || group_base < 0 || total_groups <= 0)) return fail(B200OLS_ERR_INVALID, "bad peer table");
+    c->n_peers = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_coef[r]) return fail(B200OLS_ERR_INVALID, "peer_coef[%d] is NULL", r);
+        c->peer_coef[r] = static_cast<double *>(peer_coef[r]);
+    }
+    c->peer_group_base = group_base;
+    c->peer_total_groups = total_groups;
+    return 0;
+}
+
+// generic fallback of the fused gather: after kernels that rewrite beta (QR / SVD / CD / split groups)
+struct PeerScatterParams {
+    const double *beta;
+    double *peer[8];
+    int n_peers;
+    int64_t n, base_elems;
+};
+static __global__ void peer_scatter_kernel(const PeerScatterParams p) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const double v = p.beta[i];
+    for (int r = 0; r < p.n_peers; ++r) p.peer[r][p.base_elems + i] = v;
+}
 
 extern "C" int b200ols_set_profiling(b200ols_ctx *c, int enabled) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
@@ -823,8 +901,12 @@ static constexpr double ILLCOND_RATIO = 1.0e7;  // squared-pivot ratio above whi
 
 static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
-    if (!kw || !out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    const bool peer_mode = c->n_peers > 0 && mode == B200OLS_COEFFICIENTS && f && f->memspace == B200OLS_DEVICE;
+    if (!kw || !out || (!out->values && !peer_mode)) return fail(B200OLS_ERR_INVALID, "NULL argument");
     TRY(validate_frame(f));
+    if (peer_mode && c->peer_group_base + f->n_groups > c->peer_total_groups)
+        return fail(B200OLS_ERR_INVALID, "peer gather: shard [%lld, %lld) exceeds total_groups %lld", (long long)c->peer_group_base,
+                    (long long)(c->peer_group_base + f->n_groups), (long long)c->peer_total_groups);
     if (mode != B200OLS_PREDICTIONS && mode != B200OLS_RESIDUALS && mode != B200OLS_COEFFICIENTS)
         return fail(B200OLS_ERR_INVALID, "bad mode %d", mode);
     StaticRoute rt;
@@ -886,6 +968,13 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     const bool cd = rt.route == ROUTE_CD || rt.route == ROUTE_CD_ACTIVE;
     gp.fused = (!pl.split && !cd && F <= 16) ? 1 : 0;
     if (!gp.fused) gp.partial = arena_alloc<double>(c, static_cast<size_t>(pl.nseg) * P);
+    // fused gather: only when the streaming kernel's beta is final (no QR / SVD re-solve afterwards)
+    const bool peer_direct = peer_mode && gp.fused && !rt.ols_qr_guard && !rt.svd_all && !rt.svd_wide;
+    if (peer_direct) {
+        gp.n_peers = c->n_peers;
+        for (int r = 0; r < c->n_peers; ++r) gp.peer_beta[r] = c->peer_coef[r];
+        gp.peer_group_base = c->peer_group_base;
+    }
 
     ARENA_GUARD(c);
     if (f->dtype == B200OLS_F64) TRY(launch_gram<double>(c, gp)); else TRY(launch_gram<float>(c, gp));
@@ -996,6 +1085,19 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     }
 
     // outputs
+    if (peer_mode && !peer_direct) {
+        PeerScatterParams ps;
+        std::memset(&ps, 0, sizeof(ps));
+        ps.beta = beta;
+        ps.n_peers = c->n_peers;
+        for (int r = 0; r < c->n_peers; ++r) ps.peer[r] = c->peer_coef[r];
+        ps.n = static_cast<int64_t>(G) * F;
+        ps.base_elems = c->peer_group_base * F;
+        peer_scatter_kernel<<<static_cast<unsigned>((ps.n + 255) / 256), 256, 0, c->stream>>>(ps);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (peer_mode && !out->values) return 0;
     if (mode == B200OLS_COEFFICIENTS) {
         const size_t ob = static_cast<size_t>(G) * F * sizeof(double);
         if (f->memspace == B200OLS_HOST) {

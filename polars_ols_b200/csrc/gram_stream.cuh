@@ -54,6 +54,10 @@ struct GramParams {
     double alpha;                     // ridge penalty added to the diagonal (NOT scaled by n)
     int use_lu;                       // "lu": skip Cholesky
     double illcond_ratio;             // flag groups whose squared-pivot ratio exceeds this
+    // fused multi-GPU gather: beta is also stored into every rank's full buffer (P2P over NVLink)
+    int n_peers;
+    double *peer_beta[8];             // [total_groups][F] on rank r
+    int64_t peer_group_base;          // first global group index of this rank's shard
 };
 
 template <typename T> struct V2;
@@ -186,7 +190,10 @@ __device__ __forceinline__ void gram_finish(const GramParams &p, int nfit, int64
     }
     if (nfit > 0 && nfit <= F) fl |= FLAG_WIDE;
     if (lane == 0) p.flags[g] = fl;
-    if (lane < F) p.beta[g * F + lane] = ci;
+    if (lane < F) {
+        p.beta[g * F + lane] = ci;
+        for (int r = 0; r < p.n_peers; ++r) p.peer_beta[r][(p.peer_group_base + g) * F + lane] = ci;  // fused gather
+    }
     __syncwarp();
 }
 

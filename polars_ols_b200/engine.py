@@ -305,6 +305,37 @@ class Engine:
         return v, m
 
 
+    # -- fused multi-GPU gather (peer memory over NVLink) -------------------------------------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = self._lib.b200ols_device_alloc(self._ctx, nbytes)
+        if not p:
+            raise L.B200OLSError(L.ERR_CUDA, self._lib.b200ols_last_error().decode())
+        return p
+
+    def device_free(self, ptr: int):
+        self._lib.b200ols_device_free(self._ctx, C.c_void_p(ptr))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        h = (C.c_uint8 * 64)()
+        L.check(self._lib.b200ols_ipc_export(self._ctx, C.c_void_p(ptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        L.check(self._lib.b200ols_ipc_open(self._ctx, h, C.byref(out)))
+        return out.value
+
+    def ipc_close(self, ptr: int):
+        L.check(self._lib.b200ols_ipc_close(self._ctx, C.c_void_p(ptr)))
+
+    def copy_to_host(self, dst: np.ndarray, src_ptr: int):
+        L.check(self._lib.b200ols_copy_to_host(self._ctx, dst.ctypes.data, C.c_void_p(src_ptr), dst.nbytes))
+
+    def set_peer_gather(self, peer_ptrs: Sequence[int], group_base: int, total_groups: int):
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
+        L.check(self._lib.b200ols_set_peer_gather(self._ctx, len(peer_ptrs), arr, group_base, total_groups))
+
     def predict(self, coefficients: List[Col], features: List[Col], add_intercept: bool, null_policy: int):
         """b200ols_predict: row-wise dot of features with per-row coefficient columns."""
         n = len(coefficients[0])

@@ -49,3 +49,49 @@ def gather_group_results(local, shards: List[Tuple[int, int]], group=None, out=N
     dist.all_gather_into_tensor(out, pad, group=group)
     out = out.view(world, gmax, k)
     return torch.cat([out[r, : shards[r][1] - shards[r][0]] for r in range(world)], dim=0)
+
+
+class PeerGather:
+    """Fused gather of per-rank coefficient chunks through NVLink peer memory (no collective per step).
+
+    Every rank owns a full [total_groups, n_coef] f64 buffer (cudaMalloc, exported with CUDA IPC); after
+    `attach()` the engine's `least_squares_coefficients` on a DEVICE frame stores rows
+    [group_base, group_base + n_groups) into EVERY rank's buffer straight from the solver warps
+    (`b200ols_set_peer_gather`).  A rank may read its buffer after all ranks synchronised (stream sync +
+    barrier), exactly as after a collective."""
+
+    def __init__(self, engine, total_groups: int, n_coef: int, group_base: int, group=None):
+        import torch.distributed as dist
+        self.engine, self.total_groups, self.n_coef, self.group_base = engine, total_groups, n_coef, group_base
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("peer gather supports up to 8 ranks (one NVSwitch domain)")
+        self.nbytes = total_groups * n_coef * 8
+        self.local = engine.device_alloc(self.nbytes)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, engine.ipc_export(self.local), group=group)
+        self.peers = [self.local if r == self.rank else engine.ipc_open(handles[r]) for r in range(self.world)]
+        dist.barrier(group)
+        self.group = group
+
+    def attach(self):
+        self.engine.set_peer_gather(self.peers, self.group_base, self.total_groups)
+
+    def detach(self):
+        self.engine.set_peer_gather([], 0, 0)
+
+    def read(self) -> np.ndarray:
+        out = np.empty((self.total_groups, self.n_coef))
+        self.engine.copy_to_host(out, self.local)
+        return out
+
+    def close(self):
+        import torch.distributed as dist
+        self.detach()
+        self.engine.synchronize()
+        dist.barrier(self.group)
+        for r, p in enumerate(self.peers):
+            if r != self.rank:
+                self.engine.ipc_close(p)
+        dist.barrier(self.group)
+        self.engine.device_free(self.local)
