@@ -209,8 +209,13 @@ def main():
     peer = None
     if world > 1 and a.gather == "peer":
         # fused gather: beta goes from the solver warps into every rank's [world*G, K] buffer over NVLink
-        peer = PeerGather(eng, world * G, K, rank * G)
-        peer.attach()
+        try:
+            peer = PeerGather(eng, world * G, K, rank * G)
+            peer.attach()
+        except Exception as exc:  # no P2P / IPC on this box: fall back to the NCCL all-gather (same results)
+            peer = None
+            a.gather = "nccl"
+            print(f"[bench] peer gather unavailable ({exc}); using NCCL", file=sys.stderr)
     # in peer mode the only outputs are the gathered buffers (no local [G, K] copy)
     steps_fn = [eng.prepare_least_squares(batch, kw, L.COEFFICIENTS, None if peer is not None else c_) for c_ in coefs]
     shards = [(r * G, (r + 1) * G) for r in range(world)]
