@@ -128,6 +128,10 @@ typedef struct b200ols_rls_kwargs {
                                          (src/expressions.rs:604-610 vs :636) */
     int32_t null_policy;
     int32_t _reserved;
+    const double *initial_information; /* host [n_groups][n_coef*n_coef + n_coef] or NULL: information state
+                                         (A = P^-1 row-major, then b = A theta) ENTERING each series instead of the
+                                         prior (I/p0, theta0/p0) — a series continued from an earlier time shard
+                                         (SURVEY.md §8e).  Not part of the reference's RLSKwargs. */
 } b200ols_rls_kwargs;
 
 typedef struct b200ols_rolling_kwargs {
@@ -198,6 +202,16 @@ B200OLS_API int b200ols_recursive_least_squares(b200ols_ctx *ctx, const b200ols_
 /* replaces _polars_plugin_recursive_least_squares_coefficients (src/expressions.rs:594-622) */
 B200OLS_API int b200ols_recursive_least_squares_coefficients(b200ols_ctx *ctx, const b200ols_frame *frame,
                                                  const b200ols_rls_kwargs *kwargs, b200ols_output *out);
+/* Time-axis sharding of ONE long series: the information-form state LEAVING each series of the
+ * frame, state[g] = { A (n_coef x n_coef, symmetric, row-major), b (n_coef), D }, where
+ *   (A, b)_leaving = D * (A, b)_entering + (A, b)_rows   and   D = lambda ^ (#valid rows)
+ * (src/least_squares.rs:505-540 in information form).  The entering state is
+ * kwargs->initial_information, else the prior.  Called with an all-zero initial_information it returns the pure
+ * affine map of the shard; maps of consecutive shards compose, which is the only exchange a time-sharded rls
+ * needs (one all-gather of n_coef^2 + n_coef + 1 doubles per rank).  `state` is a HOST pointer
+ * [n_groups][n_coef*n_coef + n_coef + 1]; the call synchronises. */
+B200OLS_API int b200ols_recursive_least_squares_state(b200ols_ctx *ctx, const b200ols_frame *frame,
+                                                      const b200ols_rls_kwargs *kwargs, double *state);
 /* replaces _polars_plugin_rolling_least_squares (src/expressions.rs:679-701) */
 B200OLS_API int b200ols_rolling_least_squares(b200ols_ctx *ctx, const b200ols_frame *frame,
                                   const b200ols_rolling_kwargs *kwargs, int mode, b200ols_output *out);

@@ -30,6 +30,7 @@ EXPORTS = [
     "b200ols_recursive_least_squares_coefficients", "b200ols_rolling_least_squares",
     "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags", "b200ols_predict", "b200ols_device_alloc", "b200ols_device_free", "b200ols_ipc_export",
     "b200ols_ipc_open", "b200ols_ipc_close", "b200ols_copy_to_host", "b200ols_set_peer_gather",
+    "b200ols_recursive_least_squares_state",
 ]
 
 
@@ -57,7 +58,7 @@ class OLSKwargs(C.Structure):
 class RLSKwargs(C.Structure):
     _fields_ = [
         ("half_life", C.c_double), ("initial_state_covariance", C.c_double), ("initial_state_mean", C.c_void_p),
-        ("null_policy", C.c_int32), ("_reserved", C.c_int32),
+        ("null_policy", C.c_int32), ("_reserved", C.c_int32), ("initial_information", C.c_void_p),
     ]
 
 
@@ -113,6 +114,7 @@ def load() -> C.CDLL:
     L.b200ols_least_squares_coefficients.argtypes = [vp, C.POINTER(Frame), C.POINTER(OLSKwargs), C.POINTER(Output)]
     L.b200ols_recursive_least_squares.argtypes = [vp, C.POINTER(Frame), C.POINTER(RLSKwargs), i32, C.POINTER(Output)]
     L.b200ols_recursive_least_squares_coefficients.argtypes = [vp, C.POINTER(Frame), C.POINTER(RLSKwargs), C.POINTER(Output)]
+    L.b200ols_recursive_least_squares_state.argtypes = [vp, C.POINTER(Frame), C.POINTER(RLSKwargs), vp]
     L.b200ols_rolling_least_squares.argtypes = [vp, C.POINTER(Frame), C.POINTER(RollingKwargs), i32, C.POINTER(Output)]
     L.b200ols_rolling_least_squares_coefficients.argtypes = [vp, C.POINTER(Frame), C.POINTER(RollingKwargs), C.POINTER(Output)]
     L.b200ols_last_group_flags.argtypes = [vp, vp, i64]

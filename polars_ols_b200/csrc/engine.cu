@@ -746,7 +746,9 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     }
     if (c->variant == 3 && KB <= 2) {  // CTA-cooperative warp-specialised TMA pipeline (k <= 16)
         const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
-        const size_t fixed = cta_fixed_smem<T>(KB, F);
+        // the accumulator ring of a 16-coefficient Gram is 18 KB per entry: keep it shallow, the stages need the room
+        gp.red_depth = KB == 1 ? CTA_RED_DEPTH : 3;
+        const size_t fixed = cta_fixed_smem<T>(KB, F, gp.red_depth);
         // default tile = the longest segment (whole groups per stage: fewest, largest bulk copies), shrunk until
         // at least two stages fit
         int R = c->tile_rows > 0 ? c->tile_rows
@@ -762,6 +764,14 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));  // sweep hook: warps_per_cta caps the stages
         gp.tile_rows = R;
         gp.stages = S;
+        // short groups: fewer consumer warps per segment (teams), >= ~16 row octets per warp; needs one tile per segment
+        gp.team = 0;
+        if (gp.max_seg_rows <= R) {
+            int team = CTA_CONSUMERS;
+            while (team > 1 && gp.max_seg_rows <= 128 * (team / 2)) team >>= 1;
+            if (c->ctas_per_sm > 0) team = std::min(CTA_CONSUMERS, std::max(1, c->ctas_per_sm));  // sweep hook (power of two)
+            gp.team = team;
+        }
         const size_t smem = static_cast<size_t>(S) * NC * gram_col_stride<T>(R) + fixed;
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, gp.nseg));
         ProfScope prof(c);
@@ -1379,9 +1389,9 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
 }
 
 static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, const b200ols_rls_kwargs *rk,
-                           const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out) {
+                           const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out, double *state_host = nullptr) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
-    if (!out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    if (!state_host && (!out || !out->values)) return fail(B200OLS_ERR_INVALID, "NULL argument");
     TRY(validate_frame(f));
     const int policy = kind == MOVING_RLS ? rk->null_policy : wk->null_policy;
     if (policy < B200OLS_NULL_IGNORE || policy > B200OLS_NULL_DROP_WINDOW) return fail(B200OLS_ERR_INVALID, "Invalid null_policy detected!");
@@ -1449,10 +1459,25 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
     mp.target_is_packed = st.y_raw_packed;
     mp.target_validity = st.y_validity;
     mp.mask_predictions = (st.mask != nullptr) ? 1 : 0;  // src/expressions.rs:640-645,695-700
-    const size_t out_elems = mode == B200OLS_COEFFICIENTS ? static_cast<size_t>(N) * F : static_cast<size_t>(N);
-    double *dout = out->values;
-    uint8_t *dval = out->validity;
-    if (f->memspace == B200OLS_HOST) {
+    const size_t NE = static_cast<size_t>(F) * F + F;
+    if (kind == MOVING_RLS && rk->initial_information) {  // series continued from an earlier time shard
+        const size_t ib = sizeof(double) * NE * static_cast<size_t>(G);
+        TRY(pinned_reserve(c, c->pinned_off + ib + 256));
+        char *h = c->pinned + c->pinned_off;
+        c->pinned_off += round_up(ib, 256);
+        std::memcpy(h, rk->initial_information, ib);
+        double *d = arena_alloc<double>(c, NE * static_cast<size_t>(G));
+        CU(cudaMemcpyAsync(d, h, ib, cudaMemcpyHostToDevice, c->stream));
+        mp.init_info = d;
+    }
+    if (state_host) {
+        mp.state_out = arena_alloc<double>(c, (NE + 1) * static_cast<size_t>(G));
+        mp.state_only = 1;
+    }
+    const size_t out_elems = state_host ? 0 : (mode == B200OLS_COEFFICIENTS ? static_cast<size_t>(N) * F : static_cast<size_t>(N));
+    double *dout = state_host ? nullptr : out->values;
+    uint8_t *dval = state_host ? nullptr : out->validity;
+    if (!state_host && f->memspace == B200OLS_HOST) {
         dout = arena_alloc<double>(c, out_elems);
         dval = out->validity ? arena_alloc<uint8_t>(c, out_elems) : nullptr;
     }
@@ -1464,6 +1489,29 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
         ProfScope prof(c);
         TRY(launch_moving(c->stream, mp, st.offsets.data(), f->dtype == B200OLS_F64, c->sm_count, ws, &c->launches));
     }
+    if (state_host) {
+        // state leaving each series: dense [A (F x F, symmetric), b (F), D]
+        if (N == 0) {  // nothing launched: the state is the entering one
+            for (int64_t g = 0; g < G; ++g) {
+                double *o = state_host + g * (NE + 1);
+                for (size_t e = 0; e < NE; ++e) {
+                    if (rk->initial_information) o[e] = rk->initial_information[g * NE + e];
+                    else if (e < static_cast<size_t>(F) * F) o[e] = (e / F == e % F) ? 1.0 / mp.p0 : 0.0;
+                    else o[e] = (mp.has_mean ? mp.mean[e - static_cast<size_t>(F) * F] : 0.0) / mp.p0;
+                }
+                o[NE] = 1.0;
+            }
+            return 0;
+        }
+        CU(cudaMemcpyAsync(state_host, mp.state_out, sizeof(double) * (NE + 1) * G, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int64_t g = 0; g < G; ++g) {  // the device carries the lower triangle
+            double *A = state_host + g * (NE + 1);
+            for (int i = 0; i < F; ++i)
+                for (int j = i + 1; j < F; ++j) A[i * F + j] = A[j * F + i];
+        }
+        return 0;
+    }
     if (f->memspace == B200OLS_HOST) {
         CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * out_elems, cudaMemcpyDeviceToHost, c->stream));
         if (dval) CU(cudaMemcpyAsync(out->validity, dval, out_elems, cudaMemcpyDeviceToHost, c->stream));
@@ -1473,8 +1521,8 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
 }
 
 static int run_moving(b200ols_ctx *c, const b200ols_frame *f, int kind, const b200ols_rls_kwargs *rk,
-                      const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out) {
-    const int rc = run_moving_impl(c, f, kind, rk, wk, mode, out);
+                      const b200ols_rolling_kwargs *wk, int mode, b200ols_output *out, double *state_host = nullptr) {
+    const int rc = run_moving_impl(c, f, kind, rk, wk, mode, out, state_host);
     if (c && c->pinned) pinned_end(c);
     return rc;
 }
@@ -1489,6 +1537,13 @@ extern "C" int b200ols_recursive_least_squares_coefficients(b200ols_ctx *c, cons
                                                             const b200ols_rls_kwargs *kw, b200ols_output *out) {
     if (!kw) return fail(B200OLS_ERR_INVALID, "kwargs is NULL");
     return run_moving(c, f, MOVING_RLS, kw, nullptr, B200OLS_COEFFICIENTS, out);
+}
+extern "C" int b200ols_recursive_least_squares_state(b200ols_ctx *c, const b200ols_frame *f, const b200ols_rls_kwargs *kw,
+                                                     double *state) {
+    if (!kw) return fail(B200OLS_ERR_INVALID, "kwargs is NULL");
+    if (!state) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    // the prior mean belongs to the state whatever the mode (the caller composes states, not predictions)
+    return run_moving(c, f, MOVING_RLS, kw, nullptr, B200OLS_COEFFICIENTS, nullptr, state);
 }
 extern "C" int b200ols_rolling_least_squares(b200ols_ctx *c, const b200ols_frame *f, const b200ols_rolling_kwargs *kw, int mode,
                                              b200ols_output *out) {

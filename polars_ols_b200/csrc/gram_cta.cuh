@@ -14,6 +14,10 @@
 //   warps W+1..W+4    SOLVERS  : (round-robin over segments) each sums the W partial fragments in a fixed order (deterministic), runs the
 //                                warp-cooperative register Cholesky (LU fallback) of gram_stream.cuh and
 //                                writes beta — overlapped with the consumers' next segment.
+// Short groups (team mode): when every segment fits one tile, the consumers split into W / team TEAMS of `team`
+// warps and consecutive segments go to consecutive teams, so that a warp sees every (W / team)-th group only
+// and its fixed per-group cost (barrier round trips, publishing the accumulator fragments) is amortised over
+// team-times more rows; with team = 1 a warp owns whole groups and the solver has a single slot to read.
 // One persistent CTA per SM; the unit of scheduling is the SM, so 10k groups spread over 148 SMs with
 // < 1 % imbalance (a warp-per-group mapping quantises at 2.8 groups per warp), and up to STAGES whole
 // tiles (~200 KB) are in flight per SM irrespective of occupancy or register pressure.
@@ -24,7 +28,7 @@ namespace b200 {
 
 constexpr int CTA_CONSUMERS = 8;
 constexpr int CTA_SOLVERS = 4;   // the k x k solve is a long dependent chain: several groups are solved concurrently
-constexpr int CTA_RED_DEPTH = 6; // ring of published partial-fragment buffers (consumers may run this far ahead)
+constexpr int CTA_RED_DEPTH = 6; // max ring depth of published partial-fragment buffers (GramParams::red_depth; consumers may run this far ahead)
 constexpr int CTA_THREADS = (CTA_CONSUMERS + CTA_SOLVERS + 1) * 32;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -35,8 +39,8 @@ template <int KB>
 __host__ __device__ constexpr int cta_red_doubles() { return KB * (KB + 1) + KB + 1; }  // acc frags, cy, nfit
 
 template <typename T>
-__host__ __device__ inline size_t cta_fixed_smem(int KB, int F) {
-    const size_t red = static_cast<size_t>(CTA_RED_DEPTH) * CTA_CONSUMERS * 32 * (KB * (KB + 1) + KB + 1) * sizeof(double);
+__host__ __device__ inline size_t cta_fixed_smem(int KB, int F, int red_depth) {
+    const size_t red = static_cast<size_t>(red_depth) * CTA_CONSUMERS * 32 * (KB * (KB + 1) + KB + 1) * sizeof(double);
     return red + CTA_SOLVERS * gram_scratch_bytes<T>(F, 1) + 128;
 }
 
@@ -49,7 +53,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     constexpr int RED = cta_red_doubles<KB>();
 
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES], red_full[CTA_RED_DEPTH], red_empty[CTA_RED_DEPTH];
+    __shared__ uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES], red_full[CTA_RED_DEPTH * CTA_CONSUMERS],
+        red_empty[CTA_RED_DEPTH * CTA_CONSUMERS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fb = lane >> 2, q = lane & 3;
@@ -57,18 +62,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     const int ycol = kd, wcol = kd + 1, mcol = kd + 1 + (p.has_w ? 1 : 0);
     const int NC = kd + 1 + (p.has_w ? 1 : 0) + (p.has_mask ? 1 : 0);
     const int R = p.tile_rows, S = p.stages;
+    const int TEAM = (p.team > 0 && p.team < W) ? p.team : W;  // consumer warps per segment
+    const int NT = W / TEAM;                                    // teams; segment i (CTA-local) -> team i % NT
+    const int DEPTH = (p.red_depth > 0 && p.red_depth < CTA_RED_DEPTH) ? p.red_depth : CTA_RED_DEPTH;
+    const int RD = DEPTH * NT;                                  // ring of published buffers (TEAM slots each)
     const uint32_t stride = gram_col_stride<T>(R);
     const uint32_t stage_bytes = static_cast<uint32_t>(NC) * stride;
     double *red = reinterpret_cast<double *>(smem + static_cast<size_t>(S) * stage_bytes);
-    double *Gs_base = red + CTA_RED_DEPTH * W * 32 * RED;
+    double *Gs_base = red + DEPTH * W * 32 * RED;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], W);
+            mbar_init(&empty_bar[s], TEAM);
         }
-        for (int b = 0; b < CTA_RED_DEPTH; ++b) {
-            mbar_init(&red_full[b], W);
+        for (int b = 0; b < RD; ++b) {
+            mbar_init(&red_full[b], TEAM);
             mbar_init(&red_empty[b], 1);
         }
         fence_mbar_init();
@@ -89,7 +98,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
         for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
             const int64_t r0 = nr0, r1 = nr1;
             if (seg + gridDim.x < nseg) { nr0 = p.seg_off[seg + gridDim.x]; nr1 = p.seg_off[seg + gridDim.x + 1]; }
-            for (int64_t row = r0; row < r1; row += R) {
+            // team mode maps tile index == segment index, so an empty segment still takes one (empty) tile
+            for (int64_t row = r0; row < r1 || (NT > 1 && row == r0); row += R) {
                 const int64_t b = (row + R < r1) ? row + R : r1;
                 const int64_t a_al = row & ~static_cast<int64_t>(A - 1);
                 int64_t b_al = (b + (A - 1)) & ~static_cast<int64_t>(A - 1);
@@ -102,9 +112,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                     mbar_arrive_expect_tx(&full_bar[stage], bytes * static_cast<uint32_t>(NC));
                 }
                 __syncwarp();
-                for (int c = lane; c < NC; c += 32)
-                    bulk_g2s(sb + static_cast<size_t>(c) * stride, static_cast<const T *>(p.cols[c]) + a_al, bytes,
-                             &full_bar[stage]);
+                if (bytes)
+                    for (int c = lane; c < NC; c += 32)
+                        bulk_g2s(sb + static_cast<size_t>(c) * stride, static_cast<const T *>(p.cols[c]) + a_al, bytes,
+                                 &full_bar[stage]);
                 if (++stage == S) {
                     stage = 0;
                     phase ^= 1u;
@@ -113,15 +124,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
         }
     } else if (warp <= W) {
         // ================================ CONSUMERS ================================
-        const int cw = warp - 1;
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t red_i = 0;
+        const int cw = (warp - 1) % TEAM, team_id = (warp - 1) / TEAM;
+        // team mode (NT > 1) requires one tile per segment, so tile index == CTA-local segment index
+        uint32_t red_i = team_id;
+        int stage = team_id % S;
+        uint32_t phase = (team_id / S) & 1u;
+        const int64_t seg_step = static_cast<int64_t>(NT) * gridDim.x;
+        const int64_t seg_first = blockIdx.x + static_cast<int64_t>(team_id) * gridDim.x;
         int64_t nr0 = 0, nr1 = 0;
-        if (static_cast<int64_t>(blockIdx.x) < nseg) { nr0 = p.seg_off[blockIdx.x]; nr1 = p.seg_off[blockIdx.x + 1]; }
-        for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        if (seg_first < nseg) { nr0 = p.seg_off[seg_first]; nr1 = p.seg_off[seg_first + 1]; }
+        for (int64_t seg = seg_first; seg < nseg; seg += seg_step) {
             const int64_t r0 = nr0, r1 = nr1;
-            if (seg + gridDim.x < nseg) { nr0 = p.seg_off[seg + gridDim.x]; nr1 = p.seg_off[seg + gridDim.x + 1]; }
+            if (seg + seg_step < nseg) { nr0 = p.seg_off[seg + seg_step]; nr1 = p.seg_off[seg + seg_step + 1]; }
             constexpr bool DUAL = KB <= 2;
             double acc[NPAIR][2], acc2[DUAL ? NPAIR : 1][2];
             double cy[KB];
@@ -133,12 +147,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
             for (int i = 0; i < KB; ++i) cy[i] = 0.0;
             int nfit = 0;
 
-            for (int64_t row = r0; row < r1; row += R) {
+            for (int64_t row = r0; row < r1 || (NT > 1 && row == r0); row += R) {
                 const int64_t b = (row + R < r1) ? row + R : r1;
                 const int o = static_cast<int>(row & (A - 1));
                 const int hi = o + static_cast<int>(b - row);  // valid local rows are [o, hi)
                 const int noct = (hi + 7) >> 3;
-                const int per = (noct + W - 1) / W;
+                const int per = (noct + TEAM - 1) / TEAM;
                 const int j0 = cw * per;
                 const int j1 = (j0 + per < noct) ? j0 + per : noct;
                 mbar_wait(&full_bar[stage], phase);
@@ -247,15 +261,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
-                if (++stage == S) {
-                    stage = 0;
-                    phase ^= 1u;
+                if (NT == 1) {
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                } else {  // next tile of this team: NT tiles further on
+                    const uint32_t t = red_i + NT;
+                    stage = static_cast<int>(t % S);
+                    phase = (t / S) & 1u;
                 }
             }
             // ---- publish this warp's partial fragments ----
-            const int buf = red_i % CTA_RED_DEPTH;
-            mbar_wait(&red_empty[buf], ((red_i / CTA_RED_DEPTH) & 1u) ^ 1u);
-            double *slot = red + (static_cast<size_t>(buf) * W + cw) * 32 * RED;
+            const int buf = red_i % RD;
+            mbar_wait(&red_empty[buf], ((red_i / RD) & 1u) ^ 1u);
+            double *slot = red + (static_cast<size_t>(buf) * TEAM + cw) * 32 * RED;
 #pragma unroll
             for (int i = 0; i < NPAIR; ++i) {
                 slot[(2 * i) * 32 + lane] = DUAL ? acc[i][0] + acc2[i][0] : acc[i][0];
@@ -266,7 +286,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
             slot[(2 * NPAIR + KB) * 32 + lane] = static_cast<double>(nfit);
             __syncwarp();
             if (lane == 0) mbar_arrive(&red_full[buf]);
-            ++red_i;
+            red_i += NT;
         }
     } else {
         // ================================ SOLVERS ================================
@@ -276,16 +296,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
         uint32_t red_i = sw;
         for (int64_t seg = blockIdx.x + static_cast<int64_t>(sw) * gridDim.x; seg < nseg;
              seg += static_cast<int64_t>(CTA_SOLVERS) * gridDim.x, red_i += CTA_SOLVERS) {
-            const int buf = red_i % CTA_RED_DEPTH;
-            mbar_wait(&red_full[buf], (red_i / CTA_RED_DEPTH) & 1u);
+            const int buf = red_i % RD;
+            mbar_wait(&red_full[buf], (red_i / RD) & 1u);
             double acc[NPAIR][2], cy[KB];
             double nf = 0.0;
 #pragma unroll
             for (int i = 0; i < NPAIR; ++i) acc[i][0] = acc[i][1] = 0.0;
 #pragma unroll
             for (int i = 0; i < KB; ++i) cy[i] = 0.0;
-            for (int cw = 0; cw < W; ++cw) {  // fixed order: deterministic sums
-                const double *slot = red + (static_cast<size_t>(buf) * W + cw) * 32 * RED;
+            for (int cw = 0; cw < TEAM; ++cw) {  // fixed order: deterministic sums
+                const double *slot = red + (static_cast<size_t>(buf) * TEAM + cw) * 32 * RED;
 #pragma unroll
                 for (int i = 0; i < NPAIR; ++i) {
                     acc[i][0] += slot[(2 * i) * 32 + lane];

@@ -29,7 +29,7 @@ namespace b200 {
 
 constexpr int GRAM_MAX_COLS = 72;   // 64 features + y + w + mask (+ slack)
 constexpr int GRAM_MAX_WARPS = 16;
-constexpr int GRAM_MAX_STAGES = 8;
+constexpr int GRAM_MAX_STAGES = 16;
 
 struct GramParams {
     const void *cols[GRAM_MAX_COLS];  // [0,kd) features, [kd] y, then sqrt-weights/weights, then row mask
@@ -46,6 +46,8 @@ struct GramParams {
     int64_t max_seg_rows;             // host-side hint: longest segment (tile sizing)
     int tile_rows;                    // R, multiple of 8
     int stages;                       // tiles in flight per warp
+    int team;                         // gram_cta: consumer warps per segment (0 = all)
+    int red_depth;                    // gram_cta: ring depth of published accumulator buffers (0 = max)
     // outputs
     int fused;                        // 1: solve in the epilogue and write beta; 0: write partials
     double *partial;                  // [nseg][F*F + F + 1]  (G row-major, c, n_fit)

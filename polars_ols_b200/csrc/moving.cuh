@@ -60,6 +60,10 @@ struct MovingParams {
     const int64_t *sup_c0, *sup_c1, *group_sup_off;
     double *sup;                      // [n_super][REC]
     int64_t *series_info;             // [G][3] rolling: mpv, n_valid, all_nan
+    // rls continued from / summarised for another time shard (single long series):
+    const double *init_info;          // [G][F*F+F] information state ENTERING each series (A row-major, b) or nullptr = prior
+    double *state_out;                // [G][F*F+F+1] state LEAVING each series (lower triangle of A, b) and the decay D, or nullptr
+    int state_only;                   // stop after the scan (b200ols_recursive_least_squares_state)
 };
 
 constexpr int MOVING_REC = MOVING_MAX_K * MOVING_MAX_K + MOVING_MAX_K + 1;
@@ -287,13 +291,18 @@ __global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int
         for (int t = 0; t < NT; ++t) {
             const int e = lane + 32 * t;
             double v = 0.0;
-            if (e < K * K) v = ((e / K) == (e % K)) ? 1.0 / p.p0 : 0.0;                  // A0 = I / p0
+            if (p.init_info) {                                                            // continued series
+                if (e < K * K) v = ((e % K) <= (e / K)) ? p.init_info[wid * NE + e] : 0.0;  // lower triangle only
+                else if (e < NE) v = p.init_info[wid * NE + e];
+            } else if (e < K * K) v = ((e / K) == (e % K)) ? 1.0 / p.p0 : 0.0;           // A0 = I / p0
             else if (e < NE) v = (p.has_mean ? p.mean[e - K * K] : 0.0) / p.p0;         // b0 = A0 theta0
             carry[t] = v;
         }
+        double Dall = 1.0;
         for (int64_t sc = group_sup_off[wid]; sc < group_sup_off[wid + 1]; ++sc) {
             double *rec = sup + sc * MOVING_REC;
             const double D = rec[NE];
+            Dall *= D;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const int e = lane + 32 * t;
@@ -304,6 +313,14 @@ __global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int
                 }
             }
             __syncwarp();
+        }
+        if (p.state_out) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int e = lane + 32 * t;
+                if (e < NE) p.state_out[wid * (NE + 1) + e] = carry[t];
+            }
+            if (lane == 0) p.state_out[wid * (NE + 1) + NE] = Dall;
         }
         return;
     }
@@ -359,7 +376,7 @@ __global__ void __launch_bounds__(128) rls_main_kernel(const MovingParams p) {
     const DevSrcT<T, K> src = make_src_t<T, K>(p, c);
     const int64_t g = p.chunk_group[c];
     const int64_t r0 = p.chunk_r0[c];
-    const bool first = r0 == p.group_off[g];
+    const bool first = (r0 == p.group_off[g]) && !p.init_info;  // a continued series enters through its information state
     RlsCfg cfg{p.lambda, p.p0};
     NormalState<K> in;
     if (!first) {
@@ -426,9 +443,11 @@ static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const i
         const unsigned sb = static_cast<unsigned>((p.n_super * 32 + 127) / 128);
         rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 0, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
         rls_scan_kernel<K><<<static_cast<unsigned>((p.n_groups * 32 + 127) / 128), 128, 0, stream>>>(p, 1, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
+        *launches += 3;
+        if (p.state_only) return cudaGetLastError();
         rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 2, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
         rls_main_kernel<T, K><<<cb, 128, 0, stream>>>(p);
-        *launches += 5;
+        *launches += 2;
     }
     return cudaGetLastError();
 }

@@ -292,6 +292,16 @@ class Engine:
         del keep, mean_keepalive
         return v, m
 
+    def recursive_least_squares_state(self, b: Batch, kw: L.RLSKwargs, keepalive=None) -> np.ndarray:
+        """b200ols_recursive_least_squares_state: [G, F*F + F + 1] information state leaving each series
+        (A row-major symmetric, b, decay D) given kw.initial_information (or the prior)."""
+        fr, keep, dtype, memspace, n, G = self._frame(b)
+        F = len(b.features) + (1 if b.add_intercept else 0)
+        out = np.empty((G, F * F + F + 1), dtype=np.float64)
+        L.check(self._lib.b200ols_recursive_least_squares_state(self._ctx, C.byref(fr), C.byref(kw), out.ctypes.data))
+        del keep, keepalive
+        return out
+
     def rolling_least_squares(self, b: Batch, kw: L.RollingKwargs, mode: int):
         fr, keep, dtype, memspace, n, G = self._frame(b)
         F = len(b.features) + (1 if b.add_intercept else 0)

@@ -236,7 +236,21 @@ class LsExpr:
         return self.mode if self.mode == "coefficients" else self.target.output_name or self.mode
 
     # -- evaluation ----------------------------------------------------------------------------------
-    def evaluate(self, frame: "Frame", engine: Optional[Engine] = None) -> Result:
+    def rls_c_kwargs(self, n_coef: int, initial_information: Optional[np.ndarray] = None):
+        """(ctypes RLSKwargs, buffers to keep alive).  `initial_information` [G, n_coef^2 + n_coef] continues each
+        series from the information state of an earlier time shard (parallel.time_sharded)."""
+        kw: RLSKwargs = self.kwargs
+        mean_arr = None
+        if kw.initial_state_mean is not None:
+            mean_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(kw.initial_state_mean, dtype=np.float64), (n_coef,)))
+        info = None if initial_information is None else np.ascontiguousarray(initial_information, dtype=np.float64)
+        ckw = L.RLSKwargs(nan_or(kw.half_life), nan_or(kw.initial_state_covariance),
+                          None if mean_arr is None else mean_arr.ctypes.data, L.NULL_POLICY[kw.null_policy], 0,
+                          None if info is None else info.ctypes.data)
+        return ckw, (mean_arr, info)
+
+    def batch(self, frame: "Frame"):
+        """(Batch of the resolved input columns, coefficient field names) — no grouping yet."""
         target = self.target.resolve(frame)
         feats = [f.resolve(frame) for f in self.features]
         names = [f.output_name or str(i) for i, f in enumerate(self.features)]  # src/expressions.rs:126-130
@@ -247,7 +261,12 @@ class LsExpr:
         if add_intercept:
             names = names + ["const"]
         weights = self.sample_weights.resolve(frame) if self.sample_weights is not None else None
-        b = Batch(target, feats, weights, add_intercept)
+        return Batch(target, feats, weights, add_intercept), names
+
+    def evaluate(self, frame: "Frame", engine: Optional[Engine] = None,
+                 initial_information: Optional[np.ndarray] = None) -> Result:
+        b, names = self.batch(frame)
+        target = b.target
         keys = group_of_row = None
         if self._over:
             key_arrays = []
@@ -268,15 +287,8 @@ class LsExpr:
                 return Result(self.output_name, v, None, names, keys, group_of_row)
             return Result(self.output_name, v, m)
         if self.kind == "recursive_least_squares":
-            kw: RLSKwargs = self.kwargs
-            mean = kw.initial_state_mean
-            n_coef = len(names)
-            mean_arr = None
-            if mean is not None:
-                mean_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(mean, dtype=np.float64), (n_coef,)))
-            ckw = L.RLSKwargs(nan_or(kw.half_life), nan_or(kw.initial_state_covariance),
-                              None if mean_arr is None else mean_arr.ctypes.data, L.NULL_POLICY[kw.null_policy], 0)
-            v, m = engine.recursive_least_squares(b, ckw, mode, mean_arr)
+            ckw, keep = self.rls_c_kwargs(len(names), initial_information)
+            v, m = engine.recursive_least_squares(b, ckw, mode, keep)
         else:
             v, m = engine.rolling_least_squares(b, self.kwargs.to_c(), mode)
         if self.mode == "coefficients":

@@ -394,3 +394,81 @@ def test_predict_intercept_and_null_policies():                            # tes
         p = Fm.select(col("coefficients").least_squares.predict("x1", "x2", "x3", null_policy=pol))["predictions"]
         ref = S.predict([cb[:, j] for j in range(3)], [dm["x1"], dm["x2"], dm["x3"]], pol)
         _close(p.to_numpy(), _ref(ref))
+
+
+# ----------------------------------------------------------------------------------- time-axis shards (§8e)
+def _run_time_sharded(expr, frame, world):
+    """all ranks of parallel.time_sharded, one after the other in this process (the exchange is the only
+    cross-rank step: pass 1 records every rank's shard map, pass 2 hands all of them to every rank)."""
+    from polars_ols_b200.parallel import time_sharded
+    maps = {}
+    if expr.kind == "recursive_least_squares":
+        for rank in range(world):
+            def record(local, rank=rank):
+                maps[rank] = local
+                return [local] * world
+            time_sharded(expr, frame, rank, world, exchange=record)
+    outs = []
+    for rank in range(world):
+        r, (r0, r1) = time_sharded(expr, frame, rank, world, exchange=lambda local: [maps[q] for q in range(world)])
+        v = r.to_numpy()
+        assert v.shape[0] == r1 - r0
+        outs.append(v)
+    return np.concatenate(outs, axis=0)
+
+
+@pytest.mark.parametrize("half_life,mean,policy", [(None, None, "drop"), (252.0, [0.5, -0.5, 0.25], "drop"), (30.0, None, "zero")])
+@pytest.mark.parametrize("mode", ["coefficients", "predictions"])
+def test_time_sharded_rls_matches_whole_series(half_life, mean, policy, mode):
+    d = _make_data(30_000, 3, add_missing=True, seed=12)
+    kw = dict(half_life=half_life, initial_state_mean=mean, null_policy=policy)
+    expr = col("y").least_squares.rls("x1", "x2", "x3", mode=mode, **kw)
+    got = _run_time_sharded(expr, Frame(d), 3)
+    ref = _ref(S.recursive_least_squares(d["y"], d["x1"], d["x2"], d["x3"], mode=mode, kwargs=S.RLSKwargs(**kw)))
+    _close(got[100:], ref[100:], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("window,min_periods,policy,missing", [(252, 6, "drop", False), (50, 10, "drop", True),
+                                                               (64, 8, "drop_window", True), (40, None, "zero", True)])
+@pytest.mark.parametrize("mode", ["coefficients", "residuals"])
+def test_time_sharded_rolling_matches_whole_series(window, min_periods, policy, missing, mode):
+    d = _make_data(30_000, 3, add_missing=missing, seed=13)
+    kw = dict(window_size=window, min_periods=min_periods, null_policy=policy)
+    expr = col("y").least_squares.rolling_ols("x1", "x2", "x3", mode=mode, **kw)
+    got = _run_time_sharded(expr, Frame(d), 4)
+    ref = _ref(S.rolling_least_squares(d["y"], d["x1"], d["x2"], d["x3"], mode=mode, kwargs=S.RollingKwargs(**kw)))
+    assert (np.isnan(got) == np.isnan(ref)).all()
+    ok = ~np.isnan(ref) & (np.abs(ref) < 1e6)
+    assert np.allclose(got[ok], ref[ok], rtol=1e-6, atol=1e-7)
+
+
+def test_rls_state_abi_against_information_form():
+    """b200ols_recursive_least_squares_state: (A, b, D) leaving each series, prior and continued."""
+    from polars_ols_b200 import _lib as L
+    from polars_ols_b200.engine import Batch, as_col
+    rng = np.random.default_rng(5)
+    n, k, lam = 4000, 3, np.exp(np.log(0.5) / 100.0)
+    x = rng.standard_normal((n, k))
+    y = x @ np.array([1.0, -2.0, 0.5]) + 0.1 * rng.standard_normal(n)
+    offs = np.array([0, 1500, 1500, 4000], dtype=np.int64)      # three series, the middle one empty
+    b = Batch(as_col(y), [as_col(np.ascontiguousarray(x[:, j])) for j in range(k)], offsets=offs)
+    eng = pls.get_engine(0)
+    mean = np.array([0.1, 0.2, 0.3])
+    for info in (None, rng.standard_normal((3, k * k + k))):
+        if info is not None:
+            for g in range(3):
+                a = rng.standard_normal((k, k))
+                info[g, :k * k] = (a @ a.T + np.eye(k)).reshape(-1)
+        kw = L.RLSKwargs(100.0, 5.0, mean.ctypes.data, L.NULL_POLICY["drop"], 0, None if info is None else info.ctypes.data)
+        st = eng.recursive_least_squares_state(b, kw, (mean, info))
+        for g in range(3):
+            if info is None:
+                A, bb = np.eye(k) / 5.0, mean / 5.0
+            else:
+                A, bb = info[g, :k * k].reshape(k, k).copy(), info[g, k * k:].copy()
+            D = 1.0
+            for r in range(offs[g], offs[g + 1]):
+                A, bb, D = lam * A + np.outer(x[r], x[r]), lam * bb + x[r] * y[r], D * lam
+            np.testing.assert_allclose(st[g, :k * k].reshape(k, k), A, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(st[g, k * k:k * k + k], bb, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(st[g, -1], D, rtol=1e-10, atol=1e-300)

@@ -28,7 +28,7 @@ def test_struct_layouts_match_the_header():
     from polars_ols_b200 import _lib
     assert C.sizeof(_lib.Column) == 16
     assert C.sizeof(_lib.Frame) == 8 + 16 + 16 + 8 + 8 + 8 + 8 + 8
-    assert C.sizeof(_lib.OLSKwargs) == 56 and C.sizeof(_lib.RLSKwargs) == 32 and C.sizeof(_lib.RollingKwargs) == 32
+    assert C.sizeof(_lib.OLSKwargs) == 56 and C.sizeof(_lib.RLSKwargs) == 40 and C.sizeof(_lib.RollingKwargs) == 32
     assert _lib.Frame.target.offset == 24 and _lib.Frame.group_offsets.offset == 64
 
 
@@ -143,3 +143,78 @@ def test_world_size_2_gather_over_gloo():
     [p.join(60) for p in ps]
     for rank, vals in res:
         assert vals == [0.0, 1.0, 2.0, 3.0, 4.0]
+
+
+# ---- time-axis sharding of one long series -------------------------------------------
+def _rolling_case(rng, n, k, null_frac, lead_nulls):
+    x = rng.standard_normal((n, k))
+    y = x @ (1 + 0.25 * rng.standard_normal(k)) + 0.1 * rng.standard_normal(n)
+    valid = rng.random(n) >= null_frac
+    valid[:lead_nulls] = False
+    return y, x, valid
+
+
+@pytest.mark.parametrize("null_policy", ["drop", "drop_window"])
+@pytest.mark.parametrize("null_frac,lead_nulls", [(0.0, 0), (0.3, 0), (0.7, 0), (0.2, 37), (0.95, 0)])
+def test_rolling_halo_reproduces_whole_series(null_policy, null_frac, lead_nulls):
+    """rows >= start computed from [halo_start, n) equal the whole-series result (oracle on both sides)."""
+    from oracle import semantics as S
+    from polars_ols_b200.parallel import rolling_halo_start
+
+    rng = np.random.default_rng(7)
+    n, k = 600, 3
+    fixed = null_policy == "drop_window"
+    for trial in range(12):
+        W = int(rng.integers(k + 5, 40))            # min_periods > k keeps every solved window well-posed, so the
+        mp = int(rng.integers(k + 2, W + 1))        # comparison is not between two roundings of a singular solve
+        y, x, valid = _rolling_case(rng, n, k, null_frac, lead_nulls)
+        yz, xz = np.where(valid, y, 0.0), np.where(valid[:, None], x, 0.0)
+        full = S.solve_rolling_ols(yz, xz, W, mp, None, None, valid, null_policy)
+        vf = None if valid.all() else (lambda a, b: valid[a:b].copy())
+        for start in (8, 64, 200, 424, 592):
+            h = rolling_halo_start(vf, start, W, mp, fixed, align=8)
+            assert 0 <= h <= start and h % 8 == 0
+            part = S.solve_rolling_ols(np.ascontiguousarray(yz[h:]), np.ascontiguousarray(xz[h:]), W, mp, None, None,
+                                       np.ascontiguousarray(valid[h:]), null_policy)
+            np.testing.assert_allclose(part[start - h:], full[start:], rtol=1e-8, atol=1e-10, equal_nan=True)
+        if null_frac == 0.0:  # without nulls a bounded halo always suffices
+            assert rolling_halo_start(vf, 592, W, mp, fixed, align=8) > 0 or 592 <= 2 * W + 16 + mp
+
+
+def test_rls_shard_maps_compose_to_the_sequential_filter():
+    """information-form maps of consecutive shards, folded over the prior, give the state the sequential
+    reference filter reaches (src/least_squares.rs:505-540)."""
+    from oracle import semantics as S
+    from polars_ols_b200.parallel import rls_entering_state, rls_prior_information, shard_rows
+
+    rng = np.random.default_rng(3)
+    n, k = 500, 4
+    x = rng.standard_normal((n, k))
+    y = x @ np.arange(1, k + 1) + 0.1 * rng.standard_normal(n)
+    valid = rng.random(n) > 0.1
+    for half_life, mean in ((None, None), (30.0, [0.5] * k)):
+        lam = 1.0 if half_life is None else np.exp(np.log(0.5) / half_life)
+        coef = S.solve_recursive_least_squares(np.where(valid, y, 0), np.where(valid[:, None], x, 0), half_life, 10.0, mean, valid)
+        shards = shard_rows(n, 4, align=8)
+        maps = []
+        for a, b in shards:
+            A, bb, D = np.zeros((k, k)), np.zeros(k), 1.0
+            for r in range(a, b):
+                if valid[r]:
+                    A, bb, D = lam * A + np.outer(x[r], x[r]), lam * bb + x[r] * y[r], D * lam
+            maps.append(np.concatenate([A.reshape(-1), bb, [D]]))
+        maps = np.stack(maps)
+        prior = rls_prior_information(k, 10.0, mean)
+        for rank in range(1, 4):
+            st = rls_entering_state(maps, prior, rank)
+            theta = np.linalg.solve(st[:k * k].reshape(k, k), st[k * k:])
+            np.testing.assert_allclose(theta, coef[shards[rank][0] - 1], rtol=1e-8, atol=1e-10)
+
+
+def test_shard_rows_alignment_and_cover():
+    from polars_ols_b200.parallel import shard_rows
+    for n in (0, 1, 63, 64, 1000, 50_000_000):
+        for w in (1, 2, 3, 8):
+            sh = shard_rows(n, w)
+            assert sh[0][0] == 0 and sh[-1][1] == n
+            assert all(a % 64 == 0 for a, _ in sh) and all(sh[i][1] == sh[i + 1][0] for i in range(w - 1))
