@@ -29,6 +29,7 @@
 #include "qr_fallback.cuh"
 #include "small_solve.cuh"
 #include "svd_solve.cuh"
+#include "big.cuh"
 #include "cd_solve.cuh"
 
 using namespace b200;
@@ -435,8 +436,8 @@ static int validate_frame(const b200ols_frame *f) {
     if (f->n_features < 0) return fail(B200OLS_ERR_INVALID, "n_features < 0");
     // src/expressions.rs:72 `assert!(m > 1, "must pass at least 2 series")`
     if (f->n_features + (f->add_intercept ? 1 : 0) < 1) return fail(B200OLS_ERR_INVALID, "must pass at least 2 series");
-    if (f->n_features + (f->add_intercept ? 1 : 0) > 64)
-        return fail(B200OLS_ERR_UNSUPPORTED, "more than 64 coefficients (%d) is not implemented on the device yet",
+    if (f->n_features + (f->add_intercept ? 1 : 0) > BIG_MAX_F)
+        return fail(B200OLS_ERR_UNSUPPORTED, "more than %d coefficients (%d) is not implemented on the device", BIG_MAX_F,
                     f->n_features + (f->add_intercept ? 1 : 0));
     if (f->dtype != B200OLS_F64 && f->dtype != B200OLS_F32) return fail(B200OLS_ERR_INVALID, "bad dtype %d", f->dtype);
     if (f->memspace != B200OLS_HOST && f->memspace != B200OLS_DEVICE) return fail(B200OLS_ERR_INVALID, "bad memspace");
@@ -764,13 +765,26 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));  // sweep hook: warps_per_cta caps the stages
         gp.tile_rows = R;
         gp.stages = S;
-        // short groups: fewer consumer warps per segment (teams), >= ~16 row octets per warp; needs one tile per segment
+        // short groups: fewer consumer warps per segment (teams), >= ~16 row octets per warp; needs one tile per segment.
+        // A parity wait may only ever be one phase behind or level with its barrier, never ahead of it, so every
+        // barrier must be waited on by the SAME warps in every phase: stages % teams == 0 (a stage always belongs to
+        // one team) and ring % solvers == 0 (a published buffer always goes to the same solver warp).
         gp.team = 0;
         if (gp.max_seg_rows <= R) {
             int team = CTA_CONSUMERS;
             while (team > 1 && gp.max_seg_rows <= 128 * (team / 2)) team >>= 1;
-            if (c->ctas_per_sm > 0) team = std::min(CTA_CONSUMERS, std::max(1, c->ctas_per_sm));  // sweep hook (power of two)
-            gp.team = team;
+            if (c->ctas_per_sm > 0) {  // sweep hook: nearest power of two <= 8
+                team = 1;
+                while (team * 2 <= std::min(CTA_CONSUMERS, c->ctas_per_sm)) team *= 2;
+            }
+            while (team < CTA_CONSUMERS && S / (CTA_CONSUMERS / team) == 0) team <<= 1;  // fewer teams than stages
+            if (team < CTA_CONSUMERS) {
+                const int nt = CTA_CONSUMERS / team;
+                S = S / nt * nt;
+                if ((gp.red_depth * nt) % CTA_SOLVERS != 0) gp.red_depth -= gp.red_depth % 2;  // nt = 2: even ring depth
+                gp.stages = S;
+                gp.team = team;
+            }
         }
         const size_t smem = static_cast<size_t>(S) * NC * gram_col_stride<T>(R) + fixed;
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, gp.nseg));
@@ -909,6 +923,270 @@ static int64_t choose_seg_max(const b200ols_ctx *c, int64_t n_groups, int64_t n_
 }
 static constexpr double ILLCOND_RATIO = 1.0e7;  // squared-pivot ratio above which OLS is re-solved by QR
 
+// ------------------------------------------------------------------------------------------------
+// static models with more than 64 coefficients (big.cuh): general, slower path
+// ------------------------------------------------------------------------------------------------
+static int upload_small(b200ols_ctx *c, const void *src, size_t bytes, void **dev) {
+    TRY(pinned_reserve(c, c->pinned_off + bytes + 256));
+    char *h = c->pinned + c->pinned_off;
+    c->pinned_off += round_up(bytes, 256);
+    std::memcpy(h, src, bytes);
+    char *d = arena_alloc<char>(c, bytes);
+    CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    *dev = d;
+    return 0;
+}
+
+static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, const StaticRoute &rt, int mode,
+                          b200ols_output *out, bool peer_mode) {
+    const int kd = f->n_features, F = kd + (f->add_intercept ? 1 : 0), has_w = f->sample_weights ? 1 : 0;
+    const int ncol = kd + 1 + has_w;
+    const int64_t G = f->n_groups, N = f->n_rows;
+    const size_t esz = f->dtype == B200OLS_F64 ? 8 : 4;
+    const size_t P = static_cast<size_t>(F) * F + F + 1;
+    const bool cd = rt.route == ROUTE_CD || rt.route == ROUTE_CD_ACTIVE;
+    const bool any_svd = rt.svd_all || rt.svd_wide;
+
+    std::vector<int64_t> offsets(static_cast<size_t>(G) + 1);
+    if (f->group_offsets) std::memcpy(offsets.data(), f->group_offsets, sizeof(int64_t) * (G + 1));
+    else { offsets[0] = 0; offsets[1] = N; }
+    bool any_wide = false, any_tall = false;
+    for (int64_t g = 0; g < G; ++g) {
+        const int64_t len = offsets[g + 1] - offsets[g];
+        if (len < 0) return fail(B200OLS_ERR_INVALID, "group_offsets must be non-decreasing");
+        if (len > 0 && len <= F) any_wide = true;
+        if (len > F) any_tall = true;
+    }
+
+    const size_t bm_bytes = static_cast<size_t>((N + 7) / 8);
+    size_t bytes = static_cast<size_t>(ncol) * 64 + (static_cast<size_t>(G) + 8) * 16 + (1 << 20);
+    if (f->memspace == B200OLS_HOST)
+        bytes += static_cast<size_t>(ncol) * (round_up(static_cast<size_t>(N) * esz, 256) + round_up(bm_bytes, 256) + 512) +
+                 round_up(static_cast<size_t>(N) * 8, 256) + static_cast<size_t>(N) * 9 + 8192;
+    bytes += static_cast<size_t>(F + 1) * N * 8 + static_cast<size_t>(N) + static_cast<size_t>(G) * P * 8 + 4096;   // W, mask, records
+    if (rt.route == ROUTE_CHOL) bytes += static_cast<size_t>(G) * F * F * 8 + 256;                                    // Cholesky copy
+    bytes += static_cast<size_t>(G) * F * (8 + 4 + 8 + 2 * 4 + 2 * 8) + static_cast<size_t>(G) * 4 + 8192;           // beta, perm, z, cd scratch, flags
+    if (any_svd) bytes += 2 * static_cast<size_t>(N) * F * 8 + static_cast<size_t>(G) * F * F * 8 + 4096;             // X^T, J, V
+    TRY(arena_reserve(c, bytes));
+    c->arena_off = 0;
+    TRY(pinned_begin(c));
+
+    // columns on the device + pointer tables
+    std::vector<const void *> vals(ncol);
+    std::vector<const uint8_t *> valid(ncol);
+    for (int cidx = 0; cidx < ncol; ++cidx) {
+        const b200ols_column *col = cidx < kd ? &f->features[cidx] : (cidx == kd ? &f->target : f->sample_weights);
+        if (N > 0 && !col->values) return fail(B200OLS_ERR_INVALID, "column %d: values is NULL", cidx);
+        if (f->memspace == B200OLS_DEVICE) {
+            vals[cidx] = col->values;
+            valid[cidx] = col->validity;
+        } else {
+            char *d = arena_alloc<char>(c, static_cast<size_t>(N) * esz + 16);
+            if (N > 0) CU(cudaMemcpyAsync(d, col->values, static_cast<size_t>(N) * esz, cudaMemcpyHostToDevice, c->stream));
+            vals[cidx] = d;
+            valid[cidx] = nullptr;
+            if (col->validity) {
+                uint8_t *b = arena_alloc<uint8_t>(c, bm_bytes);
+                CU(cudaMemcpyAsync(b, col->validity, bm_bytes, cudaMemcpyHostToDevice, c->stream));
+                valid[cidx] = b;
+            }
+        }
+    }
+    BigParams bp;
+    std::memset(&bp, 0, sizeof(bp));
+    {
+        void *d = nullptr;
+        TRY(upload_small(c, vals.data(), sizeof(void *) * ncol, &d));
+        bp.vals = static_cast<const void *const *>(d);
+        TRY(upload_small(c, valid.data(), sizeof(void *) * ncol, &d));
+        bp.valid = static_cast<const uint8_t *const *>(d);
+        TRY(upload_small(c, offsets.data(), sizeof(int64_t) * (G + 1), &d));
+        bp.group_off = static_cast<const int64_t *>(d);
+    }
+    if (f->row_index) {
+        if (f->memspace == B200OLS_DEVICE) bp.row_index = f->row_index;
+        else {
+            int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(N));
+            CU(cudaMemcpyAsync(d, f->row_index, sizeof(int64_t) * N, cudaMemcpyHostToDevice, c->stream));
+            bp.row_index = d;
+        }
+    }
+    bool any_validity = false;
+    for (int cidx = 0; cidx < ncol; ++cidx) any_validity = any_validity || valid[cidx] != nullptr;
+    int fill, mask_kind;
+    policy_to_prep(kw->null_policy, false, &fill, &mask_kind);
+    bp.kd = kd;
+    bp.intercept = f->add_intercept ? 1 : 0;
+    bp.F = F;
+    bp.has_w = has_w;
+    bp.f32 = f->dtype == B200OLS_F32;
+    bp.fill = fill;
+    bp.mask_kind = any_validity ? mask_kind : MASK_NONE;
+    bp.n_rows = N;
+    bp.n_groups = G;
+    bp.W = arena_alloc<double>(c, static_cast<size_t>(F + 1) * N + 8);
+    bp.mask = arena_alloc<uint8_t>(c, static_cast<size_t>(N) + 8);
+    bp.rec = arena_alloc<double>(c, static_cast<size_t>(G) * P);
+    bp.work = rt.route == ROUTE_CHOL ? arena_alloc<double>(c, static_cast<size_t>(G) * F * F) : nullptr;
+    bp.beta = arena_alloc<double>(c, static_cast<size_t>(G) * F);
+    bp.flags = arena_alloc<int32_t>(c, static_cast<size_t>(G));
+    bp.route = rt.svd_all ? ROUTE_FLAGS_ONLY : rt.route;
+    bp.alpha = rt.alpha;
+    bp.l1_ratio = rt.l1_ratio;
+    bp.tol = rt.tol;
+    bp.illcond_ratio = ILLCOND_RATIO;
+    bp.max_iter = rt.max_iter;
+    bp.positive = rt.positive;
+    bp.svd_ridge = rt.svd_ridge ? 1 : 0;
+    bp.skip_wide = rt.svd_wide ? 1 : 0;
+    bp.rcond = rt.rcond;
+    bp.max_sweeps = 60;
+    c->last_flags = bp.flags;
+    c->last_flags_n = G;
+    ARENA_GUARD(c);
+
+    const unsigned row_blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, static_cast<int64_t>(c->sm_count) * 16)));
+    if (N > 0) {
+        big_materialise_kernel<<<row_blocks, 256, 0, c->stream>>>(bp);
+        c->launches++;
+    }
+    {
+        const int ntile = (F + BIG_TILE - 1) / BIG_TILE;
+        const int64_t blocks = G * (static_cast<int64_t>(ntile) * (ntile + 1) / 2);
+        if (blocks > 0x7fffffffLL) return fail(B200OLS_ERR_UNSUPPORTED, "too many groups x coefficient tiles for one launch");
+        ProfScope prof(c);
+        big_gram_kernel<<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(bp, ntile);
+        c->launches++;
+    }
+    big_xty_kernel<<<static_cast<unsigned>((G * F * 32 + 255) / 256), 256, 0, c->stream>>>(bp);
+    c->launches++;
+    {
+        const size_t smem = big_solve_smem(F);
+        static size_t attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || smem > attr_set[dev])) {
+            CU(cudaFuncSetAttribute(big_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            if (dev >= 0 && dev < 64) attr_set[dev] = smem;
+        }
+        big_solve_kernel<<<static_cast<unsigned>(G), BIG_SOLVE_THREADS, smem, c->stream>>>(bp);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    if (cd && any_wide) {
+        int *iws = arena_alloc<int>(c, static_cast<size_t>(G) * 2 * F);
+        double *dws = arena_alloc<double>(c, static_cast<size_t>(G) * 2 * F);
+        ARENA_GUARD(c);
+        big_cd_wide_kernel<<<static_cast<unsigned>((G * 32 + 127) / 128), 128, 0, c->stream>>>(bp, iws, dws);
+        c->launches++;
+    }
+    if (rt.ols_qr_guard && any_tall) {
+        QrParams qp;
+        std::memset(&qp, 0, sizeof(qp));
+        qp.kd = kd;
+        qp.intercept = bp.intercept;
+        qp.F = F;
+        qp.n_groups = G;
+        qp.n_rows = N;
+        qp.group_off = bp.group_off;
+        qp.ws = bp.W;
+        qp.beta = bp.beta;
+        qp.flags = bp.flags;
+        qp.materialised = 1;
+        qp.perm_ws = arena_alloc<int>(c, static_cast<size_t>(G) * F);
+        qp.z_ws = arena_alloc<double>(c, static_cast<size_t>(G) * F);
+        ARENA_GUARD(c);
+        CU(launch_qr_fallback_kernel(c->stream, qp, true));
+        c->launches++;
+    }
+    if (any_svd) {
+        if (any_tall && rt.svd_all) {  // n > k groups with solve_method = "svd": one-sided Jacobi on X itself
+            SvdParams sv;
+            std::memset(&sv, 0, sizeof(sv));
+            sv.q.kd = kd;
+            sv.q.intercept = bp.intercept;
+            sv.q.F = F;
+            sv.q.n_groups = G;
+            sv.q.n_rows = N;
+            sv.q.group_off = bp.group_off;
+            sv.q.ws = bp.W;
+            sv.q.beta = bp.beta;
+            sv.q.flags = bp.flags;
+            sv.vws = arena_alloc<double>(c, static_cast<size_t>(G) * F * F + 8);
+            sv.all_groups = 1;
+            sv.ridge = rt.svd_ridge ? 1 : 0;
+            sv.alpha = rt.alpha;
+            sv.rcond = rt.rcond;
+            sv.max_sweeps = 60;
+            sv.materialised = 1;
+            sv.skip_rows_le_F = 1;
+            ARENA_GUARD(c);
+            CU(launch_svd_solve(c->stream, sv, true));
+            c->launches++;
+        }
+        if (any_wide) {
+            bp.T = arena_alloc<double>(c, static_cast<size_t>(N) * F + 8);
+            bp.J = arena_alloc<double>(c, static_cast<size_t>(N) * F + 8);
+            ARENA_GUARD(c);
+            big_svd_wide_kernel<<<static_cast<unsigned>((G * 32 + 127) / 128), 128, 0, c->stream>>>(bp, rt.svd_all ? 1 : 0);
+            c->launches++;
+        }
+    }
+    CU(cudaGetLastError());
+
+    if (peer_mode) {
+        PeerScatterParams ps;
+        std::memset(&ps, 0, sizeof(ps));
+        ps.beta = bp.beta;
+        ps.n_peers = c->n_peers;
+        for (int r = 0; r < c->n_peers; ++r) ps.peer[r] = c->peer_coef[r];
+        ps.n = static_cast<int64_t>(G) * F;
+        ps.base_elems = c->peer_group_base * F;
+        peer_scatter_kernel<<<static_cast<unsigned>((ps.n + 255) / 256), 256, 0, c->stream>>>(ps);
+        c->launches++;
+        CU(cudaGetLastError());
+        if (!out->values) return 0;
+    }
+    if (mode == B200OLS_COEFFICIENTS) {
+        const size_t ob = static_cast<size_t>(G) * F * sizeof(double);
+        if (f->memspace == B200OLS_HOST) {
+            CU(cudaMemcpyAsync(out->values, bp.beta, ob, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (out->validity)
+                for (size_t i = 0; i < static_cast<size_t>(G) * F; ++i) out->validity[i] = std::isnan(out->values[i]) ? 0 : 1;
+        } else {
+            CU(cudaMemcpyAsync(out->values, bp.beta, ob, cudaMemcpyDeviceToDevice, c->stream));
+            if (out->validity) {
+                nan_mask_kernel<<<static_cast<unsigned>((static_cast<size_t>(G) * F + 255) / 256), 256, 0, c->stream>>>(out->values, out->validity, static_cast<int64_t>(G) * F);
+                c->launches++;
+            }
+        }
+        return 0;
+    }
+    bp.residuals = mode == B200OLS_RESIDUALS;
+    bp.drop_mask = (kw->null_policy == B200OLS_NULL_DROP && any_validity) ? 1 : 0;
+    double *dout = out->values;
+    uint8_t *dval = out->validity;
+    if (f->memspace == B200OLS_HOST) {
+        dout = arena_alloc<double>(c, static_cast<size_t>(N));
+        dval = out->validity ? arena_alloc<uint8_t>(c, static_cast<size_t>(N)) : nullptr;
+        ARENA_GUARD(c);
+    }
+    bp.out = dout;
+    bp.out_valid = dval;
+    if (N > 0) {
+        big_predict_kernel<<<row_blocks, 256, 0, c->stream>>>(bp);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (f->memspace == B200OLS_HOST) {
+        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(N), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
 static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
     const bool peer_mode = c->n_peers > 0 && mode == B200OLS_COEFFICIENTS && f && f->memspace == B200OLS_DEVICE;
@@ -925,6 +1203,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     TRY(free_retired(c));
 
     const int F = f->n_features + (f->add_intercept ? 1 : 0);
+    if (F > 64) return run_static_big(c, f, kw, rt, mode, out, peer_mode);
     const int64_t G = f->n_groups, N = f->n_rows;
     const size_t P = static_cast<size_t>(F) * F + F + 1;
     // arena budget
@@ -1195,6 +1474,7 @@ struct RowDotParams {
     const double *coef[GRAM_MAX_COLS];
     const uint8_t *coef_valid[GRAM_MAX_COLS];
     int n_coef, n_feat, fill_nan, drop;
+    int accumulate;  // continue the row sums of an earlier batch of coefficient columns (more than 64 coefficients)
     int64_t n_rows;
     double *out;
     uint8_t *out_valid;
@@ -1204,8 +1484,8 @@ template <typename T>
 static __global__ void __launch_bounds__(256) rowdot_kernel(const RowDotParams p) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n_rows; r += stride) {
-        double acc = 0.0;
-        bool all_valid = true;
+        double acc = p.accumulate ? p.out[r] : 0.0;
+        bool all_valid = (p.accumulate && p.drop && p.out_valid) ? (p.out_valid[r] != 0) : true;
         for (int j = 0; j < p.n_coef; ++j) {
             bool cv = p.coef_valid[j] ? ((p.coef_valid[j][r >> 3] >> (r & 7)) & 1) : true;
             const double c = cv ? p.coef[j][r] : static_cast<double>(NAN);
@@ -1228,7 +1508,7 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
                                int32_t null_policy, b200ols_output *out) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
     if (!coefficients || !out || !out->values) return fail(B200OLS_ERR_INVALID, "NULL argument");
-    if (n_rows < 0 || n_coef < 1 || n_coef > 64) return fail(B200OLS_ERR_INVALID, "bad shape");
+    if (n_rows < 0 || n_coef < 1 || n_coef > BIG_MAX_F) return fail(B200OLS_ERR_INVALID, "bad shape");
     const int n_feat = n_coef - (add_intercept ? 1 : 0);
     // src/expressions.rs:717-721 "number of coefficients must match number of features!"
     if (n_feat < 0 || (n_feat > 0 && !features)) return fail(B200OLS_ERR_INVALID, "number of coefficients must match number of features!");
@@ -1244,13 +1524,6 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
     c->arena_off = 0;
     TRY(pinned_begin(c));
     c->last_flags = nullptr;
-    RowDotParams rp;
-    std::memset(&rp, 0, sizeof(rp));
-    rp.n_coef = n_coef;
-    rp.n_feat = n_feat;
-    rp.fill_nan = null_policy == B200OLS_NULL_IGNORE;
-    rp.drop = null_policy == B200OLS_NULL_DROP;
-    rp.n_rows = n_rows;
     auto stage = [&](const b200ols_column &col, size_t es, const void **v, const uint8_t **m) -> int {
         if (memspace == B200OLS_DEVICE) {
             *v = col.values;
@@ -1268,29 +1541,39 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
         }
         return 0;
     };
-    for (int j = 0; j < n_coef; ++j) {
-        const void *v;
-        TRY(stage(coefficients[j], 8, &v, &rp.coef_valid[j]));
-        rp.coef[j] = static_cast<const double *>(v);
-        if (j < n_feat) TRY(stage(features[j], esz, &rp.feat[j], &rp.feat_valid[j]));
-    }
     double *dout = out->values;
     uint8_t *dval = out->validity;
     if (memspace == B200OLS_HOST) {
         dout = arena_alloc<double>(c, static_cast<size_t>(n_rows));
         dval = out->validity ? arena_alloc<uint8_t>(c, static_cast<size_t>(n_rows)) : nullptr;
     }
-    rp.out = dout;
-    rp.out_valid = dval;
-    ARENA_GUARD(c);
     const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((n_rows + 255) / 256, static_cast<int64_t>(c->sm_count) * 16));
-    {
+    // the kernel takes up to 64 coefficient columns by value; more are summed batch after batch (same order of
+    // additions per row as one pass)
+    for (int b0 = 0; b0 < n_coef; b0 += 64) {
+        RowDotParams rp;
+        std::memset(&rp, 0, sizeof(rp));
+        rp.n_coef = std::min(64, n_coef - b0);
+        rp.n_feat = std::max(0, std::min(rp.n_coef, n_feat - b0));
+        rp.fill_nan = null_policy == B200OLS_NULL_IGNORE;
+        rp.drop = null_policy == B200OLS_NULL_DROP;
+        rp.accumulate = b0 > 0;
+        rp.n_rows = n_rows;
+        for (int j = 0; j < rp.n_coef; ++j) {
+            const void *v;
+            TRY(stage(coefficients[b0 + j], 8, &v, &rp.coef_valid[j]));
+            rp.coef[j] = static_cast<const double *>(v);
+            if (j < rp.n_feat) TRY(stage(features[b0 + j], esz, &rp.feat[j], &rp.feat_valid[j]));
+        }
+        rp.out = dout;
+        rp.out_valid = dval;
+        ARENA_GUARD(c);
         ProfScope prof(c);
         if (dtype == B200OLS_F64) rowdot_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(rp);
         else rowdot_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(rp);
+        c->launches++;
+        CU(cudaGetLastError());
     }
-    c->launches++;
-    CU(cudaGetLastError());
     if (memspace == B200OLS_HOST) {
         CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * n_rows, cudaMemcpyDeviceToHost, c->stream));
         if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(n_rows), cudaMemcpyDeviceToHost, c->stream));
@@ -1348,11 +1631,11 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     int32_t *d_cg = reinterpret_cast<int32_t *>(take(nc * 4 + 8));
     int64_t *d_gco = reinterpret_cast<int64_t *>(take((G + 1) * 8));
     p.series_info = reinterpret_cast<int64_t *>(take(static_cast<size_t>(G) * 24 + 8));
-    p.summaries = reinterpret_cast<double *>(take(p.kind == MOVING_RLS ? nc * MOVING_REC * 8 + 8 : 8));
+    p.summaries = reinterpret_cast<double *>(take(p.kind == MOVING_RLS ? nc * moving_rec(p.F) * 8 + 8 : 8));
     int64_t *d_s0 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
     int64_t *d_s1 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
     int64_t *d_gso = reinterpret_cast<int64_t *>(take((G + 1) * 8));
-    p.sup = reinterpret_cast<double *>(take(ns * MOVING_REC * 8 + 8));
+    p.sup = reinterpret_cast<double *>(take(ns * moving_rec(p.F) * 8 + 8));
     p.n_super = static_cast<int64_t>(ns);
     {   // chunk-interleaved column copies (filled by chunk_transpose_kernel)
         p.chunk_len = L;

@@ -66,7 +66,7 @@ struct MovingParams {
     int state_only;                   // stop after the scan (b200ols_recursive_least_squares_state)
 };
 
-constexpr int MOVING_REC = MOVING_MAX_K * MOVING_MAX_K + MOVING_MAX_K + 1;
+__host__ __device__ constexpr int moving_rec(int K) { return K * K + K + 1; }  // doubles per chunk record: A, b, D
 
 template <typename T, int K>
 struct DevSrc {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(128) rls_summary_kernel(const MovingParams p) 
     RlsCfg cfg{p.lambda, p.p0};
     RlsSummary<K> s;
     rls_summarise<K>(src, cfg, p.chunk_r0[c], p.chunk_r1[c], s);
-    double *rec = p.summaries + c * MOVING_REC;
+    double *rec = p.summaries + c * moving_rec(K);
 #pragma unroll
     for (int i = 0; i < K; ++i) {
 #pragma unroll
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int
         }
         double Dall = 1.0;
         for (int64_t sc = group_sup_off[wid]; sc < group_sup_off[wid + 1]; ++sc) {
-            double *rec = sup + sc * MOVING_REC;
+            double *rec = sup + sc * moving_rec(K);
             const double D = rec[NE];
             Dall *= D;
 #pragma unroll
@@ -330,14 +330,14 @@ __global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
         const int e = lane + 32 * t;
-        carry[t] = (phase == 2 && e < NE) ? sup[wid * MOVING_REC + e] : 0.0;  // phase 0 starts from the zero map offset
+        carry[t] = (phase == 2 && e < NE) ? sup[wid * moving_rec(K) + e] : 0.0;  // phase 0 starts from the zero map offset
     }
     for (int64_t cb = c0; cb < c1; cb += SCAN_PF) {
         double add[SCAN_PF][NT], Dv[SCAN_PF];
 #pragma unroll
         for (int u = 0; u < SCAN_PF; ++u) {
             const int64_t c = (cb + u < c1) ? cb + u : c1 - 1;
-            const double *rec = p.summaries + c * MOVING_REC;
+            const double *rec = p.summaries + c * moving_rec(K);
             Dv[u] = rec[NE];
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int
 #pragma unroll
         for (int u = 0; u < SCAN_PF; ++u) {
             if (cb + u < c1) {
-                double *rec = p.summaries + (cb + u) * MOVING_REC;
+                double *rec = p.summaries + (cb + u) * moving_rec(K);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const int e = lane + 32 * t;
@@ -363,9 +363,9 @@ __global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             const int e = lane + 32 * t;
-            if (e < NE) sup[wid * MOVING_REC + e] = carry[t];
+            if (e < NE) sup[wid * moving_rec(K) + e] = carry[t];
         }
-        if (lane == 0) sup[wid * MOVING_REC + NE] = Dtot;
+        if (lane == 0) sup[wid * moving_rec(K) + NE] = Dtot;
     }
 }
 
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(128) rls_main_kernel(const MovingParams p) {
     RlsCfg cfg{p.lambda, p.p0};
     NormalState<K> in;
     if (!first) {
-        const double *rec = p.summaries + c * MOVING_REC;
+        const double *rec = p.summaries + c * moving_rec(K);
 #pragma unroll
         for (int i = 0; i < K; ++i) {
 #pragma unroll
@@ -404,8 +404,8 @@ inline int64_t moving_chunk_len(int64_t n_rows, int sm_count, int kind, int64_t 
 inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int F) {
     const size_t max_chunks = static_cast<size_t>(n_rows / 64 + n_groups + 2);
     const size_t max_super = max_chunks / 256 + static_cast<size_t>(n_groups) + 2;
-    return max_chunks * (MOVING_REC * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (3 * 8 + 8 + 8) +
-           max_super * (MOVING_REC * 8 + 16) + 16384 +
+    return max_chunks * (moving_rec(F) * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (3 * 8 + 8 + 8) +
+           max_super * (moving_rec(F) * 8 + 16) + 16384 +
            // chunk-interleaved column copies: (F + 3) columns x padded rows (every series pads < one chunk)
            static_cast<size_t>(F + 3) * (static_cast<size_t>(n_rows) * 2 + static_cast<size_t>(n_groups + 1) * 64 + 4096) * 8;
 }
@@ -462,7 +462,15 @@ static cudaError_t launch_moving_k(cudaStream_t s, MovingParams &p, const int64_
         case 5: return launch_moving_t<T, 5>(s, p, gco, launches);
         case 6: return launch_moving_t<T, 6>(s, p, gco, launches);
         case 7: return launch_moving_t<T, 7>(s, p, gco, launches);
-        default: return launch_moving_t<T, 8>(s, p, gco, launches);
+        case 8: return launch_moving_t<T, 8>(s, p, gco, launches);
+        case 9: return launch_moving_t<T, 9>(s, p, gco, launches);
+        case 10: return launch_moving_t<T, 10>(s, p, gco, launches);
+        case 11: return launch_moving_t<T, 11>(s, p, gco, launches);
+        case 12: return launch_moving_t<T, 12>(s, p, gco, launches);
+        case 13: return launch_moving_t<T, 13>(s, p, gco, launches);
+        case 14: return launch_moving_t<T, 14>(s, p, gco, launches);
+        case 15: return launch_moving_t<T, 15>(s, p, gco, launches);
+        default: return launch_moving_t<T, 16>(s, p, gco, launches);
     }
 }
 

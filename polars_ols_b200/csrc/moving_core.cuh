@@ -22,7 +22,7 @@
 
 namespace b200 {
 
-constexpr int MOVING_MAX_K = 8;
+constexpr int MOVING_MAX_K = 16;  // K <= 8 lives in registers; 9..16 spills to local memory (slower, same results)
 enum : int { MOVING_RLS = 0, MOVING_ROLLING = 1 };
 
 // ---- register-resident small matrices --------------------------------------------------------------

@@ -25,6 +25,12 @@ struct QrParams {
     double *ws;                       // [(F+1)][n_rows] column-major workspace
     double *beta;
     int32_t *flags;
+    // more than 64 coefficients (big.cuh): the fit matrix is already in `ws` and the per-group scratch that
+    // otherwise lives in registers / local memory comes from global memory
+    int materialised;
+    int *perm_ws;                     // [n_groups][F] or nullptr (F <= 64)
+    double *z_ws;                     // [n_groups][F] or nullptr
+    int all_flagged;                  // 1: every non-empty, non-wide group (no Cholesky pre-pass decided)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -39,13 +45,13 @@ __global__ void __launch_bounds__(128) qr_fallback_kernel(const QrParams p) {
     const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (g >= p.n_groups) return;
     const int fl = p.flags[g];
-    if (!(fl & (FLAG_ILLCOND | FLAG_LU_FALLBACK)) || (fl & (FLAG_EMPTY | FLAG_WIDE))) return;  // wide groups -> SVD kernel
+    if ((!p.all_flagged && !(fl & (FLAG_ILLCOND | FLAG_LU_FALLBACK))) || (fl & (FLAG_EMPTY | FLAG_WIDE))) return;  // wide groups -> SVD kernel
     const int F = p.F, kd = p.kd;
     const int64_t r0 = p.group_off[g], r1 = p.group_off[g + 1], n = r1 - r0;
     const int64_t N = p.n_rows;
     double *b = p.ws + static_cast<size_t>(F) * N;
     // 1) materialise the fit matrix (sqrt-weight scaling, intercept, dropped rows -> zero rows)
-    for (int64_t r = r0 + lane; r < r1; r += 32) {
+    for (int64_t r = r0 + lane; r < r1 && !p.materialised; r += 32) {
         T s = T(1);
         if (p.w) {
             const T wv = static_cast<const T *>(p.w)[r];
@@ -59,8 +65,11 @@ __global__ void __launch_bounds__(128) qr_fallback_kernel(const QrParams p) {
         b[r] = keep ? static_cast<double>(static_cast<T>(static_cast<const T *>(p.cols[kd])[r] * s)) : 0.0;
     }
     __syncwarp();
-    int perm[64];
-    for (int c = 0; c < F; ++c) perm[c] = c;
+    int perm_local[64];
+    int *perm = p.perm_ws ? p.perm_ws + g * F : perm_local;  // global scratch: written by lane 0 only
+    const bool perm_shared = p.perm_ws != nullptr;
+    for (int c = 0; c < F; ++c)
+        if (!perm_shared || lane == 0) perm[c] = c;
     const int steps = (n < F) ? static_cast<int>(n) : F;
     for (int j = 0; j < steps; ++j) {
         // pivot: remaining column with the largest norm over rows j..n-1
@@ -76,7 +85,7 @@ __global__ void __launch_bounds__(128) qr_fallback_kernel(const QrParams p) {
         if (piv != j) {
             double *a = p.ws + static_cast<size_t>(j) * N + r0, *c2 = p.ws + static_cast<size_t>(piv) * N + r0;
             for (int64_t i = lane; i < n; i += 32) { const double t = a[i]; a[i] = c2[i]; c2[i] = t; }
-            const int t = perm[j]; perm[j] = perm[piv]; perm[piv] = t;
+            if (!perm_shared || lane == 0) { const int t = perm[j]; perm[j] = perm[piv]; perm[piv] = t; }
             __syncwarp();
         }
         double *aj = p.ws + static_cast<size_t>(j) * N + r0;
@@ -106,7 +115,8 @@ __global__ void __launch_bounds__(128) qr_fallback_kernel(const QrParams p) {
     }
     // back substitution on the F x F upper triangle (rows 0..F-1 of the workspace), R z = (Q^T b)[:F]
     if (lane == 0) {
-        double z[64];
+        double z_local[64];
+        double *z = p.z_ws ? p.z_ws + g * F : z_local;
         for (int i = F - 1; i >= 0; --i) {
             double s = (i < n) ? b[r0 + i] : 0.0;
             for (int c = i + 1; c < F; ++c) s -= ((i < n) ? p.ws[static_cast<size_t>(c) * N + r0 + i] : 0.0) * z[c];

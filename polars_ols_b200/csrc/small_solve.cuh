@@ -12,7 +12,7 @@
 
 namespace b200 {
 
-enum : int { ROUTE_CHOL = 0, ROUTE_LU = 1, ROUTE_CD = 2, ROUTE_CD_ACTIVE = 3 };
+enum : int { ROUTE_CHOL = 0, ROUTE_LU = 1, ROUTE_CD = 2, ROUTE_CD_ACTIVE = 3, ROUTE_FLAGS_ONLY = 4 /* big.cuh: an SVD kernel solves */ };
 
 struct SolveParams {
     int F;

@@ -25,12 +25,14 @@ namespace b200 {
 
 struct SvdParams {
     QrParams q;          // columns, weights, mask, group offsets, workspace, beta, flags
-    double *vws;         // [n_groups][F * F] right singular vectors (row-major V[i][c])
+    double *vws;         // [n_groups][F * F] right singular vectors, column c contiguous: V[i][c] at vws[c * F + i]
     int all_groups;      // 1: solve_method = "svd" (every non-empty group); 0: only groups flagged FLAG_WIDE
     int ridge;           // 1: ridge-SVD formula
     double alpha;
     double rcond;        // NaN = None
     int max_sweeps;
+    int materialised;    // big.cuh: q.ws already holds the fit matrix
+    int skip_rows_le_F;  // big.cuh: groups with n <= F rows are solved by big_svd_wide_kernel
 };
 
 template <typename T>
@@ -46,9 +48,10 @@ __global__ void __launch_bounds__(128) svd_solve_kernel(const SvdParams sp) {
     const int64_t r0 = p.group_off[g], r1 = p.group_off[g + 1], n = r1 - r0;
     const int64_t N = p.n_rows;
     double *b = p.ws + static_cast<size_t>(F) * N;
+    if (sp.skip_rows_le_F && n <= F) return;
     double *V = sp.vws + static_cast<size_t>(g) * F * F;
     // 1) materialise the fit matrix (sqrt-weight scaling, intercept, dropped rows -> zero rows) and V = I
-    for (int64_t r = r0 + lane; r < r1; r += 32) {
+    for (int64_t r = r0 + lane; r < r1 && !sp.materialised; r += 32) {
         T s = T(1);
         if (p.w) {
             const T wv = static_cast<const T *>(p.w)[r];
@@ -90,9 +93,9 @@ __global__ void __launch_bounds__(128) svd_solve_kernel(const SvdParams sp) {
                     aq[i] = sn * x + cs * y;
                 }
                 for (int i = lane; i < F; i += 32) {
-                    const double x = V[i * F + pi], y = V[i * F + qi];
-                    V[i * F + pi] = cs * x - sn * y;
-                    V[i * F + qi] = sn * x + cs * y;
+                    const double x = V[pi * F + i], y = V[qi * F + i];
+                    V[pi * F + i] = cs * x - sn * y;
+                    V[qi * F + i] = sn * x + cs * y;
                 }
                 __syncwarp();
             }
@@ -111,7 +114,8 @@ __global__ void __launch_bounds__(128) svd_solve_kernel(const SvdParams sp) {
     const int64_t mx = (n > F) ? n : F;
     const double cutoff = sp.ridge ? ((sp.rcond == sp.rcond) ? sp.rcond : DBL_EPSILON * static_cast<double>(mx)) * smax
                                    : DBL_EPSILON * smax;
-    double beta_l[2] = {0.0, 0.0};  // lane holds coefficients lane and lane + 32
+    double *beta = p.beta + g * F;  // lane accumulates coefficients lane, lane + 32, ...
+    for (int i = lane; i < F; i += 32) beta[i] = 0.0;
     for (int c = 0; c < F; ++c) {
         const double *a = p.ws + static_cast<size_t>(c) * N + r0;
         double s2 = 0.0, ay = 0.0;
@@ -125,11 +129,8 @@ __global__ void __launch_bounds__(128) svd_solve_kernel(const SvdParams sp) {
         double coef;
         if (sp.ridge) coef = (sv < cutoff) ? 0.0 : ay / (s2 + sp.alpha);   // V d U^T y with d = s / (s^2 + alpha)
         else coef = (sv <= cutoff) ? 0.0 : ay / s2;                         // V S^+ U^T y
-        if (lane < F) beta_l[0] = fma(V[lane * F + c], coef, beta_l[0]);
-        if (lane + 32 < F) beta_l[1] = fma(V[(lane + 32) * F + c], coef, beta_l[1]);
+        for (int i = lane; i < F; i += 32) beta[i] = fma(V[c * F + i], coef, beta[i]);
     }
-    if (lane < F) p.beta[g * F + lane] = beta_l[0];
-    if (lane + 32 < F) p.beta[g * F + lane + 32] = beta_l[1];
     if (lane == 0) p.flags[g] = (fl & ~(FLAG_ILLCOND | FLAG_LU_FALLBACK | FLAG_QR)) | FLAG_SVD;
 }
 

@@ -472,3 +472,92 @@ def test_rls_state_abi_against_information_form():
             np.testing.assert_allclose(st[g, :k * k].reshape(k, k), A, rtol=1e-10, atol=1e-12)
             np.testing.assert_allclose(st[g, k * k:k * k + k], bb, rtol=1e-10, atol=1e-12)
             np.testing.assert_allclose(st[g, -1], D, rtol=1e-10, atol=1e-300)
+
+
+def test_moving_models_with_ten_features_and_weights():                    # tests/test_ols.py:969-996 shape (k = 10)
+    d = _make_data(20_000, 10, n_groups=5, add_missing=True, seed=21)
+    rng = np.random.default_rng(0)
+    d["weights"] = rng.uniform(0.1, 10.0, size=20_000)
+    names = _xs(d)
+    kw = dict(window_size=100, min_periods=12, null_policy="drop")
+    r = Frame(d).select(col("y").least_squares.rolling_ols(*names, sample_weights="weights", mode="coefficients", **kw).over("group"))
+    ref = S.over(S.rolling_least_squares, d["group"], d["y"], *_oracle_cols(d, names), sample_weights=d["weights"],
+                 mode="coefficients", kwargs=S.RollingKwargs(**kw))
+    got, refv = r["coefficients"].to_numpy(), _ref(ref)
+    assert (np.isnan(got) == np.isnan(refv)).all()
+    ok = ~np.isnan(refv) & (np.abs(refv) < 1e6)
+    assert np.allclose(got[ok], refv[ok], rtol=1e-6, atol=1e-7)
+    assert abs(np.nanmean(got[-1]) - 1.0) < 0.05
+    r = Frame(d).select(col("y").least_squares.rls(*names, half_life=500.0, mode="predictions").over("group"))["y"]
+    ref = S.over(S.recursive_least_squares, d["group"], d["y"], *_oracle_cols(d, names), kwargs=S.RLSKwargs(half_life=500.0))
+    got, refv = r.to_numpy(), _ref(ref)
+    assert (np.isnan(got) == np.isnan(refv)).all()
+    m = ~np.isnan(refv)
+    m[:2000] = False                                   # diffuse-prior rows are conditioned like p0 |x|^2
+    _close(got[m], refv[m], rtol=1e-6, atol=1e-8)
+
+
+# ----------------------------------------------------------------------------------- more than 64 coefficients (big.cuh)
+@pytest.mark.parametrize("n_features", (100, 1000))
+def test_fit_wide_hundreds_of_features(n_features):                        # tests/test_ols.py:272-313
+    d = _make_data(10, n_features, scale=1.0e-4, seed=n_features)
+    names, F = _xs(d), Frame(d)
+    xs = _oracle_cols(d, names)
+    r = F.select(col("y").least_squares.ols(*names, mode="coefficients"))["coefficients"]
+    _close(r.to_numpy()[0], _ref(S.least_squares(d["y"], *xs, mode="coefficients")), rtol=1e-6, atol=1e-9)   # dgelsd min-norm
+    assert pls.get_engine(0).last_group_flags(1)[0] & 32
+    F["coefficients"] = np.broadcast_to(r.to_numpy()[0], (10, n_features)).copy()
+    p = F.select(col("coefficients").least_squares.predict(*names))["predictions"].to_numpy()
+    assert np.corrcoef(p, d["y"])[0, 1] == pytest.approx(1.0, rel=1e-5, abs=1e-5)
+    r = F.select(col("y").least_squares.ridge(*names, mode="coefficients", alpha=1.0e-5))["coefficients"]
+    ref = _ref(S.least_squares(d["y"], *xs, mode="coefficients", kwargs=S.OLSKwargs(alpha=1.0e-5, l1_ratio=0.0)))
+    _close(r.to_numpy()[0], ref, rtol=1e-6, atol=1e-9)
+    kw = dict(alpha=1.0e-6, tol=1.0e-8, max_iter=3_000)
+    r = F.select(col("y").least_squares.lasso(*names, mode="coefficients", **kw))["coefficients"]
+    ref = _ref(S.least_squares(d["y"], *xs, mode="coefficients", kwargs=S.OLSKwargs(l1_ratio=1.0, **kw)))
+    _close(r.to_numpy()[0], ref, rtol=1e-6, atol=1e-9)
+    p = F.select(col("y").least_squares.lasso(*names, **kw))["y"].to_numpy()
+    assert np.corrcoef(p, d["y"])[0, 1] == pytest.approx(1.0, rel=1e-5, abs=1e-5)
+
+
+@pytest.mark.parametrize("model,kw", [("ols", {}), ("ols", {"solve_method": "qr"}), ("ols", {"solve_method": "svd"}),
+                                      ("ridge", {"alpha": 0.1}), ("ridge", {"alpha": 0.1, "solve_method": "lu"}),
+                                      ("lasso", {"alpha": 1e-3}), ("elastic_net", {"alpha": 1e-3, "l1_ratio": 0.3, "solve_method": "cd_active_set"})])
+def test_hundred_features_over_groups(model, kw):                          # k = 100 > 64, tall groups, nulls + weights
+    d = _make_data(3000, 100, n_groups=3, sparsity=0.5, add_missing=False, seed=31)
+    rng = np.random.default_rng(1)
+    d["weights"] = rng.uniform(0.2, 5.0, size=3000)
+    d["x7"] = (d["x7"], rng.random(3000) >= 0.05)
+    d["y"] = (d["y"], rng.random(3000) >= 0.05)
+    names, F = _xs(d), Frame(d)
+    xs = _oracle_cols(d, names)
+    okw = dict(kw)
+    if model == "ridge":
+        okw["l1_ratio"] = 0.0
+    if model == "lasso":
+        okw["l1_ratio"] = 1.0
+    for mode in ("coefficients", "residuals"):
+        e = getattr(col("y").least_squares, model)(*names, sample_weights="weights", add_intercept=True, mode=mode,
+                                                   null_policy="drop", **kw).over("group")
+        r = F.select(e)["coefficients" if mode == "coefficients" else "y"]
+        if mode == "coefficients":
+            keys, c, m = S.over(S.least_squares, d["group"], d["y"], *xs, sample_weights=d["weights"], add_intercept=True,
+                                per_group=True, mode=mode, kwargs=S.OLSKwargs(null_policy="drop", **okw))
+            _close(r.to_numpy(), c, rtol=1e-6, atol=1e-8)
+        else:
+            ref = S.over(S.least_squares, d["group"], d["y"], *xs, sample_weights=d["weights"], add_intercept=True, mode=mode,
+                         kwargs=S.OLSKwargs(null_policy="drop", **okw))
+            _close(r.to_numpy(), _ref(ref), rtol=1e-6, atol=1e-8)
+
+
+def test_hundred_features_f32_device_frame():
+    import torch
+    d = _make_data(4000, 80, seed=33, dtype=np.float32)
+    names = _xs(d)
+    dev = {k: torch.as_tensor(v, device="cuda") for k, v in d.items()}
+    r = Frame(dev).select(col("y").least_squares.ridge(*names, alpha=1e-2, mode="coefficients"))["coefficients"]
+    ref = S.least_squares(d["y"], *_oracle_cols(d, names), mode="coefficients", kwargs=S.OLSKwargs(alpha=1e-2, l1_ratio=0.0))
+    _close(r.to_numpy()[0], _ref(ref), rtol=1e-4, atol=1e-7)
+    p = Frame(dev).select(col("y").least_squares.ridge(*names, alpha=1e-2))["y"]
+    ref = S.least_squares(d["y"], *_oracle_cols(d, names), kwargs=S.OLSKwargs(alpha=1e-2, l1_ratio=0.0))
+    _close(p.to_numpy(), _ref(ref), rtol=1e-4, atol=1e-6)
