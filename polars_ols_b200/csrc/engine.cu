@@ -30,6 +30,7 @@
 #include "small_solve.cuh"
 #include "svd_solve.cuh"
 #include "big.cuh"
+#include "batch_solve.cuh"
 #include "cd_solve.cuh"
 
 using namespace b200;
@@ -80,6 +81,7 @@ struct b200ols_ctx {
     int smem_optin = 0;
     int64_t launches = 0;
     int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
+    long long fuse_min_bytes = -1;  // < 0: default; test hook B200OLS_FUSE_MIN_BYTES (0 = always fuse the solve)
     int variant = 3, unroll = 0;  // Gram kernel variant (b200ols_set_variant); 3 = CTA-cooperative TMA pipeline
     // bump arena in device memory, reset at the start of every call
     char *arena = nullptr;
@@ -243,6 +245,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
         c->own_stream = true;
     }
     if (const char *v = std::getenv("B200OLS_VARIANT")) c->variant = std::atoi(v);  // test hook: force a Gram kernel variant
+    if (const char *v = std::getenv("B200OLS_FUSE_MIN_BYTES")) c->fuse_min_bytes = std::atoll(v);  // test hook: fused-solve threshold
     if (c->variant < 0 || c->variant > 3) c->variant = 3;
     *out = c;
     return 0;
@@ -747,45 +750,56 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     }
     if (c->variant == 3 && KB <= 2) {  // CTA-cooperative warp-specialised TMA pipeline (k <= 16)
         const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
-        // the accumulator ring of a 16-coefficient Gram is 18 KB per entry: keep it shallow, the stages need the room
-        gp.red_depth = KB == 1 ? CTA_RED_DEPTH : 3;
-        const size_t fixed = cta_fixed_smem<T>(KB, F, gp.red_depth);
-        // default tile = the longest segment (whole groups per stage: fewest, largest bulk copies), shrunk until
-        // at least two stages fit
-        int R = c->tile_rows > 0 ? c->tile_rows
+        // Ring of published accumulator buffers (18 KB per entry for a 16-coefficient Gram).  A parity wait may be one
+        // phase behind its barrier or level with it, never ahead, so: without teams (all consumers publish every
+        // segment in order) the ring must be at least CTA_SOLVERS deep; with teams every barrier must be waited on
+        // by the SAME warps in every phase: stages % teams == 0 (a stage always belongs to one team) and
+        // ring % CTA_SOLVERS == 0 (a published buffer always goes to the same solver warp).
+        int R = 0, S = 0;
+        size_t fixed = 0;
+        auto fit = [&](int depth) {
+            fixed = cta_fixed_smem<T>(KB, F, depth);
+            // default tile = the longest segment (whole groups per stage: fewest, largest bulk copies), shrunk until
+            // at least two stages fit
+            R = c->tile_rows > 0 ? c->tile_rows
                                  : static_cast<int>(std::min<int64_t>(std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, 64), 4096));
-        int S = 0;
-        for (;;) {
-            const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(R);
-            S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, (budget - fixed) / sb));
-            if (S >= 2 || R <= 16) break;
-            R -= 8;
-        }
+            for (;;) {
+                const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(R);
+                S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, (budget - fixed) / sb));
+                if (S >= 2 || R <= 16) break;
+                R -= 8;
+            }
+            if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));  // sweep hook: warps_per_cta caps the stages
+        };
+        gp.red_depth = KB == 1 ? CTA_RED_DEPTH : CTA_SOLVERS;
+        fit(gp.red_depth);
         if (S < 2) return fail(B200OLS_ERR_UNSUPPORTED, "Gram tile does not fit in shared memory (%d columns)", NC);
-        if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));  // sweep hook: warps_per_cta caps the stages
-        gp.tile_rows = R;
-        gp.stages = S;
-        // short groups: fewer consumer warps per segment (teams), >= ~16 row octets per warp; needs one tile per segment.
-        // A parity wait may only ever be one phase behind or level with its barrier, never ahead of it, so every
-        // barrier must be waited on by the SAME warps in every phase: stages % teams == 0 (a stage always belongs to
-        // one team) and ring % solvers == 0 (a published buffer always goes to the same solver warp).
+        // short groups: fewer consumer warps per segment (teams), >= ~16 row octets per warp; needs one tile per segment
         gp.team = 0;
         if (gp.max_seg_rows <= R) {
             int team = CTA_CONSUMERS;
             while (team > 1 && gp.max_seg_rows <= 128 * (team / 2)) team >>= 1;
-            if (c->ctas_per_sm > 0) {  // sweep hook: nearest power of two <= 8
+            if (c->ctas_per_sm > 0) {  // sweep hook: largest power of two <= min(8, ctas_per_sm)
                 team = 1;
                 while (team * 2 <= std::min(CTA_CONSUMERS, c->ctas_per_sm)) team *= 2;
             }
-            while (team < CTA_CONSUMERS && S / (CTA_CONSUMERS / team) == 0) team <<= 1;  // fewer teams than stages
             if (team < CTA_CONSUMERS) {
+                const int R0 = R, S0 = S;
                 const int nt = CTA_CONSUMERS / team;
-                S = S / nt * nt;
-                if ((gp.red_depth * nt) % CTA_SOLVERS != 0) gp.red_depth -= gp.red_depth % 2;  // nt = 2: even ring depth
-                gp.stages = S;
-                gp.team = team;
+                const int depth = KB == 1 ? CTA_RED_DEPTH : (nt == 2 ? 2 : 3);  // depth * nt is a multiple of CTA_SOLVERS
+                fit(depth);
+                if (R == R0 && S / nt >= 1) {
+                    S = S / nt * nt;
+                    gp.red_depth = depth;
+                    gp.team = team;
+                } else {  // not enough stages for that many teams: keep the plain ring
+                    fit(gp.red_depth);
+                    (void)S0;
+                }
             }
         }
+        gp.tile_rows = R;
+        gp.stages = S;
         const size_t smem = static_cast<size_t>(S) * NC * gram_col_stride<T>(R) + fixed;
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, gp.nseg));
         ProfScope prof(c);
@@ -1255,7 +1269,12 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     gp.beta = beta;
     gp.flags = flags;
     const bool cd = rt.route == ROUTE_CD || rt.route == ROUTE_CD_ACTIVE;
-    gp.fused = (!pl.split && !cd && F <= 16) ? 1 : 0;
+    // short groups: the four solver warps of a CTA cannot keep up with the stream (a k x k solve is a 3-10 us
+    // dependent chain), so the streaming kernel only writes the Gram records and batch_solve_kernel solves all
+    // groups at full occupancy; long groups keep the solve fused (no record traffic, no second launch)
+    const size_t group_bytes = static_cast<size_t>(st.max_group_rows) * (st.kd + 1 + st.has_w) * st.esz;
+    const size_t fuse_min = c->fuse_min_bytes >= 0 ? static_cast<size_t>(c->fuse_min_bytes) : (F <= 8 ? 28u << 10 : 110u << 10);
+    gp.fused = (!pl.split && !cd && F <= 16 && group_bytes >= fuse_min) ? 1 : 0;
     if (!gp.fused) gp.partial = arena_alloc<double>(c, static_cast<size_t>(pl.nseg) * P);
     // fused gather: only when the streaming kernel's beta is final (no QR / SVD re-solve afterwards)
     const bool peer_direct = peer_mode && gp.fused && !rt.ols_qr_guard && !rt.svd_all && !rt.svd_wide;
@@ -1287,6 +1306,8 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         sp.positive = rt.positive;
         if (cd) {
             CU(launch_cd_solve(c->stream, sp, c->sm_count));
+        } else if (F <= 16) {
+            CU(launch_batch_solve(c->stream, sp));
         } else {
             const unsigned blocks = static_cast<unsigned>((G + 63) / 64);
             small_solve_kernel<<<blocks, 64, 0, c->stream>>>(sp);

@@ -88,7 +88,9 @@ __host__ __device__ inline uint32_t gram_scratch_bytes(int F, int fused) {
 // with warp shuffles; one rsqrt per column replaces the divisions (results agree with the reference's
 // faer LL^T to rounding).  Returns false on a non-positive / NaN pivot (-> LU fallback); mn / mx are the
 // extreme squared pivots.  On success lane i returns beta_i in c.
-template <int FP>
+// WIDTH < 32: a sub-warp of WIDTH lanes per system (batch_solve.cuh), `lane` is the lane inside the sub-warp and
+// every sub-warp runs the whole sequence (no early exit: the shuffles need the full warp).
+template <int FP, int WIDTH = 32>
 __device__ __forceinline__ bool warp_chol_solve(double (&g)[FP], double &c, int F, int lane, double &mn, double &mx) {
     constexpr unsigned FULL = 0xffffffffu;
     bool ok = true;
@@ -99,7 +101,7 @@ __device__ __forceinline__ bool warp_chol_solve(double (&g)[FP], double &c, int 
     for (int j = 0; j < FP; ++j) {
         inv[j] = 1.0;
         if (j < F) {
-            const double d = __shfl_sync(FULL, g[j], j);
+            const double d = __shfl_sync(FULL, g[j], j, WIDTH);
             ok = ok && (d > 0.0);
             mn = fmin(mn, d);
             mx = fmax(mx, d);
@@ -110,18 +112,18 @@ __device__ __forceinline__ bool warp_chol_solve(double (&g)[FP], double &c, int 
 #pragma unroll
             for (int cc = j + 1; cc < FP; ++cc) {
                 if (cc < F) {
-                    const double lcj = __shfl_sync(FULL, lij, cc);
+                    const double lcj = __shfl_sync(FULL, lij, cc, WIDTH);
                     if (lane > j) g[cc] = fma(-lij, lcj, g[cc]);
                     else if (lane == j) g[cc] = lcj;
                 }
             }
         }
     }
-    if (!ok) return false;
+    if (WIDTH == 32 && !ok) return false;
 #pragma unroll
     for (int j = 0; j < FP; ++j) {
         if (j < F) {
-            const double zj = __shfl_sync(FULL, c * inv[j], j);
+            const double zj = __shfl_sync(FULL, c * inv[j], j, WIDTH);
             if (lane == j) c = zj;
             else if (lane > j) c = fma(-g[j], zj, c);
         }
@@ -129,12 +131,12 @@ __device__ __forceinline__ bool warp_chol_solve(double (&g)[FP], double &c, int 
 #pragma unroll
     for (int j = FP - 1; j >= 0; --j) {
         if (j < F) {
-            const double xj = __shfl_sync(FULL, c * inv[j], j);
+            const double xj = __shfl_sync(FULL, c * inv[j], j, WIDTH);
             if (lane == j) c = xj;
             else if (lane < j) c = fma(-g[j], xj, c);
         }
     }
-    return true;
+    return ok;
 }
 
 // Second half of the epilogue: the per-warp scratch holds the symmetric Gram matrix (row stride FP + 1)

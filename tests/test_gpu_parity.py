@@ -243,11 +243,6 @@ def test_elastic_net(k, sparsity, alpha, l1_ratio, method, positive):      # tes
     d = _make_data(6000, k, n_groups=3, sparsity=sparsity, seed=11)
     expr = col("y").least_squares.elastic_net(*_xs(d), alpha=alpha, l1_ratio=l1_ratio, positive=positive,
                                               solve_method=method, mode="coefficients").over("group")
-    if k > 64:
-        with pytest.raises(pls.B200OLSError) as ei:
-            Frame(d).select(expr)
-        assert ei.value.code == -2
-        return
     r = Frame(d).select(expr)["coefficients"]
     keys, c, m = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, _xs(d)), per_group=True, mode="coefficients",
                         kwargs=S.OLSKwargs(alpha=alpha, l1_ratio=l1_ratio, positive=positive, solve_method=method))
@@ -561,3 +556,31 @@ def test_hundred_features_f32_device_frame():
     p = Frame(dev).select(col("y").least_squares.ridge(*names, alpha=1e-2))["y"]
     ref = S.least_squares(d["y"], *_oracle_cols(d, names), kwargs=S.OLSKwargs(alpha=1e-2, l1_ratio=0.0))
     _close(p.to_numpy(), _ref(ref), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("k,n_rows,n_groups", [(3, 40_000, 400), (8, 60_000, 97), (13, 50_000, 300), (16, 30_000, 7)])
+@pytest.mark.parametrize("solve_method", [None, "lu"])
+def test_fused_and_batched_solve_agree(k, n_rows, n_groups, solve_method, monkeypatch):
+    """the streaming kernel's fused solve and batch_solve_kernel are the same ladder: identical to rounding,
+    for every team size, with ragged groups (some empty, one long enough to be split)"""
+    d = _make_data(n_rows, k, n_groups=n_groups, seed=k)
+    d["group"][: n_rows // 3] = 1                      # one long group
+    d["group"][d["group"] == 5] = 6                    # an empty key range
+    names = _xs(d)
+    keys, offsets, row_index, _ = pls.least_squares._group_plan([d["group"]])
+    b = lambda: pls.Batch(pls.as_col(d["y"]), [pls.as_col(d[n]) for n in names], offsets=offsets, row_index=row_index)  # noqa: E731
+    kw = OLSKwargs(alpha=0.05, l1_ratio=0.0, solve_method=solve_method).to_c()
+    from polars_ols_b200 import _lib as L
+    res = {}
+    for fuse in ("0", str(1 << 40)):
+        monkeypatch.setenv("B200OLS_FUSE_MIN_BYTES", fuse)
+        eng = pls.Engine(0)
+        for team in (0, 1, 2, 4):
+            eng.set_tuning(0, 0, team)
+            res[(fuse, team)] = eng.least_squares(b(), kw, L.COEFFICIENTS)[0].copy()
+        eng.close()
+    _, c, _ = S.over(S.least_squares, d["group"], d["y"], *_oracle_cols(d, names), per_group=True, mode="coefficients",
+                     kwargs=S.OLSKwargs(alpha=0.05, l1_ratio=0.0, solve_method=solve_method))
+    for key, v in res.items():
+        _close(v, c, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(v, res[("0", 0)], rtol=1e-10, atol=1e-12)
