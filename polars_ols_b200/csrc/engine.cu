@@ -19,6 +19,7 @@
 
 #include "../../include/b200ols.h"
 #include "gram_cta.cuh"
+#include "gram_multi.cuh"
 #include "gram_wide.cuh"
 #include "gram_ldg.cuh"
 #include "gram_simt.cuh"
@@ -81,6 +82,7 @@ struct b200ols_ctx {
     int smem_optin = 0;
     int64_t launches = 0;
     int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
+    bool multi_enabled = true;      // test hook B200OLS_MULTI=0: never use gram_multi_kernel
     long long fuse_min_bytes = -1;  // < 0: default; test hook B200OLS_FUSE_MIN_BYTES (0 = always fuse the solve)
     int variant = 3, unroll = 0;  // Gram kernel variant (b200ols_set_variant); 3 = CTA-cooperative TMA pipeline
     // bump arena in device memory, reset at the start of every call
@@ -105,6 +107,11 @@ struct b200ols_ctx {
     int plan_F = -1;
     int64_t *plan_dev = nullptr;
     size_t plan_cap = 0;
+    // tile table of gram_multi_kernel (runs of whole groups) for the cached grouping
+    int64_t *tile_dev = nullptr;
+    size_t tile_cap = 0;
+    int64_t tile_count = 0, tile_rows_built = 0;
+    bool tile_valid = false;
     // fused multi-GPU gather (b200ols_set_peer_gather)
     int n_peers = 0;
     double *peer_coef[8] = {};
@@ -245,6 +252,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
         c->own_stream = true;
     }
     if (const char *v = std::getenv("B200OLS_VARIANT")) c->variant = std::atoi(v);  // test hook: force a Gram kernel variant
+    if (const char *v = std::getenv("B200OLS_MULTI")) c->multi_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_FUSE_MIN_BYTES")) c->fuse_min_bytes = std::atoll(v);  // test hook: fused-solve threshold
     if (c->variant < 0 || c->variant > 3) c->variant = 3;
     *out = c;
@@ -260,6 +268,7 @@ extern "C" void b200ols_destroy(b200ols_ctx *c) {
     for (void *p : c->retired) cudaFree(p);
     if (c->arena) cudaFree(c->arena);
     if (c->plan_dev) cudaFree(c->plan_dev);
+    if (c->tile_dev) cudaFree(c->tile_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int h = 0; h < 2; ++h)
         if (c->pinned_ev[h]) cudaEventDestroy(c->pinned_ev[h]);
@@ -661,6 +670,7 @@ static int build_plan(b200ols_ctx *c, const Staged &st, int64_t seg_max, Plan *p
             c->plan_cap = bytes + 4096;
         }
         c->plan_offsets.clear();  // invalid until the copy below is enqueued
+        c->tile_valid = false;
         TRY(pinned_reserve(c, c->pinned_off + bytes + 256));
         char *h = c->pinned + c->pinned_off;
         std::memcpy(h, st.offsets.data(), bytes);
@@ -748,6 +758,64 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         c->launches++;
         return 0;
     }
+    if (c->variant == 3 && KB <= 2 && !gp.fused && !gp.seg_group && c->multi_enabled &&
+        c->plan_offsets.size() == static_cast<size_t>(gp.nseg) + 1) {
+        // short groups: tiles of whole groups, one consumer warp per group (gram_multi.cuh)
+        const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
+        const size_t row_bytes = static_cast<size_t>(NC) * sizeof(T);
+        int64_t R = std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, static_cast<int64_t>((28u << 10) / row_bytes) / 8 * 8);
+        R = std::max<int64_t>(R, 64);
+        if (c->tile_rows > 0) R = std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, c->tile_rows);  // sweep hook
+        const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(static_cast<int>(R));
+        int S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, budget / sb));
+        if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));
+        if (S >= 3 && R <= 8192) {
+            if (!c->tile_valid || c->tile_rows_built != R) {
+                // greedy runs of consecutive groups whose rows fit one tile (A-aligned start included)
+                const std::vector<int64_t> &off = c->plan_offsets;
+                const int64_t G = gp.nseg, A = 16 / static_cast<int64_t>(sizeof(T));
+                std::vector<int64_t> tg;
+                tg.reserve(static_cast<size_t>(G / 2 + 2));
+                tg.push_back(0);
+                int64_t start = 0;
+                for (int64_t g = 0; g < G; ++g) {
+                    const int64_t a_al = off[start] & ~(A - 1);
+                    if (off[g + 1] - a_al > R && g > start) {  // group g does not fit any more: close the tile before it
+                        tg.push_back(g);
+                        start = g;
+                    }
+                }
+                tg.push_back(G);
+                const size_t bytes = sizeof(int64_t) * tg.size();
+                if (bytes > c->tile_cap) {
+                    if (c->tile_dev) c->retired.push_back(c->tile_dev);
+                    c->tile_dev = nullptr;
+                    void *qd = nullptr;
+                    CU(cudaMalloc(&qd, bytes + 4096));
+                    c->tile_dev = static_cast<int64_t *>(qd);
+                    c->tile_cap = bytes + 4096;
+                }
+                TRY(pinned_reserve(c, c->pinned_off + bytes + 256));
+                char *h = c->pinned + c->pinned_off;
+                c->pinned_off += round_up(bytes, 256);
+                std::memcpy(h, tg.data(), bytes);
+                CU(cudaMemcpyAsync(c->tile_dev, h, bytes, cudaMemcpyHostToDevice, c->stream));
+                c->tile_count = static_cast<int64_t>(tg.size()) - 1;
+                c->tile_rows_built = R;
+                c->tile_valid = true;
+            }
+            gp.tile_rows = static_cast<int>(R);
+            gp.stages = S;
+            MultiPlan mp{c->tile_dev, c->tile_count};
+            const size_t smem = static_cast<size_t>(S) * sb;
+            const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, c->tile_count));
+            ProfScope prof(c);
+            CU(sizeof(T) == 8 ? gram_multi_launch_f64(KB, gp, mp, static_cast<unsigned>(grid), smem, c->stream)
+                              : gram_multi_launch_f32(KB, gp, mp, static_cast<unsigned>(grid), smem, c->stream));
+            c->launches++;
+            return 0;
+        }
+    }
     if (c->variant == 3 && KB <= 2) {  // CTA-cooperative warp-specialised TMA pipeline (k <= 16)
         const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
         // Ring of published accumulator buffers (18 KB per entry for a 16-coefficient Gram).  A parity wait may be one
@@ -771,7 +839,7 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
             }
             if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));  // sweep hook: warps_per_cta caps the stages
         };
-        gp.red_depth = KB == 1 ? CTA_RED_DEPTH : CTA_SOLVERS;
+        gp.red_depth = cta_plain_depth(KB);
         fit(gp.red_depth);
         if (S < 2) return fail(B200OLS_ERR_UNSUPPORTED, "Gram tile does not fit in shared memory (%d columns)", NC);
         // short groups: fewer consumer warps per segment (teams), >= ~16 row octets per warp; needs one tile per segment
@@ -1273,7 +1341,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     // dependent chain), so the streaming kernel only writes the Gram records and batch_solve_kernel solves all
     // groups at full occupancy; long groups keep the solve fused (no record traffic, no second launch)
     const size_t group_bytes = static_cast<size_t>(st.max_group_rows) * (st.kd + 1 + st.has_w) * st.esz;
-    const size_t fuse_min = c->fuse_min_bytes >= 0 ? static_cast<size_t>(c->fuse_min_bytes) : (F <= 8 ? 28u << 10 : 110u << 10);
+    const size_t fuse_min = c->fuse_min_bytes >= 0 ? static_cast<size_t>(c->fuse_min_bytes) : (F <= 8 ? 64u << 10 : 256u << 10);
     gp.fused = (!pl.split && !cd && F <= 16 && group_bytes >= fuse_min) ? 1 : 0;
     if (!gp.fused) gp.partial = arena_alloc<double>(c, static_cast<size_t>(pl.nseg) * P);
     // fused gather: only when the streaming kernel's beta is final (no QR / SVD re-solve afterwards)

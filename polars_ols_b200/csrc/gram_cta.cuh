@@ -31,10 +31,6 @@ constexpr int CTA_SOLVERS = 4;   // the k x k solve is a long dependent chain: s
 constexpr int CTA_RED_DEPTH = 6; // max ring depth of published partial-fragment buffers (GramParams::red_depth; consumers may run this far ahead)
 constexpr int CTA_THREADS = (CTA_CONSUMERS + CTA_SOLVERS + 1) * 32;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int KB>
 __host__ __device__ constexpr int cta_red_doubles() { return KB * (KB + 1) + KB + 1; }  // acc frags, cy, nfit
 
@@ -44,7 +40,12 @@ __host__ __device__ inline size_t cta_fixed_smem(int KB, int F, int red_depth) {
     return red + CTA_SOLVERS * gram_scratch_bytes<T>(F, 1) + 128;
 }
 
-template <typename T, int KB>
+// ring depth without teams: every consumer publishes every segment in order, so a solver that got segment i knows
+// segments < i are published; the ring must then be at least CTA_SOLVERS deep (see engine.cu: launch_gram)
+__host__ __device__ constexpr int cta_plain_depth(int KB) { return KB == 1 ? CTA_RED_DEPTH : CTA_SOLVERS; }
+
+// TEAMS = false compiles the plain pipeline (all consumers on every segment) with constant team / ring sizes
+template <typename T, int KB, bool TEAMS>
 __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramParams p) {
     using Vec = typename V2<T>::type;
     constexpr int NPAIR = KB * (KB + 1) / 2;
@@ -62,9 +63,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     const int ycol = kd, wcol = kd + 1, mcol = kd + 1 + (p.has_w ? 1 : 0);
     const int NC = kd + 1 + (p.has_w ? 1 : 0) + (p.has_mask ? 1 : 0);
     const int R = p.tile_rows, S = p.stages;
-    const int TEAM = (p.team > 0 && p.team < W) ? p.team : W;  // consumer warps per segment
+    const int TEAM = TEAMS ? ((p.team > 0 && p.team < W) ? p.team : W) : W;  // consumer warps per segment
     const int NT = W / TEAM;                                    // teams; segment i (CTA-local) -> team i % NT
-    const int DEPTH = (p.red_depth > 0 && p.red_depth < CTA_RED_DEPTH) ? p.red_depth : CTA_RED_DEPTH;
+    const int DEPTH = TEAMS ? ((p.red_depth > 0 && p.red_depth < CTA_RED_DEPTH) ? p.red_depth : CTA_RED_DEPTH) : cta_plain_depth(KB);
     const int RD = DEPTH * NT;                                  // ring of published buffers (TEAM slots each)
     const uint32_t stride = gram_col_stride<T>(R);
     const uint32_t stage_bytes = static_cast<uint32_t>(NC) * stride;
@@ -324,9 +325,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     }
 }
 
-template <typename T, int KB>
+template <typename T, int KB, bool TEAMS>
 cudaError_t gram_cta_launch_t(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
-    auto kern = gram_cta_kernel<T, KB>;
+    auto kern = gram_cta_kernel<T, KB, TEAMS>;
     static size_t attr_set[64] = {};  // per device: the opt-in shared-memory size already granted to this kernel
     int dev = 0;
     cudaGetDevice(&dev);

@@ -21,10 +21,11 @@ cases = [("f32", 16, 256, 100_000, True), ("f64", 8, 64, 160_000, False), ("f64"
 if len(sys.argv) > 1:
     cases = [cases[int(i)] for i in sys.argv[1].split(",")]
 engines = {}
-for fuse in ("0", str(1 << 40)):
+for name, fuse, multi in (("fused", "0", "1"), ("batch", str(1 << 40), "0"), ("multi", str(1 << 40), "1")):
     os.environ["B200OLS_FUSE_MIN_BYTES"] = fuse
-    engines[fuse] = pls.Engine(0, 1)
-del os.environ["B200OLS_FUSE_MIN_BYTES"]
+    os.environ["B200OLS_MULTI"] = multi
+    engines[name] = pls.Engine(0, 1)
+del os.environ["B200OLS_FUSE_MIN_BYTES"], os.environ["B200OLS_MULTI"]
 engines["default"] = pls.Engine(0, 1)
 for dt, k, n, G, weighted in cases:
     tdt = torch.float32 if dt == "f32" else torch.float64
@@ -42,7 +43,7 @@ for dt, k, n, G, weighted in cases:
     for fuse, eng in engines.items():
         coef = torch.empty((G, k), dtype=torch.float64, device=dev)
         call = eng.prepare_least_squares(b, kw, L.COEFFICIENTS, coef)
-        for team in ((0,) if fuse == "default" else (0, 1, 2, 4, 8)):
+        for team in ((0,) if fuse in ("default", "multi") else (0, 2)):
             eng.set_tuning(0, 0, team)
             for _ in range(3):
                 call()
@@ -61,7 +62,7 @@ for dt, k, n, G, weighted in cases:
             if ref is None:
                 ref = cc
             err = float(np.abs(cc - ref).max())
-            key = f"{dt} k={k} n={n} G={G} solve={'fused' if fuse == '0' else ('batch' if fuse != 'default' else 'default')} team={team}"
+            key = f"{dt} k={k} n={n} G={G} solve={fuse} team={team}"
             out[key] = {"ms_per_call": round(ms_call, 4), "gram_ms": round(ms, 4), "GBps_call": round(gb / ms_call * 1e3, 1),
                         "max_abs_diff": err}
             print(key, out[key], flush=True)
