@@ -36,15 +36,16 @@ def timed(fn, reps):
     fn(); fn()
     torch.cuda.synchronize()
     eng.set_profiling(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
         out = fn()
-    e1.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
     k = eng.profile_drain()
     eng.set_profiling(False)
-    return out, e0.elapsed_time(e1) / reps, (float(np.mean(k)) if len(k) else None)
+    ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]))  # median: one allocator hiccup must not count
+    return out, ms, (float(np.median(k)) if len(k) else None)
 
 
 def report(name, ms, kms, alg_bytes, units, unit_name, err, extra=None):
