@@ -44,7 +44,7 @@ enum { B200OLS_F64 = 0, B200OLS_F32 = 1 };
 
 enum { B200OLS_HOST = 0, B200OLS_DEVICE = 1 };
 
-/* OutputMode, polars_ols/least_squares.py:57 ("statistics" is out of scope) */
+/* OutputMode, polars_ols/least_squares.py:57 ("statistics" has its own entry point, b200ols_least_squares_statistics) */
 enum { B200OLS_PREDICTIONS = 0, B200OLS_RESIDUALS = 1, B200OLS_COEFFICIENTS = 2 };
 
 /* NullPolicy, src/least_squares.rs:68-91 */
@@ -251,6 +251,34 @@ B200OLS_API int b200ols_set_peer_gather(b200ols_ctx *ctx, int n_peers, void *con
 B200OLS_API int b200ols_predict(b200ols_ctx *ctx, int64_t n_rows, int32_t n_coef, int32_t dtype, int32_t memspace,
                                 const b200ols_column *coefficients, const b200ols_column *features,
                                 int32_t add_intercept, int32_t null_policy, b200ols_output *out);
+
+/* "next" row: replaces _polars_plugin_least_squares_statistics (src/expressions.rs:469-509,
+ * src/statistics.rs:15-156), one struct row per group (`returns_scalar`).  Coefficients follow the ordinary dispatch of
+ * kwargs; r2 / mae / mse are those of the fit rows (scaled by sqrt(w) under WLS); standard errors, t and p values come
+ * from (X^T X + alpha I)^-1 by Cholesky (failure -> NaN, as the reference) with df = n - p (alpha = 0) or
+ * n - trace(inverse).  kwargs->alpha must not be None (the reference unwraps it).  A group with df <= 0 fails the call
+ * with the reference's assertion message.  Arrays live in the frame's memspace; no nulls (NaN stays NaN).  The
+ * `feature_names` list of the reference's struct is the caller's input names (host side). */
+typedef struct b200ols_statistics_output {
+    double *r2, *mae, *mse;                                           /* [n_groups] */
+    double *coefficients, *standard_errors, *t_values, *p_values;     /* [n_groups * n_coef] row-major */
+} b200ols_statistics_output;
+B200OLS_API int b200ols_least_squares_statistics(b200ols_ctx *ctx, const b200ols_frame *frame,
+                                                 const b200ols_ols_kwargs *kwargs, const b200ols_statistics_output *out);
+
+/* "next" row: replaces _polars_plugin_multi_target_least_squares (src/expressions.rs:521-591;
+ * solve_multi_target src/least_squares.rs:243-260).  The reference's first input is a struct Series of n_targets
+ * Float fields: here `targets[n_targets]` (same dtype / memspace as the frame; frame->target is ignored).  One
+ * decomposition of the group's features serves every target: OLS minimum-norm SVD solution (alpha None / 0) or ridge-SVD
+ * (alpha > 0, rcond honoured).  Nulls are ZERO-filled under every policy (fill_zero = true, :549-550,569), the row mask
+ * ANDs all targets (drop_y_zero_x) or all targets and features (drop, drop_zero).  mode PREDICTIONS | RESIDUALS only
+ * (polars_ols/least_squares.py:314-317); kwargs must be unconstrained OLS / ridge with solve_method None | "svd".
+ * out->values[n_targets * n_rows] target-major (one contiguous Float64 child array per struct field), validity bytes
+ * likewise: NaN predictions are nulls (convert_array_to_struct_series, :137-139), `drop` masks invalid rows,
+ * residuals are null where the target is. */
+B200OLS_API int b200ols_multi_target_least_squares(b200ols_ctx *ctx, const b200ols_frame *frame, int32_t n_targets,
+                                                   const b200ols_column *targets, const b200ols_ols_kwargs *kwargs,
+                                                   int mode, b200ols_output *out);
 
 /* Per-group diagnostics of the last static call on ctx (host copy): bit 0 = Cholesky failed and the
  * LU fallback ran (src/least_squares.rs:299-316), bit 1 = group had no rows after null filtering

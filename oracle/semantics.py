@@ -182,7 +182,8 @@ def solve_ridge_svd(y, x, alpha, rcond):
     cutoff = (rcond if rcond is not None else np.finfo(np.float64).eps * max(x.shape)) * s.max()
     s = np.where(s < cutoff, 0.0, s)
     d = s / (s * s + alpha)
-    return vt.T @ (d * (u.T @ y))
+    uty = u.T @ y
+    return vt.T @ ((d[:, None] * uty) if uty.ndim == 2 else (d * uty))      # multi-target: d scales the rows of U^T Y
 
 
 def solve_ridge(y, x, alpha, solve_method, rcond) -> np.ndarray:
@@ -374,6 +375,152 @@ def rolling_least_squares(target, *features, sample_weights=None, add_intercept=
     if mode == "coefficients":
         return plugin_rolling_least_squares_coefficients([t_fit, *f_fit], kw)
     return _finish_predictions(plugin_rolling_least_squares([t_fit, *f_fit], kw), target, sqrt_w, mode, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY §8f "next" rows: mode="statistics" (src/statistics.rs, src/expressions.rs:448-509) and
+# multi_target_least_squares (src/expressions.rs:511-591, src/least_squares.rs:243-260)
+# ---------------------------------------------------------------------------------------------
+def students_t_two_sided_p(t: np.ndarray, df: float) -> np.ndarray:
+    """t_value_to_p_value (src/statistics.rs:44-48) over statrs 0.17.1 StudentsT::cdf (third-party, not under
+    /root/reference; its published formula): k = t, h = df / (df + k^2), ib = 0.5 * I_h(df/2, 1/2),
+    cdf(x) = ib if x <= 0 else 1 - ib;  p = 2 * (1 - cdf(|t|)) — the 1 - (1 - ib) cancellation is kept."""
+    from scipy.special import betainc
+    t = np.abs(np.asarray(t, dtype=np.float64))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        h = df / (df + t * t)
+        ib = 0.5 * betainc(df / 2.0, 0.5, h)
+        cdf = np.where(t <= 0.0, ib, 1.0 - ib)
+        p = 2.0 * (1.0 - cdf)
+    return np.where(np.isnan(t), np.nan, p)
+
+
+def compute_residual_metrics(targets: np.ndarray, predicted: np.ndarray) -> dict:
+    """compute_residual_metrics (src/statistics.rs:15-36)."""
+    n = len(targets)
+    mean = targets.mean() if n else 0.0
+    err = targets - predicted
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sse, sae, sst = float((err ** 2).sum()), float(np.abs(err).sum()), float(((targets - mean) ** 2).sum())
+        return {"mse": np.float64(sse) / n, "mae": np.float64(sae) / n, "r2": 1.0 - np.float64(sse) / np.float64(sst)}
+
+
+def compute_feature_metrics(features: np.ndarray, targets: np.ndarray, lam: float) -> dict:
+    """compute_feature_metrics (src/statistics.rs:77-156): explicit Cholesky inverse of X^T X + lambda I."""
+    n, p = features.shape
+    xtx_reg = features.T @ features + lam * np.eye(p)
+    nans = np.full(p, np.nan)
+    try:
+        if not np.isfinite(xtx_reg).all():
+            raise np.linalg.LinAlgError
+        L = np.linalg.cholesky(xtx_reg)                                   # faer cholesky(Lower), Err -> NaNs (:101-111)
+    except np.linalg.LinAlgError:
+        return {"standard_errors": nans, "t_values": nans.copy(), "p_values": nans.copy()}
+    Li = np.linalg.inv(L)
+    xtx_inv = Li.T @ Li
+    coef = xtx_inv @ (features.T @ targets)                               # :116
+    resid = targets - features @ coef
+    rss = float((resid ** 2).sum())
+    df = n - np.trace(xtx_inv) if lam > 0.0 else float(n - p)             # :125-129
+    assert df > 0.0, "Degrees of freedom <= 0. Cannot compute standard errors."
+    sigma2 = rss / df
+    se = np.sqrt(sigma2 * np.abs(np.diag(xtx_inv)))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        tv = coef / se
+    return {"standard_errors": se, "t_values": tv, "p_values": students_t_two_sided_p(tv, df)}
+
+
+def plugin_least_squares_statistics(inputs: List[Col], kw: OLSKwargs) -> dict:
+    """least_squares_statistics (src/expressions.rs:469-509) for ONE group."""
+    pol = kw.null_policy
+    is_valid = compute_is_valid_mask(inputs, pol)
+    y, x = convert_to_ndarray(inputs, pol, is_valid)
+    lam = kw.alpha                                                        # kwargs.alpha.unwrap() (:475)
+    assert lam is not None
+    coef = get_least_squares_coefficients(y, x, kw)
+    out = compute_residual_metrics(y, x @ coef)
+    out.update(compute_feature_metrics(x, y, float(lam)))
+    out["coefficients"] = coef
+    return out
+
+
+def least_squares_statistics(target, *features, sample_weights=None, add_intercept=False,
+                             kwargs: Optional[OLSKwargs] = None) -> dict:
+    """compute_least_squares(mode="statistics") (polars_ols/least_squares.py:213-224) on a single group."""
+    kw = kwargs or OLSKwargs(alpha=0.0)
+    target = as_col(target)
+    feats = [as_col(f) for f in features]
+    w = None if sample_weights is None else as_col(sample_weights)
+    t_fit, f_fit, _ = pre_process(target, feats, w, add_intercept)
+    return plugin_least_squares_statistics([t_fit, *f_fit], kw)
+
+
+def solve_multi_target(y: np.ndarray, x: np.ndarray, alpha, rcond) -> np.ndarray:
+    """solve_multi_target (src/least_squares.rs:243-260): always SVD; ridge-SVD when alpha > 0 (rcond honoured),
+    else LAPACK dgelsd (rcond ignored)."""
+    if x.size == 0:
+        return np.zeros((x.shape[1], y.shape[1]))
+    alpha = 0.0 if alpha is None else alpha
+    if alpha > 0.0:
+        return solve_ridge_svd(y, x, alpha, rcond)
+    return np.linalg.lstsq(x, y, rcond=None)[0]
+
+
+def plugin_multi_target_least_squares(targets: List[Col], features: List[Col], kw: OLSKwargs):
+    """multi_target_least_squares (src/expressions.rs:521-591) for ONE group -> (pred [n, m], mask [n] or None).
+    Every array is built with fill_zero = true (:549-550, :569): nulls become 0 even under 'ignore'."""
+    pol = kw.null_policy
+    m = len(targets)
+    series = list(targets) + list(features)
+    if pol in ("drop", "drop_zero", "drop_window"):                       # compute_is_valid_mask(.., Some(m)) (:201-228)
+        is_valid = np.ones(len(series[0][0]), dtype=bool)
+        for c in series:
+            is_valid &= _is_valid(c)
+    elif pol == "drop_y_zero_x":
+        is_valid = np.ones(len(series[0][0]), dtype=bool)
+        for c in targets:
+            is_valid &= _is_valid(c)
+    else:
+        is_valid = None
+    sel = slice(None) if is_valid is None else is_valid                    # handle_nulls (:257-296) then fill_zero
+    x_fit = np.ascontiguousarray(np.stack([_to_f64(c, 0.0)[sel] for c in features], axis=1))
+    y_fit = np.ascontiguousarray(np.stack([_to_f64(c, 0.0)[sel] for c in targets], axis=1))
+    coef = solve_multi_target(y_fit, x_fit, kw.alpha, kw.rcond)           # [k, m]
+    if pol in ("ignore", "zero"):
+        return x_fit @ coef, None
+    pred = features_zero_filled(features) @ coef
+    return pred, (is_valid if pol == "drop" else None)
+
+
+def multi_target_least_squares(targets: Sequence, *features, sample_weights=None, add_intercept=False,
+                               mode="predictions", kwargs: Optional[OLSKwargs] = None):
+    """compute_multi_target_least_squares (polars_ols/least_squares.py:282-329) on a single group.
+    Returns (values [n, m], validity [n, m]): NaN -> null (convert_array_to_struct_series :137-139)."""
+    kw = kwargs or OLSKwargs()
+    assert not kw.positive and (kw.l1_ratio is None or kw.l1_ratio == 0.0)
+    assert kw.solve_method in ("svd", None)
+    if mode == "coefficients":
+        raise NotImplementedError("Only mode={'predictions', 'residuals'} is currently supported.")
+    tg = [as_col(t) for t in targets]
+    feats = [as_col(f) for f in features]
+    w = None if sample_weights is None else as_col(sample_weights)
+    if add_intercept:
+        feats = feats + [(np.ones(len(tg[0][0]), dtype=tg[0][0].dtype), None)]
+    sqrt_w = None
+    t_fit, f_fit = tg, feats
+    if w is not None:
+        _, f_fit, sqrt_w = pre_process(tg[0], feats, w, False)
+        t_fit = [_mul(t, sqrt_w) for t in tg]
+    pred, row_mask = plugin_multi_target_least_squares(t_fit, f_fit, kw)
+    vals, masks = [], []
+    for j, t in enumerate(tg):
+        pm = ~np.isnan(pred[:, j])
+        if row_mask is not None:
+            pm &= row_mask
+        v, mk = _finish_predictions((pred[:, j], pm), t, sqrt_w, mode, False)
+        vals.append(v)
+        masks.append(np.ones(len(v), dtype=bool) if mk is None else mk)
+    return np.stack(vals, axis=1), np.stack(masks, axis=1)
 
 
 def predict(coefficients: Sequence, features: Sequence, null_policy: str = "zero", add_intercept: bool = False) -> Col:

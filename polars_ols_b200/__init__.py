@@ -22,6 +22,7 @@ from .least_squares import (  # noqa: F401
     SolveMethod,
     col,
     compute_least_squares,
+    compute_multi_target_least_squares,
     compute_recursive_least_squares,
     compute_rolling_least_squares,
     predict,

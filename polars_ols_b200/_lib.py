@@ -30,7 +30,7 @@ EXPORTS = [
     "b200ols_recursive_least_squares_coefficients", "b200ols_rolling_least_squares",
     "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags", "b200ols_predict", "b200ols_device_alloc", "b200ols_device_free", "b200ols_ipc_export",
     "b200ols_ipc_open", "b200ols_ipc_close", "b200ols_copy_to_host", "b200ols_set_peer_gather",
-    "b200ols_recursive_least_squares_state",
+    "b200ols_recursive_least_squares_state", "b200ols_least_squares_statistics", "b200ols_multi_target_least_squares",
 ]
 
 
@@ -71,6 +71,11 @@ class RollingKwargs(C.Structure):
 
 class Output(C.Structure):
     _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p)]
+
+
+class StatisticsOutput(C.Structure):
+    _fields_ = [("r2", C.c_void_p), ("mae", C.c_void_p), ("mse", C.c_void_p), ("coefficients", C.c_void_p),
+                ("standard_errors", C.c_void_p), ("t_values", C.c_void_p), ("p_values", C.c_void_p)]
 
 
 class B200OLSError(RuntimeError):
@@ -128,6 +133,9 @@ def load() -> C.CDLL:
     L.b200ols_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
     L.b200ols_set_peer_gather.argtypes = [vp, i32, C.POINTER(vp), i64, i64]
     L.b200ols_predict.argtypes = [vp, i64, i32, i32, i32, C.POINTER(Column), C.POINTER(Column), i32, i32, C.POINTER(Output)]
+    L.b200ols_least_squares_statistics.argtypes = [vp, C.POINTER(Frame), C.POINTER(OLSKwargs), C.POINTER(StatisticsOutput)]
+    L.b200ols_multi_target_least_squares.argtypes = [vp, C.POINTER(Frame), i32, C.POINTER(Column), C.POINTER(OLSKwargs), i32,
+                                                     C.POINTER(Output)]
     _lib = L
     return L
 

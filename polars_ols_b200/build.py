@@ -1,45 +1,80 @@
-"""Builds polars_ols_b200/libb200ols.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds polars_ols_b200/libb200ols.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+Every .cu is compiled to its own object (in parallel) and re-compiled only when it or a header it includes
+(recursively) changed; objects live in polars_ols_b200/build/ (git-ignored)."""
 from __future__ import annotations
 
 import os
+import re
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
+OBJ = HERE / "build"
 SO = HERE / "libb200ols.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-cudart", "static", "-t", "0",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
     # FP contraction stays on in device code: explicit fma() is used where order matters
 ]
+LINK = ["--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+_INC = re.compile(r'^\s*#include\s+"([^"]+)"', re.M)
 
 
 def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
+def _deps(path: Path, seen=None):
+    seen = seen if seen is not None else set()
+    if path in seen or not path.exists():
+        return seen
+    seen.add(path)
+    for inc in _INC.findall(path.read_text()):
+        _deps((path.parent / inc).resolve(), seen)
+    return seen
+
+
 def deps():
     return list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "b200ols.h"]
+
+
+def _compile(src: Path, verbose: bool):
+    obj = OBJ / (src.stem + ".o")
+    newest = max(p.stat().st_mtime for p in _deps(src.resolve()))
+    newest = max(newest, Path(__file__).stat().st_mtime)
+    if obj.exists() and obj.stat().st_mtime >= newest:
+        return obj, ""
+    cmd = [NVCC, *FLAGS, "-c", "-o", str(obj), str(src)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src.name}:\n{r.stdout}{r.stderr}")
+    return obj, r.stderr
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     newest = max(p.stat().st_mtime for p in deps())
     if not force and SO.exists() and SO.stat().st_mtime >= newest:
         return SO
-    tmp = SO.with_suffix(f".{os.getpid()}.tmp.so")
-    cmd = [NVCC, *FLAGS, "-o", str(tmp), *[str(s) for s in sources()]]
+    OBJ.mkdir(exist_ok=True)
+    if force:
+        for o in OBJ.glob("*.o"):
+            o.unlink()
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        res = list(ex.map(lambda s: _compile(s, verbose), sources()))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        sys.stderr.write("".join(e for _, e in res))
+    tmp = SO.with_suffix(f".{os.getpid()}.tmp.so")
+    r = subprocess.run([NVCC, *LINK, "-o", str(tmp), *[str(o) for o, _ in res]], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libb200ols.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libb200ols.so")
     os.replace(tmp, SO)
     return SO
 

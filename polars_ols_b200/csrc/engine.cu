@@ -33,6 +33,8 @@
 #include "big.cuh"
 #include "batch_solve.cuh"
 #include "cd_solve.cuh"
+#include "stats.cuh"
+#include "multi_target.cuh"
 
 using namespace b200;
 
@@ -438,6 +440,8 @@ struct Staged {
     int64_t max_group_rows = 0;
     int64_t wide_group = -1;               // first group with 0 < n <= k (needs the min-norm SVD path), or -1
     bool prepped = false;
+    const void *raw[GRAM_MAX_COLS] = {};       // device copies of the caller's columns, ORIGINAL row order (features, target, w)
+    const uint8_t *raw_bm[GRAM_MAX_COLS] = {};  // their validity bitmaps (device) or nullptr
 };
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -491,7 +495,7 @@ static void launch_prep(b200ols_ctx *c, const PrepParams &pp) {
 
 // Brings every column of the frame onto the device (arena), applies gather + null policy when needed.
 // Arena must already be reserved.  `moving`: rls / rolling semantics for the null policy.
-static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool moving, Staged *st) {
+static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool moving, Staged *st, int extra_targets = 0) {
     const int kd = f->n_features;
     const size_t esz = f->dtype == B200OLS_F64 ? 8 : 4;
     const int64_t n = f->n_rows;
@@ -574,6 +578,10 @@ static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool 
             dev_rowidx = d;
         }
     }
+    for (int cidx = 0; cidx < ncol; ++cidx) {
+        st->raw[cidx] = dev_vals[cidx];
+        st->raw_bm[cidx] = dev_bm[cidx];
+    }
     st->row_index = dev_rowidx;
     st->y_validity = dev_bm[kd];
     st->y_raw = dev_vals[kd];
@@ -605,6 +613,7 @@ static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool 
     pp.n_rows = n;
     pp.n_rows_pad = n_pad;
     pp.row_index = dev_rowidx;
+    pp.n_targets = extra_targets + 1;
     for (int cidx = 0; cidx < ncol; ++cidx) {
         pp.in[cidx] = dev_vals[cidx];
         pp.validity[cidx] = dev_bm[cidx];
@@ -1271,10 +1280,18 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
     return 0;
 }
 
-static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
+static int run_statistics(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, const Staged &st, const Plan &pl,
+                          const double *partial, const double *beta, const b200ols_statistics_output *so);
+
+// `stats` != nullptr: mode = "statistics" (b200ols_least_squares_statistics) — the coefficients are dispatched as
+// for mode = coefficients, the Gram records are always written (no fused solve) and run_statistics() finishes
+static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out,
+                           const b200ols_statistics_output *stats = nullptr) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
-    const bool peer_mode = c->n_peers > 0 && mode == B200OLS_COEFFICIENTS && f && f->memspace == B200OLS_DEVICE;
-    if (!kw || !out || (!out->values && !peer_mode)) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    const bool peer_mode = !stats && c->n_peers > 0 && mode == B200OLS_COEFFICIENTS && f && f->memspace == B200OLS_DEVICE;
+    b200ols_output no_out = {nullptr, nullptr};
+    if (stats) out = &no_out;
+    if (!kw || !out || (!out->values && !peer_mode && !stats)) return fail(B200OLS_ERR_INVALID, "NULL argument");
     TRY(validate_frame(f));
     if (peer_mode && c->peer_group_base + f->n_groups > c->peer_total_groups)
         return fail(B200OLS_ERR_INVALID, "peer gather: shard [%lld, %lld) exceeds total_groups %lld", (long long)c->peer_group_base,
@@ -1287,6 +1304,8 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     TRY(free_retired(c));
 
     const int F = f->n_features + (f->add_intercept ? 1 : 0);
+    if (stats && F > 64)
+        return fail(B200OLS_ERR_UNSUPPORTED, "mode=statistics with more than 64 coefficients (%d) is not implemented on the device", F);
     if (F > 64) return run_static_big(c, f, kw, rt, mode, out, peer_mode);
     const int64_t G = f->n_groups, N = f->n_rows;
     const size_t P = static_cast<size_t>(F) * F + F + 1;
@@ -1299,6 +1318,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * 9 + 4096;                         // out + validity
     if (rt.ols_qr_guard || rt.svd_all || rt.svd_wide)
         bytes += static_cast<size_t>(F + 1) * static_cast<size_t>(N) * 8 + static_cast<size_t>(G) * F * F * 8 + 8192;  // QR / SVD workspace
+    if (stats) bytes += static_cast<size_t>(G) * (2 * static_cast<size_t>(F) * F + 6 * F + STATS_GS + 3) * 8 + 8 * static_cast<size_t>(G + 1) + 8192;
     bytes += 1 << 20;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
@@ -1344,7 +1364,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     // groups at full occupancy; long groups keep the solve fused (no record traffic, no second launch)
     const size_t group_bytes = static_cast<size_t>(st.max_group_rows) * (st.kd + 1 + st.has_w) * st.esz;
     const size_t fuse_min = c->fuse_min_bytes >= 0 ? static_cast<size_t>(c->fuse_min_bytes) : (F <= 8 ? 64u << 10 : 256u << 10);
-    gp.fused = (!pl.split && !cd && F <= 16 && group_bytes >= fuse_min) ? 1 : 0;
+    gp.fused = (!pl.split && !cd && F <= 16 && group_bytes >= fuse_min && !stats) ? 1 : 0;
     if (!gp.fused) gp.partial = arena_alloc<double>(c, static_cast<size_t>(pl.nseg) * P);
     // fused gather: only when the streaming kernel's beta is final (no QR / SVD re-solve afterwards)
     const bool peer_direct = peer_mode && gp.fused && !rt.ols_qr_guard && !rt.svd_all && !rt.svd_wide;
@@ -1464,6 +1484,8 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         c->launches++;
     }
 
+    if (stats) return run_statistics(c, f, kw, st, pl, gp.partial, beta, stats);
+
     // outputs
     if (peer_mode && !peer_direct) {
         PeerScatterParams ps;
@@ -1554,6 +1576,299 @@ extern "C" int b200ols_least_squares(b200ols_ctx *c, const b200ols_frame *f, con
 extern "C" int b200ols_least_squares_coefficients(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw,
                                                   b200ols_output *out) {
     return run_static(c, f, kw, B200OLS_COEFFICIENTS, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mode = "statistics" (src/expressions.rs:469-509, src/statistics.rs): stats.cuh after the Gram records
+// ------------------------------------------------------------------------------------------------
+static int device_group_offsets(b200ols_ctx *c, const Staged &st, const Plan &pl, const int64_t **out) {
+    if (!pl.split) {
+        *out = pl.seg_off;
+        return 0;
+    }
+    const size_t ob = sizeof(int64_t) * (st.n_groups + 1);  // the split plan only holds segment offsets
+    TRY(pinned_reserve(c, c->pinned_off + ob + 256));
+    char *h = c->pinned + c->pinned_off;
+    c->pinned_off += round_up(ob, 256);
+    std::memcpy(h, st.offsets.data(), ob);
+    int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(st.n_groups) + 1);
+    CU(cudaMemcpyAsync(d, h, ob, cudaMemcpyHostToDevice, c->stream));
+    *out = d;
+    return 0;
+}
+
+static int run_statistics(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, const Staged &st, const Plan &pl,
+                          const double *partial, const double *beta, const b200ols_statistics_output *so) {
+    if (!so->r2 || !so->mae || !so->mse || !so->coefficients || !so->standard_errors || !so->t_values || !so->p_values)
+        return fail(B200OLS_ERR_INVALID, "statistics output: NULL array");
+    // `let lambda = kwargs.alpha.unwrap()` (src/expressions.rs:475): alpha = None panics in the reference
+    if (kw->alpha != kw->alpha) return fail(B200OLS_ERR_INVALID, "mode=statistics requires alpha (called `Option::unwrap()` on a `None` value)");
+    const int F = st.F;
+    const int64_t G = st.n_groups;
+    const size_t GF = static_cast<size_t>(G) * F;
+    StatsParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    for (int j = 0; j < st.kd; ++j) sp.cols[j] = st.feat[j];
+    sp.cols[st.kd] = st.y;
+    sp.w = st.w;
+    sp.mask = st.mask;
+    sp.kd = st.kd;
+    sp.intercept = st.intercept;
+    sp.F = F;
+    sp.w_is_sqrt = st.w_is_sqrt;
+    sp.n_groups = G;
+    TRY(device_group_offsets(c, st, pl, &sp.group_off));
+    sp.partial = partial;
+    sp.group_seg_off = pl.group_seg_off;
+    sp.alpha = kw->alpha;
+    sp.beta = beta;
+    sp.work = arena_alloc<double>(c, static_cast<size_t>(G) * (2 * static_cast<size_t>(F) * F + F));
+    sp.beta2 = arena_alloc<double>(c, GF);
+    sp.inv_diag = arena_alloc<double>(c, GF);
+    sp.gstat = arena_alloc<double>(c, static_cast<size_t>(G) * STATS_GS);
+    const bool host = f->memspace == B200OLS_HOST;
+    // host frames: results are produced in one arena block [r2 | mae | mse | se | t | p] and copied back
+    double *blk = host ? arena_alloc<double>(c, 3 * static_cast<size_t>(G) + 3 * GF) : nullptr;
+    sp.r2 = host ? blk : so->r2;
+    sp.mae = host ? blk + G : so->mae;
+    sp.mse = host ? blk + 2 * G : so->mse;
+    sp.se = host ? blk + 3 * G : so->standard_errors;
+    sp.tv = host ? blk + 3 * G + GF : so->t_values;
+    sp.pv = host ? blk + 3 * G + 2 * GF : so->p_values;
+    sp.bad_df = arena_alloc<int32_t>(c, 4);
+    ARENA_GUARD(c);
+    CU(cudaMemsetAsync(sp.bad_df, 0, sizeof(int32_t), c->stream));
+    stats_inverse_kernel<<<static_cast<unsigned>((G + 63) / 64), 64, 0, c->stream>>>(sp);
+    const unsigned rb = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(G, static_cast<int64_t>(c->sm_count) * 8)));
+    if (f->dtype == B200OLS_F64) stats_resid_kernel<double><<<rb, 256, 0, c->stream>>>(sp);
+    else stats_resid_kernel<float><<<rb, 256, 0, c->stream>>>(sp);
+    stats_final_kernel<<<static_cast<unsigned>((GF + 127) / 128), 128, 0, c->stream>>>(sp);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    int32_t bad = 0;
+    if (host) {
+        CU(cudaMemcpyAsync(so->r2, sp.r2, sizeof(double) * G, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->mae, sp.mae, sizeof(double) * G, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->mse, sp.mse, sizeof(double) * G, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->standard_errors, sp.se, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->t_values, sp.tv, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->p_values, sp.pv, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->coefficients, beta, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CU(cudaMemcpyAsync(so->coefficients, beta, sizeof(double) * GF, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(&bad, sp.bad_df, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // src/statistics.rs:131-134 asserts per call; one batched call carries every group, so any failing group fails it
+    if (bad > 0) return fail(B200OLS_ERR_INVALID, "Degrees of freedom <= 0. Cannot compute standard errors. (%d group(s))", bad);
+    return 0;
+}
+
+extern "C" int b200ols_least_squares_statistics(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw,
+                                                const b200ols_statistics_output *out) {
+    if (!out) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    const int rc = run_static_impl(c, f, kw, B200OLS_COEFFICIENTS, nullptr, out);
+    if (c && c->pinned) pinned_end(c);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi_target_least_squares (src/expressions.rs:521-591): multi_target.cuh
+// ------------------------------------------------------------------------------------------------
+static int run_multi_target_impl(b200ols_ctx *c, const b200ols_frame *f0, int32_t m, const b200ols_column *targets,
+                                 const b200ols_ols_kwargs *kw, int mode, b200ols_output *out) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (!f0 || !kw || !out || !out->values || !targets) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    if (m < 1) return fail(B200OLS_ERR_INVALID, "the first series in a multi-target regression must be a struct (n_targets >= 1)");
+    // compute_multi_target_least_squares (polars_ols/least_squares.py:303-318)
+    if (kw->positive || !(kw->l1_ratio != kw->l1_ratio || kw->l1_ratio == 0.0))
+        return fail(B200OLS_ERR_INVALID, "Multi-target regression is only supported for unconstrained OLS & Ridge problems.");
+    if (kw->solve_method != B200OLS_SOLVE_NONE && kw->solve_method != B200OLS_SOLVE_SVD)
+        return fail(B200OLS_ERR_INVALID, "only solve_method='svd' is supported for multi-target regressions");
+    if (mode != B200OLS_PREDICTIONS && mode != B200OLS_RESIDUALS)
+        return fail(B200OLS_ERR_INVALID, "Only mode={'predictions', 'residuals'} is currently supported.");
+    const double alpha = (kw->alpha == kw->alpha) ? kw->alpha : 0.0;
+    const bool ridge = alpha > 0.0;  // src/least_squares.rs:254-259
+    const int kd = f0->n_features, icpt = f0->add_intercept ? 1 : 0;
+    const int F = kd + icpt, kdx = kd + m - 1, FX = kdx + icpt;
+    if (F < 1) return fail(B200OLS_ERR_INVALID, "must pass at least 2 series");
+    if (FX > 64 || kdx + 3 > GRAM_MAX_COLS)
+        return fail(B200OLS_ERR_UNSUPPORTED, "multi-target: features + targets (%d) above 64 is not implemented on the device", FX);
+    // the extended frame: targets 0..m-2 ride along as feature columns, target m-1 is the frame's target
+    std::vector<b200ols_column> xcols(static_cast<size_t>(kdx));
+    for (int j = 0; j < kd; ++j) {
+        if (!f0->features) return fail(B200OLS_ERR_INVALID, "features is NULL");
+        xcols[j] = f0->features[j];
+    }
+    for (int t = 0; t < m - 1; ++t) xcols[kd + t] = targets[t];
+    b200ols_frame fx = *f0;
+    fx.n_features = kdx;
+    fx.features = xcols.data();
+    fx.target = targets[m - 1];
+    const b200ols_frame *f = &fx;
+    TRY(validate_frame(f));
+    CU(cudaSetDevice(c->device));
+    TRY(free_retired(c));
+    // every array of the reference is built with fill_zero = true (src/expressions.rs:549-550,569): 'ignore' fills 0 too
+    const int policy = kw->null_policy == B200OLS_NULL_IGNORE ? B200OLS_NULL_ZERO : kw->null_policy;
+
+    const int64_t G = f->n_groups, N = f->n_rows;
+    const size_t PX = static_cast<size_t>(FX) * FX + FX + 1;
+    const int64_t seg_max = choose_seg_max(c, G, N);
+    size_t bytes = stage_bytes_bound(f) + plan_bytes_bound(f, seg_max);
+    const size_t nseg_bound = static_cast<size_t>(G) + static_cast<size_t>(N / std::max<int64_t>(seg_max / 2, 1)) + 2;
+    bytes += nseg_bound * PX * 8 + static_cast<size_t>(G) * (2 * static_cast<size_t>(F) * F + F + static_cast<size_t>(m) * F) * 8;
+    bytes += static_cast<size_t>(G) * 4 + 8 * static_cast<size_t>(G + 1) + 8192;
+    bytes += static_cast<size_t>(F + m) * static_cast<size_t>(N) * 8 + 8192;  // SVD workspace
+    if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(m) * static_cast<size_t>(N) * 9 + 8192;
+    bytes += 1 << 20;
+    TRY(arena_reserve(c, bytes));
+    c->arena_off = 0;
+    TRY(pinned_begin(c));
+
+    Staged st;
+    TRY(stage_frame(c, f, policy, false, &st, m - 1));
+    Plan pl;
+    TRY(build_plan(c, st, seg_max, &pl));
+
+    double *beta = arena_alloc<double>(c, static_cast<size_t>(G) * m * F);
+    int32_t *flags = arena_alloc<int32_t>(c, static_cast<size_t>(G));
+    c->last_flags = flags;
+    c->last_flags_n = G;
+
+    GramParams gp;
+    std::memset(&gp, 0, sizeof(gp));
+    for (int j = 0; j < st.kd; ++j) gp.cols[j] = st.feat[j];
+    gp.cols[st.kd] = st.y;
+    int nc = st.kd + 1;
+    if (st.has_w) gp.cols[nc++] = st.w;
+    if (st.mask) gp.cols[nc++] = st.mask;
+    gp.kd = st.kd;
+    gp.intercept = st.intercept;
+    gp.F = FX;
+    gp.has_w = st.has_w;
+    gp.w_is_sqrt = st.w_is_sqrt;
+    gp.has_mask = st.mask ? 1 : 0;
+    gp.n_rows_pad = st.n_pad;
+    gp.nseg = pl.nseg;
+    gp.max_seg_rows = pl.split ? std::min<int64_t>(seg_max, st.max_group_rows) : st.max_group_rows;
+    gp.seg_off = pl.seg_off;
+    gp.seg_group = pl.seg_group;
+    gp.illcond_ratio = ILLCOND_RATIO;
+    gp.beta = beta;  // unused: the solve is never fused here
+    gp.flags = flags;
+    gp.fused = 0;
+    gp.partial = arena_alloc<double>(c, static_cast<size_t>(pl.nseg) * PX);
+    ARENA_GUARD(c);
+    if (f->dtype == B200OLS_F64) TRY(launch_gram<double>(c, gp)); else TRY(launch_gram<float>(c, gp));
+
+    MultiSolveParams ms;
+    std::memset(&ms, 0, sizeof(ms));
+    ms.kd = kd;
+    ms.intercept = icpt;
+    ms.F = F;
+    ms.m = m;
+    ms.FX = FX;
+    ms.n_groups = G;
+    ms.partial = gp.partial;
+    ms.group_seg_off = pl.group_seg_off;
+    ms.alpha = ridge ? alpha : 0.0;
+    ms.illcond_ratio = ILLCOND_RATIO;
+    ms.work = arena_alloc<double>(c, static_cast<size_t>(G) * (static_cast<size_t>(F) * F + F));
+    ms.beta = beta;
+    ms.flags = flags;
+    ARENA_GUARD(c);
+    multi_solve_kernel<<<static_cast<unsigned>((G + 63) / 64), 64, 0, c->stream>>>(ms);
+    c->launches++;
+    CU(cudaGetLastError());
+
+    {   // flagged groups (ill-conditioned, failed factorisation, n <= k): the reference's SVD itself, m right-hand sides
+        SvdParams sv;
+        std::memset(&sv, 0, sizeof(sv));
+        QrParams &qp = sv.q;
+        for (int j = 0; j < kd; ++j) qp.cols[j] = st.feat[j];
+        for (int t = 0; t < m - 1; ++t) qp.cols[kd + t] = st.feat[kd + t];
+        qp.cols[kd + m - 1] = st.y;
+        qp.w = st.w;
+        qp.mask = st.mask;
+        qp.kd = kd;
+        qp.intercept = icpt;
+        qp.F = F;
+        qp.w_is_sqrt = st.w_is_sqrt;
+        qp.n_groups = G;
+        qp.n_rows = st.n;
+        qp.beta = beta;
+        qp.flags = flags;
+        TRY(device_group_offsets(c, st, pl, &qp.group_off));
+        qp.ws = arena_alloc<double>(c, static_cast<size_t>(F + m) * static_cast<size_t>(st.n) + 8);
+        sv.vws = arena_alloc<double>(c, static_cast<size_t>(G) * F * F + 8);
+        sv.all_groups = 0;
+        sv.flag_mask = FLAG_WIDE | FLAG_ILLCOND | FLAG_LU_FALLBACK;
+        sv.n_rhs = m;
+        sv.ridge = ridge ? 1 : 0;
+        sv.alpha = alpha;
+        sv.rcond = kw->rcond;
+        sv.max_sweeps = 40;
+        ARENA_GUARD(c);
+        CU(launch_svd_solve(c->stream, sv, f->dtype == B200OLS_F64));
+        c->launches++;
+    }
+
+    // predictions / residuals: one pass of the row-parallel predict kernel per target
+    double *dout = out->values;
+    uint8_t *dval = out->validity;
+    if (f->memspace == B200OLS_HOST) {
+        dout = arena_alloc<double>(c, static_cast<size_t>(N) * m);
+        dval = out->validity ? arena_alloc<uint8_t>(c, static_cast<size_t>(N) * m) : nullptr;
+        ARENA_GUARD(c);
+    }
+    for (int t = 0; t < m; ++t) {
+        PredictParams pr;
+        std::memset(&pr, 0, sizeof(pr));
+        for (int j = 0; j < kd; ++j) pr.cols[j] = st.feat[j];
+        if (st.has_w) pr.cols[kd] = st.w;
+        pr.kd = kd;
+        pr.intercept = icpt;
+        pr.F = F;
+        pr.has_w = st.has_w;
+        pr.w_is_sqrt = st.w_is_sqrt;
+        const int raw_idx = (t < m - 1) ? kd + t : kdx;  // position of target t among the staged columns
+        pr.target = st.raw[raw_idx];
+        pr.target_is_packed = 0;
+        pr.target_validity = st.raw_bm[raw_idx];
+        pr.mask = (kw->null_policy == B200OLS_NULL_DROP) ? st.mask : nullptr;
+        pr.nseg = pl.nseg;
+        pr.n_rows = N;
+        pr.seg_off = pl.seg_off;
+        pr.seg_group = pl.seg_group;
+        pr.beta = beta + static_cast<size_t>(t) * F;
+        pr.beta_stride = static_cast<int64_t>(m) * F;
+        pr.nan_is_null = 1;
+        pr.row_index = st.row_index;
+        pr.residuals = mode == B200OLS_RESIDUALS;
+        pr.out = dout + static_cast<size_t>(t) * N;
+        pr.out_valid = dval ? dval + static_cast<size_t>(t) * N : nullptr;
+        const int64_t warps_needed = (N + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
+        const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
+        if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
+        else predict_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (f->memspace == B200OLS_HOST) {
+        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * N * m, cudaMemcpyDeviceToHost, c->stream));
+        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(N) * m, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+extern "C" int b200ols_multi_target_least_squares(b200ols_ctx *c, const b200ols_frame *f, int32_t n_targets,
+                                                  const b200ols_column *targets, const b200ols_ols_kwargs *kw, int mode,
+                                                  b200ols_output *out) {
+    const int rc = run_multi_target_impl(c, f, n_targets, targets, kw, mode, out);
+    if (c && c->pinned) pinned_end(c);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

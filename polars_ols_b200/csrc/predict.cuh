@@ -25,7 +25,9 @@ struct PredictParams {
     int64_t nseg, n_rows;
     const int64_t *seg_off;
     const int32_t *seg_group;
-    const double *beta;               // [n_groups][F]
+    const double *beta;               // [n_groups][F]  (group stride `beta_stride` doubles when != 0)
+    int64_t beta_stride;              // multi-target: coefficients of target t live at beta + t*F, stride n_targets*F
+    int nan_is_null;                  // multi-target: a NaN prediction is a null (convert_array_to_struct_series fill_nan)
     const int64_t *row_index;         // packed -> original row, or nullptr
     int target_is_packed;             // target pointer is indexed by packed position (cleaned copy)
     int residuals;
@@ -43,6 +45,7 @@ __device__ __forceinline__ void predict_store(const PredictParams &p, int64_t r,
     const int64_t orow = p.row_index ? p.row_index[r] : r;
     bool valid = true;
     if (p.mask) valid = static_cast<const T *>(p.mask)[r] != T(0);
+    if (p.nan_is_null) valid = valid && (acc == acc);
     if (p.residuals) {
         const int64_t trow = p.target_is_packed ? r : orow;
         acc = static_cast<double>(static_cast<const T *>(p.target)[trow]) - acc;
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
     const int64_t wg = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const int64_t nchunks = (p.n_rows + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
-    const int F = p.F, kd = p.kd;
+    const int kd = p.kd;
+    const int64_t bs = p.beta_stride ? p.beta_stride : p.F;
     for (int64_t ch = wg; ch < nchunks; ch += nwarps) {
         const int64_t c0 = ch * PREDICT_CHUNK;
         const int64_t c1 = (c0 + PREDICT_CHUNK < p.n_rows) ? c0 + PREDICT_CHUNK : p.n_rows;
@@ -95,12 +99,12 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
         }
         int64_t seg = lo;
         int64_t seg_end = p.seg_off[seg + 1];
-        const double *beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * F;
+        const double *beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * bs;
         for (; r < c1; r += 32 * VN) {
             while (r >= seg_end) {
                 ++seg;
                 seg_end = p.seg_off[seg + 1];
-                beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * F;
+                beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * bs;
             }
             if (r + VN <= c1 && r + VN <= seg_end) {
                 // whole vector inside one group: 16-byte loads, beta_j loaded once for the VN rows
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
                     while (r + v >= se) {
                         ++sg;
                         se = p.seg_off[sg + 1];
-                        bb = p.beta + (p.seg_group ? p.seg_group[sg] : sg) * F;
+                        bb = p.beta + (p.seg_group ? p.seg_group[sg] : sg) * bs;
                     }
                     predict_row<T>(p, r + v, bb);
                 }

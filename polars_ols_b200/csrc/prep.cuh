@@ -26,6 +26,8 @@ struct PrepParams {
     int kd, has_w;
     int fill;       // PREP_NAN | PREP_ZERO
     int mask_kind;  // MASK_*
+    int n_targets;  // multi-target: the last n_targets - 1 "features" and the target are all targets (MASK_TARGET ANDs
+                    // them, compute_is_valid_mask(.., Some(m)) src/expressions.rs:218-226); 0 / 1 = single target
     int64_t n_rows;
     int64_t n_rows_pad;  // outputs are zero-padded up to here
     const int64_t *row_index;
@@ -37,6 +39,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int nc = p.kd + 1 + (p.has_w ? 1 : 0);
+    const int ft = p.n_targets > 1 ? p.kd - (p.n_targets - 1) : p.kd;
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.n_rows_pad; r += stride) {
         if (r >= p.n_rows) {  // padding rows: finite zeros so that masked smem reads stay harmless
             for (int c = 0; c < nc; ++c) static_cast<T *>(p.out[c])[r] = T(0);
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
         for (int c = 0; c <= p.kd; ++c) {
             const bool v = p.validity[c] ? bit_at(p.validity[c], src) : true;
             all_valid = all_valid && v;
-            if (c == p.kd) y_valid = v;
+            if (c >= ft) y_valid = y_valid && v;
             const T x = static_cast<const T *>(p.in[c])[src];
             static_cast<T *>(p.out[c])[r] = v ? x : (p.fill == PREP_NAN ? static_cast<T>(NAN) : T(0));
         }

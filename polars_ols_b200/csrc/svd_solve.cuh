@@ -33,6 +33,9 @@ struct SvdParams {
     int max_sweeps;
     int materialised;    // big.cuh: q.ws already holds the fit matrix
     int skip_rows_le_F;  // big.cuh: groups with n <= F rows are solved by big_svd_wide_kernel
+    int n_rhs;           // multi-target: q.cols[kd .. kd + n_rhs) are the targets, workspace holds F + n_rhs columns,
+                         // beta is [n_groups][n_rhs][F]; 0 = 1 (single target)
+    int flag_mask;       // groups selected when !all_groups (0 = FLAG_WIDE)
 };
 
 template <typename T>
@@ -43,7 +46,8 @@ __global__ void __launch_bounds__(128) svd_solve_kernel(const SvdParams sp) {
     if (g >= p.n_groups) return;
     const int fl = p.flags[g];
     if (fl & FLAG_EMPTY) return;
-    if (!sp.all_groups && !(fl & FLAG_WIDE)) return;
+    if (!sp.all_groups && !(fl & (sp.flag_mask ? sp.flag_mask : FLAG_WIDE))) return;
+    const int n_rhs = sp.n_rhs > 0 ? sp.n_rhs : 1;
     const int F = p.F, kd = p.kd;
     const int64_t r0 = p.group_off[g], r1 = p.group_off[g + 1], n = r1 - r0;
     const int64_t N = p.n_rows;
@@ -62,7 +66,8 @@ __global__ void __launch_bounds__(128) svd_solve_kernel(const SvdParams sp) {
             const T x = (c < kd) ? static_cast<const T *>(p.cols[c])[r] : T(1);
             p.ws[static_cast<size_t>(c) * N + r] = keep ? static_cast<double>(static_cast<T>(x * s)) : 0.0;
         }
-        b[r] = keep ? static_cast<double>(static_cast<T>(static_cast<const T *>(p.cols[kd])[r] * s)) : 0.0;
+        for (int t = 0; t < n_rhs; ++t)
+            b[static_cast<size_t>(t) * N + r] = keep ? static_cast<double>(static_cast<T>(static_cast<const T *>(p.cols[kd + t])[r] * s)) : 0.0;
     }
     for (int e = lane; e < F * F; e += 32) V[e] = ((e / F) == (e % F)) ? 1.0 : 0.0;
     __syncwarp();
@@ -114,22 +119,25 @@ __global__ void __launch_bounds__(128) svd_solve_kernel(const SvdParams sp) {
     const int64_t mx = (n > F) ? n : F;
     const double cutoff = sp.ridge ? ((sp.rcond == sp.rcond) ? sp.rcond : DBL_EPSILON * static_cast<double>(mx)) * smax
                                    : DBL_EPSILON * smax;
-    double *beta = p.beta + g * F;  // lane accumulates coefficients lane, lane + 32, ...
-    for (int i = lane; i < F; i += 32) beta[i] = 0.0;
-    for (int c = 0; c < F; ++c) {
-        const double *a = p.ws + static_cast<size_t>(c) * N + r0;
-        double s2 = 0.0, ay = 0.0;
-        for (int64_t i = lane; i < n; i += 32) {
-            s2 = fma(a[i], a[i], s2);
-            ay = fma(a[i], b[r0 + i], ay);
+    for (int t = 0; t < n_rhs; ++t) {
+        double *beta = p.beta + (g * n_rhs + t) * F;  // lane accumulates coefficients lane, lane + 32, ...
+        const double *bt = b + static_cast<size_t>(t) * N;
+        for (int i = lane; i < F; i += 32) beta[i] = 0.0;
+        for (int c = 0; c < F; ++c) {
+            const double *a = p.ws + static_cast<size_t>(c) * N + r0;
+            double s2 = 0.0, ay = 0.0;
+            for (int64_t i = lane; i < n; i += 32) {
+                s2 = fma(a[i], a[i], s2);
+                ay = fma(a[i], bt[r0 + i], ay);
+            }
+            s2 = warp_sum(s2);
+            ay = warp_sum(ay);
+            const double sv = sqrt(s2);
+            double coef;
+            if (sp.ridge) coef = (sv < cutoff) ? 0.0 : ay / (s2 + sp.alpha);   // V d U^T y with d = s / (s^2 + alpha)
+            else coef = (sv <= cutoff) ? 0.0 : ay / s2;                         // V S^+ U^T y
+            for (int i = lane; i < F; i += 32) beta[i] = fma(V[c * F + i], coef, beta[i]);
         }
-        s2 = warp_sum(s2);
-        ay = warp_sum(ay);
-        const double sv = sqrt(s2);
-        double coef;
-        if (sp.ridge) coef = (sv < cutoff) ? 0.0 : ay / (s2 + sp.alpha);   // V d U^T y with d = s / (s^2 + alpha)
-        else coef = (sv <= cutoff) ? 0.0 : ay / s2;                         // V S^+ U^T y
-        for (int i = lane; i < F; i += 32) beta[i] = fma(V[c * F + i], coef, beta[i]);
     }
     if (lane == 0) p.flags[g] = (fl & ~(FLAG_ILLCOND | FLAG_LU_FALLBACK | FLAG_QR)) | FLAG_SVD;
 }

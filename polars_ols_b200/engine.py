@@ -264,6 +264,36 @@ class Engine:
         del keep
         return v, m
 
+    def least_squares_statistics(self, b: Batch, kw: L.OLSKwargs) -> dict:
+        """b200ols_least_squares_statistics: per-group r2 / mae / mse [G] and coefficients / standard_errors / t_values /
+        p_values [G, F] (numpy for host frames, CUDA tensors for device frames)."""
+        fr, keep, dtype, memspace, n, G = self._frame(b)
+        F = len(b.features) + (1 if b.add_intercept else 0)
+        names = ("r2", "mae", "mse", "coefficients", "standard_errors", "t_values", "p_values")
+        arrs = {}
+        for nm in names:
+            shape = (G,) if nm in ("r2", "mae", "mse") else (G, F)
+            arrs[nm] = (torch.empty(shape, dtype=torch.float64, device=b.target.values.device) if memspace == L.DEVICE
+                        else np.empty(shape, dtype=np.float64))
+        so = L.StatisticsOutput(*[_ptr(arrs[nm]) for nm in names])
+        L.check(self._lib.b200ols_least_squares_statistics(self._ctx, C.byref(fr), C.byref(kw), C.byref(so)))
+        del keep
+        return arrs
+
+    def multi_target_least_squares(self, b: Batch, targets: List[Col], kw: L.OLSKwargs, mode: int):
+        """b200ols_multi_target_least_squares: values / validity of shape [n_targets, n_rows] (target-major)."""
+        tcols = list(targets)
+        b2 = Batch(tcols[-1], list(b.features) + tcols[:-1], b.weights, b.add_intercept, b.offsets, b.row_index, b.n_groups)
+        dtype, memspace = b2.harmonise()      # one dtype / memory space over features, targets and weights
+        b.target = tcols[-1]
+        fr, keep, dtype, memspace, n, G = self._frame(b)
+        m = len(tcols)
+        tt = (L.Column * m)(*[L.Column(_ptr(t.values), _ptr(t.validity)) for t in tcols])
+        o, v, msk = self._alloc_out(memspace, (m, n), True, tcols[0].values)
+        L.check(self._lib.b200ols_multi_target_least_squares(self._ctx, C.byref(fr), m, tt, C.byref(kw), mode, C.byref(o)))
+        del keep, b2
+        return v, msk
+
     def prepare_least_squares(self, b: Batch, kw: L.OLSKwargs, mode: int, out_values, out_validity=None):
         """Marshal once, call many times: returns a zero-argument callable that re-issues the same C-ABI
         call (same buffers).  Used by steady-state loops (bench.py) to keep Python out of the timed region."""

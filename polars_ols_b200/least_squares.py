@@ -35,7 +35,7 @@ logger = logging.getLogger(__name__)
 
 __all__ = [
     "compute_least_squares", "compute_recursive_least_squares", "compute_rolling_least_squares",
-    "OLSKwargs", "RLSKwargs", "RollingKwargs", "NullPolicy", "OutputMode", "SolveMethod",
+    "compute_multi_target_least_squares", "OLSKwargs", "RLSKwargs", "RollingKwargs", "NullPolicy", "OutputMode", "SolveMethod",
     "LeastSquares", "Frame", "col", "Expr", "Result", "predict", "PredictExpr",
 ]
 
@@ -138,6 +138,14 @@ class Result:
             v = v[self.group_of_row]
         return v
 
+    def to_struct(self) -> Dict[str, np.ndarray]:
+        """struct-valued results as {field: array}: multi-target predictions / residuals ({target: [n]}, nulls as NaN)
+        and mode="statistics" ({r2, mae, mse: [G]; feature_names: list; coefficients, ...: [G, k]})."""
+        if isinstance(self.values, dict):
+            return {k: (v.cpu().numpy() if _is_torch(v) else v) for k, v in self.values.items()}
+        v = self.to_numpy()
+        return {f: v[j] for j, f in enumerate(self.fields)}
+
     def is_null(self) -> np.ndarray:
         if self.valid is not None:
             m = self.valid.cpu().numpy() if _is_torch(self.valid) else np.asarray(self.valid)
@@ -233,7 +241,9 @@ class LsExpr:
             return self._alias
         # reference: coefficients / statistics are aliased to the mode (least_squares.py:224);
         # predictions keep the target's name (src/expressions.rs:404)
-        return self.mode if self.mode == "coefficients" else self.target.output_name or self.mode
+        if self.kind == "multi_target_least_squares":     # Field::new("predictions", ..) src/expressions.rs:518
+            return "predictions" if self.mode == "predictions" else (self.target.output_name or self.mode)
+        return self.mode if self.mode in ("coefficients", "statistics") else self.target.output_name or self.mode
 
     # -- evaluation ----------------------------------------------------------------------------------
     def rls_c_kwargs(self, n_coef: int, initial_information: Optional[np.ndarray] = None):
@@ -249,9 +259,17 @@ class LsExpr:
                           None if info is None else info.ctypes.data)
         return ckw, (mean_arr, info)
 
+    def target_struct(self, frame: "Frame"):
+        """multi-target: the target is a struct column, here {field: column} -> [(field, Col)]"""
+        t = self.target._data if self.target._data is not None else frame[self.target._name]
+        assert isinstance(t, dict) and len(t) > 0, (
+            "the first series in a multi-target regression must be of polars struct dtype with each field "
+            "corresponding to an output")                 # src/expressions.rs:513-517
+        return [(str(k), as_col(v)) for k, v in t.items()]
+
     def batch(self, frame: "Frame"):
         """(Batch of the resolved input columns, coefficient field names) — no grouping yet."""
-        target = self.target.resolve(frame)
+        target = self.target_struct(frame)[0][1] if self.kind == "multi_target_least_squares" else self.target.resolve(frame)
         feats = [f.resolve(frame) for f in self.features]
         names = [f.output_name or str(i) for i, f in enumerate(self.features)]  # src/expressions.rs:126-130
         add_intercept = self.add_intercept
@@ -280,6 +298,16 @@ class LsExpr:
         if engine is None:
             dev = target.values.device.index if target.is_device else 0
             engine = get_engine(dev or 0, torch_stream=target.is_device)
+        if self.kind == "multi_target_least_squares":
+            tcols = self.target_struct(frame)
+            b.target = tcols[0][1]
+            v, m = engine.multi_target_least_squares(b, [c_ for _, c_ in tcols], self.kwargs.to_c(), L.MODE[self.mode])
+            return Result(self.output_name, v, m, [n_ for n_, _ in tcols])
+        if self.mode == "statistics":
+            st = engine.least_squares_statistics(b, self.kwargs.to_c())
+            st["feature_names"] = list(names)            # src/expressions.rs:483-484
+            order = ("r2", "mae", "mse", "feature_names", "coefficients", "standard_errors", "t_values", "p_values")
+            return Result(self.output_name, {k_: st[k_] for k_ in order}, None, list(order), keys, group_of_row)
         mode = L.MODE[self.mode]
         if self.kind == "least_squares":
             v, m = engine.least_squares(b, self.kwargs.to_c(), mode)
@@ -369,9 +397,23 @@ def compute_least_squares(target: ExprOrStr, *features: ExprOrStr, sample_weight
                           add_intercept: bool = False, mode: OutputMode = "predictions",
                           ols_kwargs: Optional[OLSKwargs] = None) -> LsExpr:
     assert mode in _VALID_OUTPUT_MODES, f"'mode' must be one of {_VALID_OUTPUT_MODES}"
-    if mode == "statistics":
-        raise NotImplementedError("mode='statistics' is outside the accelerated hot path (SURVEY.md §8)")
     return _make("least_squares", target, features, sample_weights, add_intercept, mode, ols_kwargs or OLSKwargs())
+
+
+def compute_multi_target_least_squares(targets: ExprOrStr, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None,
+                                       add_intercept: bool = False, mode: OutputMode = "predictions",
+                                       ols_kwargs: Optional[OLSKwargs] = None) -> LsExpr:
+    """reference polars_ols/least_squares.py:282-329: `targets` is a struct column ({field: array} in a Frame)."""
+    ols_kwargs = ols_kwargs or OLSKwargs()
+    multi_target_conditions = not ols_kwargs.positive and (ols_kwargs.l1_ratio is None or ols_kwargs.l1_ratio == 0.0)
+    msg = "Consider running multiple independent regressions on a multi-expression target!"
+    assert multi_target_conditions, (
+        "Multi-target regression is only supported for unconstrained OLS & Ridge problems." + msg)
+    assert ols_kwargs.solve_method in {"svd", None}, "only solve_method='svd' is supported for multi-target regressions"
+    if mode == "coefficients":
+        raise NotImplementedError("Only mode={'predictions', 'residuals'} is currently supported. " + msg)
+    assert mode in ("predictions", "residuals"), f"'mode' must be one of {_VALID_OUTPUT_MODES}"
+    return _make("multi_target_least_squares", targets, features, sample_weights, add_intercept, mode, ols_kwargs)
 
 
 def compute_recursive_least_squares(target: ExprOrStr, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None,
@@ -401,14 +443,16 @@ class LeastSquares:
     def least_squares(self, *features: ExprOrStr, sample_weights: Optional[ExprOrStr] = None, add_intercept: bool = False,
                       mode: OutputMode = "predictions", null_policy: NullPolicy = "ignore",
                       solve_method: Optional[SolveMethod] = None, multi_target: bool = False, **ols_kwargs) -> LsExpr:
-        if multi_target:
-            raise NotImplementedError("multi_target_ols is a 'next' row of SURVEY.md §8f")
-        return compute_least_squares(self._expr, *features, sample_weights=sample_weights, add_intercept=add_intercept,
+        ols_func = compute_least_squares if not multi_target else compute_multi_target_least_squares  # __init__.py:90
+        return ols_func(self._expr, *features, sample_weights=sample_weights, add_intercept=add_intercept,
                                      mode=mode,
                                      ols_kwargs=OLSKwargs(null_policy=null_policy, solve_method=solve_method, **ols_kwargs))
 
     def ols(self, *features: ExprOrStr, **kwargs) -> LsExpr:
         return self.least_squares(*features, **kwargs)
+
+    def multi_target_ols(self, *features: ExprOrStr, **kwargs) -> LsExpr:   # polars_ols/__init__.py:104-105
+        return self.least_squares(*features, multi_target=True, **kwargs)
 
     def wls(self, *features: ExprOrStr, sample_weights: ExprOrStr, **kwargs) -> LsExpr:
         return self.least_squares(*features, sample_weights=sample_weights, **kwargs)

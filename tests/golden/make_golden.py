@@ -33,6 +33,12 @@ golden = {
     # README.md:119-138: rls(x1, x2, mode="coefficients").over("group"), head(5) (group 1)
     "coefficients_rls_group1": [[1.235503, 0.411834], [0.963515, 0.760769], [0.975484, 0.966029],
                                 [0.975657, 0.953735], [0.97898, 0.909793]],
+    # README.md:143-165: ols(x1, x2, mode="statistics", add_intercept=True) -> r2, mae, mse + per-feature rows
+    "statistics_ols_intercept": {
+        "r2": 0.99631, "mae": 0.061732, "mse": 0.00794, "feature_names": ["x1", "x2", "const"],
+        "coefficients": [0.977375, 0.987413, 0.000757], "standard_errors": [0.037286, 0.037321, 0.037474],
+        "t_values": [26.212765, 26.457169, 0.02021], "p_values": [3.0095e-8, 2.8218e-8, 0.98444],
+        "printed_rel_tol": 5e-5},          # 5 significant digits printed for r2 / mse / p / t(const)
     # 6 printed decimals; one entry (group 1, x2: 0.977495 printed vs 0.97749434 from LAPACK on the
     # printed data) is off by 6.6e-7, so the pin is 1e-6 absolute.
     "printed_abs_tol_coefficients": 1e-6,

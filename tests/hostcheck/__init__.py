@@ -28,5 +28,8 @@ def lib():
     L.hc_rolling.restype = None
     L.hc_rls.argtypes = [vp, vp, vp, i64, i32, d, d, vp, i64, vp]
     L.hc_rls.restype = None
+    L.hc_students_t_p.argtypes = [d, d]
+    L.hc_students_t_p.restype = d
+    L.hc_chol_inverse.argtypes = [vp, i32]
     _lib = L
     return L

@@ -8,6 +8,7 @@
 
 #include "../../polars_ols_b200/csrc/moving_core.cuh"
 #include "../../polars_ols_b200/csrc/solvers.cuh"
+#include "../../polars_ols_b200/csrc/stats_math.cuh"
 
 using namespace b200;
 
@@ -22,6 +23,13 @@ HC_API int hc_cd_gram(const double *G, int F, const double *c, double a, double 
                       int positive, int active_set, double *w) {
     std::vector<double> scratch(3 * F + 2);
     return cd_gram_solve(G, F, F, c, a, l1_ratio, max_iter, tol, positive != 0, active_set != 0, w, scratch.data());
+}
+
+HC_API double hc_students_t_p(double t, double df) { return students_t_two_sided_p(t, df); }
+
+HC_API int hc_chol_inverse(double *A, int n) {
+    std::vector<double> M(static_cast<size_t>(n) * n), diag(n);
+    return chol_inverse(A, M.data(), n, diag.data());
 }
 
 template <int K>

@@ -593,3 +593,177 @@ def test_fused_and_batched_solve_agree(k, n_rows, n_groups, solve_method, monkey
     for key, v in res.items():
         _close(v, c, rtol=1e-6, atol=1e-9)
         np.testing.assert_allclose(v, res[("0", "1", 0)], rtol=1e-10, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------------- §8f: mode = "statistics"
+STAT_KEYS = ("r2", "mae", "mse", "coefficients", "standard_errors", "t_values", "p_values")
+
+
+def _stats_oracle_by_group(d, names, group=None, **kw):
+    gid = np.zeros(len(d["y"] if not isinstance(d["y"], tuple) else d["y"][0]), dtype=int) if group is None else d[group]
+    out = []
+    for g in np.unique(gid):
+        sel = gid == g
+        take = lambda c: (c[0][sel], c[1][sel]) if isinstance(c, tuple) else c[sel]  # noqa: E731
+        kk = {k: (take(v) if k == "sample_weights" and v is not None else v) for k, v in kw.items()}
+        out.append(S.least_squares_statistics(take(d["y"]), *[take(d[n]) for n in names], **kk))
+    return out
+
+
+def _check_stats(res, refs, rtol=1e-6):
+    got = res.to_struct()
+    for i, ref in enumerate(refs):
+        for k in STAT_KEYS:
+            g, r = np.asarray(got[k][i]), np.asarray(ref[k])
+            assert (np.isnan(g) == np.isnan(r)).all(), (k, i)
+            m = ~np.isnan(r)
+            # p-values below ~1e-12 are dominated by the reference's own 1 - (1 - ib) cancellation (multiples of 1.1e-16)
+            assert np.allclose(g[m], r[m], rtol=rtol, atol=(3e-16 if k == "p_values" else 1e-12)), (k, i, g, r)
+
+
+def test_statistics_readme_frame():                                         # README.md:143-165
+    F = Frame({k: np.asarray(v, dtype=np.float64) for k, v in GOLD["frame"].items()})
+    r = F.select(col("y").least_squares.ols("x1", "x2", mode="statistics", add_intercept=True))["statistics"]
+    g, st = GOLD["statistics_ols_intercept"], r.to_struct()
+    assert st["feature_names"] == g["feature_names"]
+    for k in ("r2", "mae", "mse"):
+        assert st[k][0] == pytest.approx(g[k], rel=g["printed_rel_tol"])
+    for k in ("standard_errors", "t_values", "p_values"):
+        assert np.allclose(st[k][0], g[k], rtol=g["printed_rel_tol"], atol=0)
+    assert np.allclose(st["coefficients"][0], g["coefficients"], atol=GOLD["printed_abs_tol_coefficients"], rtol=0)
+
+
+@pytest.mark.parametrize("model,kw", [("ols", {}), ("ridge", {"alpha": 10.0}), ("ridge", {"alpha": 0.3, "solve_method": "lu"}),
+                                      ("lasso", {"alpha": 1e-3}), ("ols", {"solve_method": "svd"})])
+@pytest.mark.parametrize("null_policy", ["ignore", "drop", "drop_y_zero_x", "zero"])
+def test_statistics_over_groups(model, kw, null_policy):                    # tests/test_ols.py:998-1029, grouped + nulls + WLS
+    d = _make_data(6000, 5, n_groups=7, scale=1.0, add_missing=null_policy != "ignore", seed=11)
+    rng = np.random.default_rng(2)
+    d["w"] = rng.uniform(0.2, 3.0, size=6000)
+    names = _xs(d)
+    e = getattr(col("y").least_squares, model)(*names, mode="statistics", add_intercept=True, sample_weights="w",
+                                                null_policy=null_policy, **kw).over("group")
+    r = Frame(d).select(e)["statistics"]
+    okw = dict(kw)
+    okw.setdefault("alpha", 0.0)
+    if model == "ridge":
+        okw["l1_ratio"] = 0.0
+    if model == "lasso":
+        okw["l1_ratio"] = 1.0
+    refs = _stats_oracle_by_group(d, names, "group", sample_weights=d["w"], add_intercept=True,
+                                  kwargs=S.OLSKwargs(null_policy=null_policy, **okw))
+    _check_stats(r, refs)
+    assert r.to_struct()["feature_names"] == names + ["const"]
+
+
+def test_statistics_f32_device_frame_and_long_group():
+    import torch
+    rng = np.random.default_rng(3)
+    n, k = 120_000, 12                                                       # split into segments, k > 8 (wide record path)
+    x = rng.normal(size=(n, k)).astype(np.float32)
+    y = (x @ rng.normal(size=k) + rng.normal(size=n)).astype(np.float32)
+    g = np.repeat(np.arange(3), n // 3)
+    dev = torch.device("cuda", 0)
+    d = {f"x{j}": torch.as_tensor(x[:, j].copy(), device=dev) for j in range(k)}
+    d["y"] = torch.as_tensor(y, device=dev)
+    d["group"] = g
+    names = [f"x{j}" for j in range(k)]
+    r = Frame(d).select(col("y").least_squares.ridge(*names, alpha=2.0, mode="statistics").over("group"))["statistics"]
+    dn = {f"x{j}": x[:, j] for j in range(k)}
+    dn["y"], dn["group"] = y, g
+    refs = _stats_oracle_by_group(dn, names, "group", kwargs=S.OLSKwargs(alpha=2.0, l1_ratio=0.0))
+    _check_stats(r, refs, rtol=1e-4)                                         # f32 inputs
+
+
+def test_statistics_failure_modes():
+    d = _make_data(50, 3, seed=4)
+    F = Frame(d)
+    # collinear features, alpha = 0: the Cholesky of X^T X fails -> NaN feature metrics, residual metrics still reported
+    d2 = dict(d)
+    d2["x4"] = d["x1"] * 2.0
+    r = Frame(d2).select(col("y").least_squares.ols("x1", "x2", "x3", "x4", mode="statistics", solve_method="svd"))["statistics"].to_struct()
+    ref = S.least_squares_statistics(d2["y"], d2["x1"], d2["x2"], d2["x3"], d2["x4"], kwargs=S.OLSKwargs(alpha=0.0, solve_method="svd"))
+    if np.isnan(ref["standard_errors"]).all():                              # (numpy's Cholesky may squeak through on rounding)
+        assert np.isnan(r["standard_errors"][0]).all() and np.isnan(r["p_values"][0]).all()
+    assert r["r2"][0] == pytest.approx(ref["r2"], rel=1e-6)
+    # df <= 0: the reference asserts (src/statistics.rs:131-134)
+    tiny = Frame({k: v[:3] for k, v in d.items()})
+    with pytest.raises(pls.B200OLSError, match="Degrees of freedom"):
+        tiny.select(col("y").least_squares.ols("x1", "x2", "x3", mode="statistics", solve_method="chol"))
+    # alpha = None: `kwargs.alpha.unwrap()` panics in the reference
+    with pytest.raises(pls.B200OLSError, match="alpha"):
+        F.select(pls.compute_least_squares("y", "x1", mode="statistics", ols_kwargs=OLSKwargs(alpha=None)))
+
+
+# ----------------------------------------------------------------------------------- §8f: multi-target
+def _multi_oracle(d, tnames, names, group, mode, kw, **extra):
+    n = len(d[group])
+    out_v, out_m = np.full((len(tnames), n), np.nan), np.zeros((len(tnames), n), dtype=bool)
+    take = lambda c, sel: (c[0][sel], c[1][sel]) if isinstance(c, tuple) else c[sel]  # noqa: E731
+    for g in np.unique(d[group]):
+        sel = d[group] == g
+        ex = {k: (take(v, sel) if k == "sample_weights" else v) for k, v in extra.items()}
+        v, m = S.multi_target_least_squares([take(d[t], sel) for t in tnames], *[take(d[x], sel) for x in names], mode=mode,
+                                            kwargs=kw, **ex)
+        out_v[:, sel], out_m[:, sel] = v.T, m.T
+    return out_v, out_m
+
+
+@pytest.mark.parametrize("alpha,mode,null_policy", [(0.0, "residuals", "ignore"), (0.0, "residuals", "drop"),
+                                                    (0.0001, "residuals", "drop_y_zero_x"), (0.01, "residuals", "drop_zero"),
+                                                    (0.5, "predictions", "zero"), (0.0, "predictions", "drop")])
+def test_multi_target_regression(alpha, mode, null_policy):                # tests/test_ols.py:76-127
+    d = _make_data(10_000, 3, n_groups=3, seed=21)
+    if null_policy not in ("zero", "ignore"):
+        d["x1"] = (d["x1"], np.random.default_rng(5).random(10_000) >= 0.1)    # missing_columns=("x1",)
+    x1, x2, x3 = (d["x1"][0] if isinstance(d["x1"], tuple) else d["x1"]), d["x2"], d["x3"]
+    m1 = d["x1"][1] if isinstance(d["x1"], tuple) else None
+    ys = {"y1": x1 + x2 + x3, "y2": x1 - x2 + x3, "y3": -x1 + x2 - x3}
+    ys = {k: (v, m1) if m1 is not None else v for k, v in ys.items()}           # struct fields inherit x1's nulls
+    F = Frame(d)
+    F["ys"] = ys
+    names = _xs(d)
+    kw = OLSKwargs(null_policy=null_policy, solve_method="svd", alpha=alpha)
+    r = F.select(pls.compute_multi_target_least_squares("ys", *names, mode=mode, ols_kwargs=kw).over("group").alias(mode))[mode]
+    assert r.fields == ["y1", "y2", "y3"]
+    dd = dict(d)
+    dd.update(ys)
+    okw = S.OLSKwargs(null_policy=null_policy, solve_method="svd", alpha=alpha)
+    ref_v, ref_m = _multi_oracle(dd, list(ys), names, "group", mode, okw)
+    _close(r.to_numpy(), np.where(ref_m, ref_v, np.nan), rtol=1e-6, atol=1e-8)
+    # the reference's own assertion: equal to independent single-target regressions
+    for j, t in enumerate(ys):
+        F1 = Frame(dd)
+        r1 = F1.select(col(t).least_squares.least_squares(*names, mode=mode, null_policy=null_policy, solve_method="svd",
+                                                          alpha=alpha).over("group"))[t]
+        a, b = r.to_numpy()[j], r1.to_numpy()
+        ok = ~(np.isnan(a) | np.isnan(b))
+        assert np.allclose(a[ok], b[ok], atol=1e-8, rtol=1e-6)
+
+
+def test_multi_target_weights_intercept_rank_deficient_and_wide():
+    rng = np.random.default_rng(9)
+    n = 900
+    d = _make_data(n, 4, n_groups=4, seed=8)
+    d["x5"] = d["x1"] - 2.0 * d["x2"]                                           # exactly collinear -> SVD kernel (min-norm)
+    d["group"][:3] = 99                                                         # a 3-row group: n <= k -> SVD kernel
+    d["w"] = rng.uniform(0.3, 2.0, size=n)
+    names = _xs(d)
+    ys = {"a": d["y"], "b": d["x1"] * 0.5 - d["x3"] + 0.1 * rng.normal(size=n)}
+    F = Frame(d)
+    F["ys"] = ys
+    dd = dict(d)
+    dd.update(ys)
+    for alpha in (0.0, 0.25):
+        kw = OLSKwargs(solve_method="svd", alpha=alpha)
+        r = F.select(col("ys").least_squares.multi_target_ols(*names, sample_weights="w", add_intercept=True, alpha=alpha,
+                                                               solve_method="svd").over("group"))["predictions"]
+        ref_v, ref_m = _multi_oracle(dd, ["a", "b"], names, "group", "predictions", S.OLSKwargs(solve_method="svd", alpha=alpha),
+                                     sample_weights=d["w"], add_intercept=True)
+        _close(r.to_numpy(), np.where(ref_m, ref_v, np.nan), rtol=1e-6, atol=1e-7)
+        fl = pls.get_engine(0).last_group_flags(5)
+        assert (fl & 32).any()                                                  # some groups went through the Jacobi SVD kernel
+    with pytest.raises(AssertionError):
+        pls.compute_multi_target_least_squares("ys", *names, ols_kwargs=OLSKwargs(l1_ratio=0.5, alpha=0.1))
+    with pytest.raises(NotImplementedError):
+        pls.compute_multi_target_least_squares("ys", *names, mode="coefficients")

@@ -102,3 +102,29 @@ def test_rls_chunks_match_sequential_oracle(k, half_life, p0, chunk, null_frac, 
     lo = 3 * k
     assert _rel(out[lo:], ref[lo:]) < 1e-6
     assert np.allclose(out[:lo], ref[:lo], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------- mode = "statistics" building blocks
+def test_students_t_p_value_matches_scipy():
+    """stats_math.cuh (the device routine, compiled for the host) against the oracle's scipy restatement of
+    statrs StudentsT::cdf, including the reference's 1 - (1 - ib) cancellation to exactly 0 for huge |t|."""
+    rng = np.random.default_rng(0)
+    for df in (1.0, 2.5, 7.0, 30.0, 197.0, 997.3, 9999.0, 1.0e6, 2.5e7):
+        ts = np.concatenate([[0.0, 1e-8, 1e-3, 0.02021, 0.5, 1.0, 2.0, 5.0, 26.212765, 60.0, 1e3, np.inf], rng.normal(size=20) * 3])
+        ref = S.students_t_two_sided_p(ts, df)
+        got = np.array([hostcheck.lib().hc_students_t_p(float(t), df) for t in ts])
+        assert np.all(np.abs(got - ref) <= 1e-7 * np.abs(ref) + 1e-15), (df, ts[np.argmax(np.abs(got - ref))])
+    assert np.isnan(hostcheck.lib().hc_students_t_p(float("nan"), 5.0))
+
+
+def test_cholesky_inverse():
+    rng = np.random.default_rng(1)
+    for n in (1, 3, 8, 17, 64):
+        x = rng.normal(size=(4 * n + 5, n))
+        A = np.ascontiguousarray(x.T @ x + 1e-3 * np.eye(n))
+        ref = np.linalg.inv(A)
+        a = A.copy()
+        assert hostcheck.lib().hc_chol_inverse(a.ctypes.data, n) == 0
+        assert np.allclose(a, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+    bad = np.ascontiguousarray(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    assert hostcheck.lib().hc_chol_inverse(bad.ctypes.data, 2) == 1

@@ -265,3 +265,61 @@ def test_predict_semantics():                                                 # 
     assert (m == mx).all()
     p, m = S.predict([c[:, j] for j in range(3)], [(x[:, 0], mx), x[:, 1], x[:, 2]], "ignore")
     assert (np.isnan(p) == ~mx).all()
+
+
+# ----------------------------------------------------------------------------- §8f rows: statistics, multi-target
+def test_readme_statistics_frame():
+    """README.md:143-165 (the reference's printed statistics struct) pins mode="statistics" of the oracle."""
+    g = GOLD["statistics_ols_intercept"]
+    r = S.least_squares_statistics(F["y"], F["x1"], F["x2"], add_intercept=True, kwargs=S.OLSKwargs(alpha=0.0))
+    rt = g["printed_rel_tol"]
+    for k in ("r2", "mae", "mse"):
+        assert r[k] == pytest.approx(g[k], rel=rt)
+    for k in ("standard_errors", "t_values", "p_values"):
+        assert np.allclose(r[k], g[k], rtol=rt, atol=0)
+    assert np.allclose(r["coefficients"], g["coefficients"], atol=TOLC, rtol=0)
+
+
+def test_statistics_against_textbook_ols_and_scipy():
+    """tests/test_ols.py:998-1029 compares against statsmodels (absent here): the same closed forms via scipy."""
+    from scipy import stats
+    d = _make_data(n_samples=2000, n_features=4, scale=1.0)
+    x, y = d["x"], d["y"]
+    r = S.least_squares_statistics(y, *x.T, add_intercept=True, kwargs=S.OLSKwargs(alpha=0.0))
+    X = np.column_stack([x, np.ones(len(y))])
+    b = np.linalg.lstsq(X, y, rcond=None)[0]
+    res = y - X @ b
+    dof = len(y) - X.shape[1]
+    se = np.sqrt(res @ res / dof * np.diag(np.linalg.inv(X.T @ X)))
+    assert np.allclose(r["coefficients"], b, rtol=1e-9)
+    assert np.allclose(r["standard_errors"], se, rtol=1e-9)
+    assert np.allclose(r["t_values"], b / se, rtol=1e-8)
+    pv = 2 * stats.t.sf(np.abs(b / se), dof)
+    big = pv > 1e-12                                     # below that the reference's 1 - (1 - ib) has cancelled
+    assert np.allclose(r["p_values"][big], pv[big], rtol=1e-6)
+    assert r["r2"] == pytest.approx(1 - res @ res / ((y - y.mean()) ** 2).sum(), rel=1e-12)
+    assert r["mae"] == pytest.approx(np.abs(res).mean(), rel=1e-12)
+    # ridge: df = n - trace((X^T X + lambda I)^-1)  (src/statistics.rs:125-129)
+    rr = S.least_squares_statistics(y, *x.T, kwargs=S.OLSKwargs(alpha=10.0, l1_ratio=0.0))
+    inv = np.linalg.inv(x.T @ x + 10.0 * np.eye(4))
+    br = inv @ x.T @ y
+    rs = y - x @ br
+    assert np.allclose(rr["standard_errors"], np.sqrt(rs @ rs / (len(y) - np.trace(inv)) * np.diag(inv)), rtol=1e-9)
+
+
+@pytest.mark.parametrize("alpha,policy", [(0.0, "ignore"), (0.0, "drop"), (1e-4, "drop_y_zero_x"), (0.01, "drop_zero"), (0.5, "zero")])
+def test_multi_target_equals_independent_regressions(alpha, policy):
+    """tests/test_ols.py:76-127: a multi-target fit equals one single-target (svd) fit per target."""
+    d = _make_data(n_samples=3000, n_features=3, add_missing=policy not in ("zero", "ignore"))
+    x = d["x"]
+    xs = [(x[:, j], d["masks"][j] if (j == 0 and "masks" in d) else None) for j in range(3)]
+    ys = [x[:, 0] + x[:, 1] + x[:, 2], x[:, 0] - x[:, 1] + x[:, 2], -x[:, 0] + x[:, 1] - x[:, 2]]
+    ys = [(v, xs[0][1]) for v in ys]                                   # y_t inherits x1's nulls, as in the reference test
+    kw = S.OLSKwargs(null_policy=policy, solve_method="svd", alpha=alpha)
+    v, m = S.multi_target_least_squares(ys, *xs, mode="residuals", kwargs=kw)
+    for t in range(3):
+        v1, m1 = S.least_squares(ys[t], *xs, mode="residuals", kwargs=kw)
+        m1 = np.ones(len(v1), bool) if m1 is None else m1
+        both = m[:, t] & m1 & ~np.isnan(v1)
+        assert (m[:, t] == (m1 & ~np.isnan(v1))).all() or policy == "ignore"
+        assert np.allclose(v[both, t], v1[both], atol=1e-9)
