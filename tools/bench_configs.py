@@ -17,7 +17,7 @@ from polars_ols_b200 import _lib as L  # noqa: E402
 from oracle import semantics as S  # noqa: E402  (checker)
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--only", default="C1,C2,C3,C4,C5")
+ap.add_argument("--only", default="C1,C2,F,C3,C4,C5")
 ap.add_argument("--out", default="gpurun_out/configs.json")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--scale", type=float, default=1.0, help="shrink the big configs (debug)")
@@ -106,6 +106,28 @@ if "C2" in only:
         out, ms, kms = timed(lambda: eng.least_squares(b, kw, mode)[0], a.reps)
         report(f"C2 ridge {nm} 10kx1000x8 f64", ms, kms, G * (per * 9 * 8 + per * 8), G, "regressions", None)
     del x, y
+
+# ------------------------------------------------------------------------------------------------ §8f rows on the C2 shape
+if "F" in only:
+    G, per, k, m = 10_000, 1000, 8, 4
+    x, y = gen(G * per, k, G, torch.float64, 2)
+    offs = np.arange(G + 1, dtype=np.int64) * per
+    b = pls.Batch(pls.Col(y), [pls.Col(x[i]) for i in range(k)], offsets=offs)
+    kw = pls.OLSKwargs(alpha=1e-3, l1_ratio=0.0).to_c()
+    out, ms, kms = timed(lambda: eng.least_squares_statistics(b, kw), a.reps)
+    g0 = slice(0, per)
+    ref = S.least_squares_statistics(y[g0].cpu().numpy(), *[x[i, g0].cpu().numpy() for i in range(k)], kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.0))
+    err = max(rel_err(out[nm][0].cpu().numpy(), np.asarray(ref[nm])) for nm in ("r2", "mae", "mse", "coefficients", "standard_errors", "t_values"))
+    report("F4 ridge statistics 10kx1000x8 f64", ms, kms, G * (per * 9 * 8 + (3 + 4 * k) * 8), G, "regressions", err)
+    g = torch.Generator(device=dev).manual_seed(7)
+    ys = [y] + [x[j] - 0.5 * x[j + 1] + 0.1 * torch.randn(G * per, dtype=torch.float64, device=dev, generator=g) for j in range(m - 1)]
+    kws = pls.OLSKwargs(alpha=1e-3, solve_method="svd").to_c()
+    out, ms, kms = timed(lambda: eng.multi_target_least_squares(b, [pls.Col(t) for t in ys], kws, L.PREDICTIONS)[0], a.reps)
+    ref = S.multi_target_least_squares([t[g0].cpu().numpy() for t in ys], *[x[i, g0].cpu().numpy() for i in range(k)],
+                                       kwargs=S.OLSKwargs(alpha=1e-3, solve_method="svd"))[0]
+    report(f"F2 multi-target ridge predictions 10kx1000x8, {m} targets f64", ms, kms, G * per * ((k + m) * 8 + m * 8), G * m,
+           "regressions", rel_err(out[:, g0].cpu().numpy().T, ref))
+    del x, y, ys
 
 # ------------------------------------------------------------------------------------------------ C3
 if "C3" in only:
