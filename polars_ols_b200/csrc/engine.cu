@@ -20,6 +20,7 @@
 #include "../../include/b200ols.h"
 #include "gram_cta.cuh"
 #include "gram_multi.cuh"
+#include "gram_pred.cuh"
 #include "gram_wide.cuh"
 #include "gram_ldg.cuh"
 #include "gram_simt.cuh"
@@ -85,6 +86,7 @@ struct b200ols_ctx {
     int64_t launches = 0;
     int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
     bool multi_enabled = true;      // test hook B200OLS_MULTI=0: never use gram_multi_kernel
+    bool pred_enabled = true;       // test hook B200OLS_PRED=0: never use the fused Gram -> solve -> predict kernel
     long long fuse_min_bytes = -1;  // < 0: default; test hook B200OLS_FUSE_MIN_BYTES (0 = always fuse the solve)
     int variant = 3, unroll = 0;  // Gram kernel variant (b200ols_set_variant); 3 = CTA-cooperative TMA pipeline
     // bump arena in device memory, reset at the start of every call
@@ -255,6 +257,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
     }
     if (const char *v = std::getenv("B200OLS_VARIANT")) c->variant = std::atoi(v);  // test hook: force a Gram kernel variant
     if (const char *v = std::getenv("B200OLS_MULTI")) c->multi_enabled = std::atoi(v) != 0;
+    if (const char *v = std::getenv("B200OLS_PRED")) c->pred_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_FUSE_MIN_BYTES")) c->fuse_min_bytes = std::atoll(v);  // test hook: fused-solve threshold
     if (c->variant < 0 || c->variant > 3) c->variant = 3;
     *out = c;
@@ -1374,8 +1377,47 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         gp.peer_group_base = c->peer_group_base;
     }
 
+    // mode = predictions | residuals with whole groups per tile: ONE kernel (gram_pred.cuh) keeps the tile in shared
+    // memory until beta is known and predicts from it, so the features are read from HBM once instead of twice
+    bool pred_fused = false;
+    double *dout = out->values;
+    uint8_t *dval = out->validity;
+    if (mode != B200OLS_COEFFICIENTS && f->memspace == B200OLS_HOST) {
+        dout = arena_alloc<double>(c, static_cast<size_t>(N));
+        dval = out->validity ? arena_alloc<uint8_t>(c, static_cast<size_t>(N)) : nullptr;
+    }
+    if (mode != B200OLS_COEFFICIENTS && !stats && c->variant == 3 && c->pred_enabled && gp.fused && !st.prepped && !st.mask &&
+        !st.row_index && !rt.svd_all && st.max_group_rows <= 8192) {
+        const int KBp = (F + 7) / 8;
+        const int NCp = st.kd + 1 + st.has_w;
+        const int R = static_cast<int>(std::max<int64_t>((st.max_group_rows + 7) / 8 * 8, 64));
+        const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
+        const size_t fixed = st.esz == 8 ? pred_fixed_smem<double>(KBp, F) : pred_fixed_smem<float>(KBp, F);
+        const size_t sb = static_cast<size_t>(NCp) * (st.esz == 8 ? gram_col_stride<double>(R) : gram_col_stride<float>(R));
+        int S = budget > fixed ? static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, (budget - fixed) / sb)) : 0;
+        if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));  // sweep hook, as for gram_cta
+        if (S >= 2) {
+            pred_fused = true;
+            gp.tile_rows = R;
+            gp.stages = S;
+            PredOut po{dout, mode == B200OLS_RESIDUALS ? 1 : 0};
+            const size_t smem = static_cast<size_t>(S) * sb + fixed;
+            const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, gp.nseg));
+            ARENA_GUARD(c);
+            if (dval) CU(cudaMemsetAsync(dval, 1, static_cast<size_t>(N), c->stream));  // null-free frame: every row is valid
+            {
+                ProfScope prof(c);
+                CU(st.esz == 8 ? gram_pred_launch_f64(KBp, gp, po, static_cast<unsigned>(grid), smem, c->stream)
+                               : gram_pred_launch_f32(KBp, gp, po, static_cast<unsigned>(grid), smem, c->stream));
+            }
+            c->launches++;
+        }
+    }
+
     ARENA_GUARD(c);
-    if (f->dtype == B200OLS_F64) TRY(launch_gram<double>(c, gp)); else TRY(launch_gram<float>(c, gp));
+    if (!pred_fused) {
+        if (f->dtype == B200OLS_F64) TRY(launch_gram<double>(c, gp)); else TRY(launch_gram<float>(c, gp));
+    }
 
     if (!gp.fused) {
         SolveParams sp;
@@ -1537,15 +1579,13 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     pr.beta = beta;
     pr.row_index = st.row_index;
     pr.residuals = mode == B200OLS_RESIDUALS;
-    double *dout = out->values;
-    uint8_t *dval = out->validity;
-    if (f->memspace == B200OLS_HOST) {
-        dout = arena_alloc<double>(c, static_cast<size_t>(N));
-        dval = out->validity ? arena_alloc<uint8_t>(c, static_cast<size_t>(N)) : nullptr;
-    }
     pr.out = dout;
     pr.out_valid = dval;
-    {
+    if (pred_fused) {  // only the groups whose beta was re-solved after the fused kernel (pivoted QR / min-norm SVD) are redone
+        pr.flags = flags;
+        pr.only_flags = FLAG_QR | FLAG_SVD;
+    }
+    if (!pred_fused || rt.ols_qr_guard || rt.svd_wide) {
         const int64_t warps_needed = (N + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
         const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
         if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);

@@ -1,0 +1,7 @@
+// pred_f64.cu — f64 instantiations of the fused Gram -> solve -> predict kernel (gram_pred.cuh)
+#include "gram_pred.cuh"
+namespace b200 {
+cudaError_t gram_pred_launch_f64(int KB, const GramParams &p, const PredOut &po, unsigned grid, size_t smem, cudaStream_t s) {
+    return KB == 1 ? gram_pred_launch_t<double, 1>(p, po, grid, smem, s) : gram_pred_launch_t<double, 2>(p, po, grid, smem, s);
+}
+}  // namespace b200

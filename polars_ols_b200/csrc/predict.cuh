@@ -27,6 +27,8 @@ struct PredictParams {
     const int32_t *seg_group;
     const double *beta;               // [n_groups][F]  (group stride `beta_stride` doubles when != 0)
     int64_t beta_stride;              // multi-target: coefficients of target t live at beta + t*F, stride n_targets*F
+    const int32_t *flags;             // [n_groups] or nullptr
+    int only_flags;                   // != 0: only rows of groups with (flags & only_flags) are (re)written
     int nan_is_null;                  // multi-target: a NaN prediction is a null (convert_array_to_struct_series fill_nan)
     const int64_t *row_index;         // packed -> original row, or nullptr
     int target_is_packed;             // target pointer is indexed by packed position (cleaned copy)
@@ -40,7 +42,8 @@ template <> struct PV<double> { using type = double2; static constexpr int N = 2
 template <> struct PV<float> { using type = float4; static constexpr int N = 4; };
 
 template <typename T>
-__device__ __forceinline__ void predict_store(const PredictParams &p, int64_t r, double acc, T s) {
+__device__ __forceinline__ void predict_store(const PredictParams &p, int64_t r, double acc, T s, int64_t group) {
+    if (p.only_flags && !(p.flags[group] & p.only_flags)) return;
     if (p.has_w) acc *= static_cast<double>(T(1) / s);  // predictions *= 1.0 / sqrt_w
     const int64_t orow = p.row_index ? p.row_index[r] : r;
     bool valid = true;
@@ -62,7 +65,7 @@ __device__ __forceinline__ T predict_scale(const PredictParams &p, T w) {
 
 // one row (vector tails and rows of a vector that straddle a group boundary)
 template <typename T>
-__device__ __forceinline__ void predict_row(const PredictParams &p, int64_t r, const double *beta) {
+__device__ __forceinline__ void predict_row(const PredictParams &p, int64_t r, const double *beta, int64_t group) {
     const int kd = p.kd;
     T s = T(1);
     if (p.has_w) s = predict_scale<T>(p, static_cast<const T *>(p.cols[kd])[r]);
@@ -73,7 +76,7 @@ __device__ __forceinline__ void predict_row(const PredictParams &p, int64_t r, c
         acc = fma(static_cast<double>(static_cast<T>(x * s)), __ldg(beta + j), acc);
     }
     if (p.intercept) acc = fma(static_cast<double>(s), __ldg(beta + kd), acc);
-    predict_store<T>(p, r, acc, s);
+    predict_store<T>(p, r, acc, s, group);
 }
 
 template <typename T>
@@ -99,12 +102,14 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
         }
         int64_t seg = lo;
         int64_t seg_end = p.seg_off[seg + 1];
-        const double *beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * bs;
+        int64_t grp = p.seg_group ? p.seg_group[seg] : seg;
+        const double *beta = p.beta + grp * bs;
         for (; r < c1; r += 32 * VN) {
             while (r >= seg_end) {
                 ++seg;
                 seg_end = p.seg_off[seg + 1];
-                beta = p.beta + (p.seg_group ? p.seg_group[seg] : seg) * bs;
+                grp = p.seg_group ? p.seg_group[seg] : seg;
+                beta = p.beta + grp * bs;
             }
             if (r + VN <= c1 && r + VN <= seg_end) {
                 // whole vector inside one group: 16-byte loads, beta_j loaded once for the VN rows
@@ -132,17 +137,18 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
                     for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(sv[v]), b, acc[v]);
                 }
 #pragma unroll
-                for (int v = 0; v < VN; ++v) predict_store<T>(p, r + v, acc[v], sv[v]);
+                for (int v = 0; v < VN; ++v) predict_store<T>(p, r + v, acc[v], sv[v], grp);
             } else {
-                int64_t sg = seg, se = seg_end;
+                int64_t sg = seg, se = seg_end, gg = grp;
                 const double *bb = beta;
                 for (int v = 0; v < VN && r + v < c1; ++v) {
                     while (r + v >= se) {
                         ++sg;
                         se = p.seg_off[sg + 1];
-                        bb = p.beta + (p.seg_group ? p.seg_group[sg] : sg) * bs;
+                        gg = p.seg_group ? p.seg_group[sg] : sg;
+                        bb = p.beta + gg * bs;
                     }
-                    predict_row<T>(p, r + v, bb);
+                    predict_row<T>(p, r + v, bb, gg);
                 }
             }
         }

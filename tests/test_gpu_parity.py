@@ -767,3 +767,60 @@ def test_multi_target_weights_intercept_rank_deficient_and_wide():
         pls.compute_multi_target_least_squares("ys", *names, ols_kwargs=OLSKwargs(l1_ratio=0.5, alpha=0.1))
     with pytest.raises(NotImplementedError):
         pls.compute_multi_target_least_squares("ys", *names, mode="coefficients")
+
+
+# ----------------------------------------------------------------------------------- fused Gram -> solve -> predict kernel
+@pytest.mark.parametrize("dtype,k,n_groups,model,kw,weights,intercept", [
+    (np.float64, 8, 40, "ridge", {"alpha": 1e-3}, False, False),                 # C2 shape (predictions / residuals)
+    (np.float64, 3, 7, "ols", {}, False, True),                                  # default OLS: QR guard + restricted re-predict
+    (np.float64, 13, 25, "ridge", {"alpha": 0.1, "solve_method": "lu"}, True, True),
+    (np.float32, 16, 30, "ridge", {"alpha": 0.5}, True, False),                  # C3 dtype, KB = 2
+    (np.float64, 5, 300, "ols", {"solve_method": "chol"}, True, False),          # short ragged groups
+])
+@pytest.mark.parametrize("mode", ["predictions", "residuals"])
+def test_fused_predict_kernel(dtype, k, n_groups, model, kw, weights, intercept, mode, monkeypatch):
+    """gram_pred.cuh (one pass) against the two-pass route (B200OLS_PRED=0) and the oracle.  B200OLS_FUSE_MIN_BYTES=0
+    makes the fused route eligible for these small groups; stage counts 2 and 3+ are both exercised."""
+    from polars_ols_b200 import _lib as L
+    rng = np.random.default_rng(k)
+    sizes = rng.integers(8, 200, size=n_groups) if n_groups >= 300 else rng.integers(200, 1000 if k <= 8 else 400, size=n_groups)
+    sizes[1] = 0                                                                # an empty group
+    n = int(sizes.sum())                                                        # no group above 1024 rows: the plan never splits one
+    d = _make_data(n, k, seed=100 + k, dtype=dtype)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    gid = np.repeat(np.arange(n_groups), sizes)
+    if model == "ols" and not kw:                                               # one nearly collinear group -> flagged, re-solved by QR
+        sl = slice(offsets[2], offsets[3])
+        d["x2"][sl] = d["x1"][sl] * (1.0 + 1e-9 * rng.normal(size=sizes[2]))
+    names = _xs(d)
+    w = rng.uniform(0.2, 3.0, size=n).astype(dtype) if weights else None
+    mk = lambda: pls.Batch(pls.as_col(d["y"]), [pls.as_col(d[nm]) for nm in names], None if w is None else pls.as_col(w),  # noqa: E731
+                           add_intercept=intercept, offsets=offsets)
+    okw = dict(kw)
+    if model == "ridge":
+        okw["l1_ratio"] = 0.0
+    ckw = OLSKwargs(**okw).to_c()
+    monkeypatch.setenv("B200OLS_FUSE_MIN_BYTES", "0")
+    res = {}
+    for pred, stages in (("1", 0), ("1", 2), ("0", 0)):
+        monkeypatch.setenv("B200OLS_PRED", pred)
+        eng = pls.Engine(0)
+        eng.set_tuning(0, stages, 0)
+        n0 = eng.launch_count
+        v, m = eng.least_squares(mk(), ckw, L.MODE[mode])
+        res[(pred, stages)] = (v.copy(), m.copy(), eng.launch_count - n0)
+        eng.close()
+    ref = S.over(S.least_squares, gid, d["y"], *_oracle_cols(d, names), sample_weights=w, add_intercept=intercept, mode=mode,
+                 kwargs=S.OLSKwargs(**okw))
+    tol = dict(rtol=1e-6, atol=1e-8) if dtype == np.float64 else dict(rtol=1e-4, atol=1e-4)
+    if model == "ols" and not kw:
+        tol = dict(rtol=1e-5, atol=1e-6)                                        # the collinear group: cond ~ 1e9
+    for key, (v, m, launches) in res.items():
+        assert m.all()
+        _close(v, _ref(ref), **tol)
+    if model == "ols" and not kw:                                               # QR guard: the flagged groups are re-predicted
+        assert res[("1", 0)][2] <= res[("0", 0)][2]
+    else:
+        assert res[("1", 0)][2] < res[("0", 0)][2]                              # fewer launches: no separate predict pass
+    np.testing.assert_allclose(res[("1", 0)][0], res[("0", 0)][0], rtol=1e-9 if dtype == np.float64 else 1e-5, atol=1e-9)
+    np.testing.assert_array_equal(res[("1", 0)][0], res[("1", 2)][0])           # stage count does not change the arithmetic
