@@ -86,6 +86,7 @@ struct b200ols_ctx {
     int64_t launches = 0;
     int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
     bool multi_enabled = true;      // test hook B200OLS_MULTI=0: never use gram_multi_kernel
+    int pred_lag = 4;               // test hook B200OLS_PRED_LAG: groups the stream may run ahead of the predictions (per SM)
     bool pred_enabled = true;       // test hook B200OLS_PRED=0: never use the fused Gram -> solve -> predict kernel
     long long fuse_min_bytes = -1;  // < 0: default; test hook B200OLS_FUSE_MIN_BYTES (0 = always fuse the solve)
     int variant = 3, unroll = 0;  // Gram kernel variant (b200ols_set_variant); 3 = CTA-cooperative TMA pipeline
@@ -258,6 +259,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
     if (const char *v = std::getenv("B200OLS_VARIANT")) c->variant = std::atoi(v);  // test hook: force a Gram kernel variant
     if (const char *v = std::getenv("B200OLS_MULTI")) c->multi_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_PRED")) c->pred_enabled = std::atoi(v) != 0;
+    if (const char *v = std::getenv("B200OLS_PRED_LAG")) c->pred_lag = std::max(1, std::atoi(v));
     if (const char *v = std::getenv("B200OLS_FUSE_MIN_BYTES")) c->fuse_min_bytes = std::atoll(v);  // test hook: fused-solve threshold
     if (c->variant < 0 || c->variant > 3) c->variant = 3;
     *out = c;
@@ -1400,7 +1402,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
             pred_fused = true;
             gp.tile_rows = R;
             gp.stages = S;
-            PredOut po{dout, mode == B200OLS_RESIDUALS ? 1 : 0};
+            PredOut po{dout, mode == B200OLS_RESIDUALS ? 1 : 0, c->pred_lag};
             const size_t smem = static_cast<size_t>(S) * sb + fixed;
             const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(c->sm_count, gp.nseg));
             ARENA_GUARD(c);

@@ -2,62 +2,72 @@
 // shared-memory tile (k <= 16, null-free contiguous groups): Gram -> solve -> predictions, every input byte read from
 // HBM once.
 //
-// The two-pass route (gram_cta_kernel, then predict_kernel) reads the features twice: 72 KB + 64 KB per C2 group for
-// 8 KB of output.  Here the group's tile STAYS in shared memory until its coefficients are known and the predictions
+// The two-pass route (gram_cta_kernel, then predict_kernel) reads the features from HBM twice: 72 KB + 64 KB per C2
+// group for 8 KB of output.  Here the group's predictions
 //   make_predictions          src/expressions.rs:175-195   (features . coefficients)
 //   predictions *= 1/sqrt_w   polars_ols/least_squares.py:234-235
 //   residuals = target - pred polars_ols/least_squares.py:238-239
-// are computed straight from it — algorithmic bytes n (k + 1) s in + 8 n out.
+// are computed inside the streaming kernel as soon as its coefficients are known, re-reading the group's rows with
+// plain 16-byte loads while they are still in L2 (they went through it a few microseconds earlier on their way to
+// shared memory) — DRAM traffic n (k + 1) s in + 8 n out (ncu: dram read = 1.00 x the input bytes).
 //
-// Same role split as gram_cta.cuh around mbarrier rings, with one more hand-off:
-//   warp 0         PRODUCER  one tile == one group (1-D bulk async copies per column, `full` mbarrier)
-//   warps 1..8     CONSUMERS Gram of group i (DMMA, as gram_cta); they only publish, they never release a stage
-//   warps 9..12    SOLVERS   sum the published fragments, register Cholesky (LU fallback), beta -> HBM and -> the
-//                            stage's shared beta slot, `beta` mbarrier
-//   warps 13..16   PREDICTORS wait for `beta`, compute the group's predictions from the tile (two rows per lane and
-//                            step, 16-byte shared loads and global stores) and release the stage (`empty`).  A first
-//                            version let the consumers predict group i-1 after the Gram of group i: the stage was
-//                            then held until the NEXT group had landed and the copy engine idled (0.24 ms for C2).
-// A stage is held for load + Gram + solve + predict (~5 us for a C2 group), so three stages are needed to keep the
-// copy engine busy; to make them fit next to 3 x 73 KB of tiles the eight consumer warps do not publish eight
-// fragment sets (8 KB per ring entry) but accumulate them IN PLACE, in fixed order inside each half of four warps
-// (named barriers), into two 1 KB half-sums that the solver adds — deterministic, 2 KB per ring entry.
+// Role split (gram_cta.cuh's pipeline plus one more role), 24 warps (k <= 8) or 16:
+//   warp 0         PRODUCER   one tile == one group (1-D bulk async copies per column, `full` mbarrier); THROTTLED:
+//                             group i is loaded only when group i - lag has been predicted, so that the rows a
+//                             predictor re-reads are still in L2 (chip-wide footprint ~ 148 x lag x 73 KB)
+//   warps 1..8     CONSUMERS  Gram of the group (DMMA, as gram_cta), release the stage, publish their fragments
+//   warps 9..12    SOLVERS    (round-robin over groups) sum the fragments in fixed order, register Cholesky (LU
+//                             fallback), beta -> HBM and -> the group's shared beta slot, `beta` mbarrier
+//   warps 13..     PREDICTORS all work on one group at a time, in order: two rows per lane and load, straight from
+//                             L2; streaming (evict-first) stores.  Each publishes its progress; the producer
+//                             throttles on the slowest one (and a beta slot is reused only 16 groups later)
+// What was tried first (profiles/r01_pred_ncu.txt): keeping the tile in shared memory until beta is known (consumers
+// or dedicated warps predicting from it) holds a stage for load + Gram + solve + predict ~ 9 us, and with the three
+// 73 KB stages that fit the copy engine idles (0.24 / 0.22 ms for C2, no better than two passes); predicting in the
+// solver warp from L2 without the throttle lets the stream run a whole ring (~100 MB) ahead: 4 % L2 hits, 1.8 x DRAM.
 #pragma once
 #include "gram_cta.cuh"
 
 namespace b200 {
 
-constexpr int PRED_DEPTH = CTA_SOLVERS;  // ring of published half-sums; >= CTA_SOLVERS (parity waits, see gram_cta.cuh)
-constexpr int PRED_WARPS = 4;            // predictor warps
-constexpr int PRED_THREADS = CTA_THREADS + PRED_WARPS * 32;
+// predictor warps: their loads are L2 round trips (~0.4 us under load), so what counts is how many are in flight —
+// k <= 8: 11 warps x 8 loads per lane (24 warps, 80 registers each); k <= 16: 3 warps (16 warps, 128 registers)
+__host__ __device__ constexpr int pred_predictors(int KB) { return KB == 1 ? 11 : 3; }
+__host__ __device__ constexpr int pred_threads(int KB) { return (1 + CTA_CONSUMERS + CTA_SOLVERS + pred_predictors(KB)) * 32; }
+constexpr int PRED_MAX_PREDICTORS = 11;
+constexpr int PRED_DEPTH = CTA_SOLVERS;  // ring of published fragment sets; == CTA_SOLVERS (parity waits, see gram_cta.cuh)
+constexpr int PRED_SLOTS = 16;           // ring of beta slots; > max lag, so a slot is never rewritten before it was read
+constexpr int PRED_MAX_LAG = 12;
 
 struct PredOut {
     double *out;    // [n_rows] (groups are contiguous, packed order == original order)
     int residuals;  // 1: target - prediction
+    int lag;        // the producer loads group i only when groups <= i - lag are finished (bounds the L2 footprint)
 };
+
+template <int KB>
+__host__ __device__ constexpr int pred_red_doubles() { return KB * (KB + 1) + KB; }  // acc fragments + cy
 
 template <typename T>
 __host__ __device__ inline size_t pred_fixed_smem(int KB, int F) {
-    const size_t red = static_cast<size_t>(PRED_DEPTH) * 2 * 32 * (KB * (KB + 1) + KB) * sizeof(double);
-    return red + CTA_SOLVERS * gram_scratch_bytes<T>(F, 1) + GRAM_MAX_STAGES * 16 * sizeof(double) + 128;
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+    const size_t red = static_cast<size_t>(PRED_DEPTH) * CTA_CONSUMERS * 32 * (KB * (KB + 1) + KB) * sizeof(double);
+    return red + CTA_SOLVERS * gram_scratch_bytes<T>(F, 1) + PRED_SLOTS * 16 * sizeof(double) + 128;
 }
 
 template <typename T, int KB>
-__global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramParams p, const PredOut po) {
+__global__ void __launch_bounds__(pred_threads(KB), 1) gram_pred_kernel(const GramParams p, const PredOut po) {
     using Vec = typename V2<T>::type;
     constexpr int NPAIR = KB * (KB + 1) / 2;
     constexpr int A = 16 / sizeof(T);
     constexpr int W = CTA_CONSUMERS;
-    constexpr int RED = KB * (KB + 1) + KB;  // acc fragments + cy (the row count is the group length: no mask here)
+    constexpr int RED = pred_red_doubles<KB>();
     constexpr bool DUAL = KB <= 2;
+    constexpr int NP = pred_predictors(KB);
 
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES], beta_bar[GRAM_MAX_STAGES], red_full[PRED_DEPTH],
-        red_empty[PRED_DEPTH];
+    __shared__ uint64_t full_bar[GRAM_MAX_STAGES], empty_bar[GRAM_MAX_STAGES], red_full[PRED_DEPTH], red_empty[PRED_DEPTH],
+        beta_bar[PRED_SLOTS];
+    __shared__ unsigned int progress[PRED_MAX_PREDICTORS];  // groups finished by each predictor warp (they may drift apart)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fb = lane >> 2, q = lane & 3;
@@ -68,19 +78,20 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramPa
     const uint32_t stride = gram_col_stride<T>(R);
     const uint32_t stage_bytes = static_cast<uint32_t>(NC) * stride;
     double *red = reinterpret_cast<double *>(smem + static_cast<size_t>(S) * stage_bytes);
-    double *Gs_base = red + PRED_DEPTH * 2 * 32 * RED;
+    double *Gs_base = red + PRED_DEPTH * W * 32 * RED;
     double *beta_s = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(Gs_base) + CTA_SOLVERS * gram_scratch_bytes<T>(F, 1));
 
     if (threadIdx.x == 0) {
+        for (int i = 0; i < PRED_MAX_PREDICTORS; ++i) progress[i] = 0;
         for (int s = 0; s < S; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], PRED_WARPS);
-            mbar_init(&beta_bar[s], 1);
+            mbar_init(&empty_bar[s], W);
         }
         for (int b = 0; b < PRED_DEPTH; ++b) {
-            mbar_init(&red_full[b], 2);
+            mbar_init(&red_full[b], W);
             mbar_init(&red_empty[b], 1);
         }
+        for (int b = 0; b < PRED_SLOTS; ++b) mbar_init(&beta_bar[b], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -90,17 +101,25 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramPa
     if (warp == 0) {
         // ================================ PRODUCER: one (possibly empty) tile per group ================================
         int stage = 0;
-        uint32_t phase = 0;
+        uint32_t phase = 0, li = 0;
+        const uint32_t lag = po.lag < 1 ? 1u : (po.lag > PRED_MAX_LAG ? static_cast<uint32_t>(PRED_MAX_LAG) : static_cast<uint32_t>(po.lag));
         int64_t nr0 = 0, nr1 = 0;
         if (static_cast<int64_t>(blockIdx.x) < nseg) { nr0 = p.seg_off[blockIdx.x]; nr1 = p.seg_off[blockIdx.x + 1]; }
-        for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x, ++li) {
+            if (li >= lag) {  // throttle (see the header): every predictor warp has finished group li - lag
+                for (;;) {
+                    const unsigned int pr = (lane < NP) ? *reinterpret_cast<volatile unsigned int *>(&progress[lane]) : 0xffffffffu;
+                    if (__all_sync(0xffffffffu, pr >= li - lag + 1)) break;
+                    __nanosleep(20);
+                }
+            }
             const int64_t r0 = nr0, r1 = nr1;
             if (seg + gridDim.x < nseg) { nr0 = p.seg_off[seg + gridDim.x]; nr1 = p.seg_off[seg + gridDim.x + 1]; }
             const int64_t a_al = r0 & ~static_cast<int64_t>(A - 1);
             int64_t b_al = (r1 + (A - 1)) & ~static_cast<int64_t>(A - 1);
             if (b_al > p.n_rows_pad) b_al = p.n_rows_pad;
             const uint32_t bytes = (r1 > r0) ? static_cast<uint32_t>(b_al - a_al) * sizeof(T) : 0u;
-            mbar_wait(&empty_bar[stage], phase ^ 1u);  // predictions of the previous tenant are stored
+            mbar_wait(&empty_bar[stage], phase ^ 1u);  // all consumers released this stage
             unsigned char *sb = smem + static_cast<size_t>(stage) * stage_bytes;
             if (lane == 0) {
                 fence_proxy_async_smem();
@@ -117,15 +136,15 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramPa
         }
     } else if (warp <= W) {
         // ================================ CONSUMERS ================================
-        const int cw = warp - 1, half = cw >> 2, pos = cw & 3;
+        const int cw = warp - 1;
         int64_t nr0 = 0, nr1 = 0;
         if (static_cast<int64_t>(blockIdx.x) < nseg) { nr0 = p.seg_off[blockIdx.x]; nr1 = p.seg_off[blockIdx.x + 1]; }
-        uint32_t li = 0;            // CTA-local group index
-
+        uint32_t li = 0;  // CTA-local group index
+        int stage = 0;
+        uint32_t phase = 0;
         for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x, ++li) {
             const int64_t r0 = nr0, r1 = nr1;
             if (seg + gridDim.x < nseg) { nr0 = p.seg_off[seg + gridDim.x]; nr1 = p.seg_off[seg + gridDim.x + 1]; }
-            const int stage = static_cast<int>(li % S);
             double acc[NPAIR][2], acc2[DUAL ? NPAIR : 1][2];
             double cy[KB];
 #pragma unroll
@@ -141,7 +160,7 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramPa
             const int per = (noct + W - 1) / W;
             const int j0 = cw * per;
             const int j1 = (j0 + per < noct) ? j0 + per : noct;
-            mbar_wait(&full_bar[stage], (li / S) & 1u);
+            mbar_wait(&full_bar[stage], phase);
             const unsigned char *sb = smem + static_cast<size_t>(stage) * stage_bytes;
             const unsigned char *xs[KB];
             bool has_x[KB];
@@ -202,32 +221,45 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramPa
                 }
                 const int jfull = hi >> 3;  // octets below jfull lie entirely inside [o, hi)
                 const int jend = (j1 < jfull) ? j1 : jfull;
+                if (!p.has_w) {  // no scaling: x * 1 is exact, skip the multiplies (as gram_cta's interior loop)
 #pragma unroll 4
-                for (; j < jend; ++j) octet(j, false);
+                    for (; j < jend; ++j) {
+                        const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
+                        double f0[KB], f1[KB];
+#pragma unroll
+                        for (int bk = 0; bk < KB; ++bk) {
+                            const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
+                            f0[bk] = has_x[bk] ? static_cast<double>(x2.x) : xconst[bk];
+                            f1[bk] = has_x[bk] ? static_cast<double>(x2.y) : xconst[bk];
+                        }
+                        mma_octet(f0, f1, static_cast<double>(y2.x), static_cast<double>(y2.y));
+                    }
+                } else {
+#pragma unroll 2
+                    for (; j < jend; ++j) octet(j, false);
+                }
                 for (; j < j1; ++j) octet(j, true);
             }
-
-            // ---- publish: in-place accumulation inside each half of four warps, fixed order (deterministic) ----
-            const int buf = static_cast<int>(li % PRED_DEPTH);
-            double *entry = red + static_cast<size_t>(buf * 2 + half) * 32 * RED;
-            if (pos == 0) mbar_wait(&red_empty[buf], ((li / PRED_DEPTH) & 1u) ^ 1u);
-#pragma unroll
-            for (int step = 0; step < 4; ++step) {
-                if (pos == step) {
-#pragma unroll
-                    for (int i = 0; i < NPAIR; ++i) {
-                        const double a0 = DUAL ? acc[i][0] + acc2[i][0] : acc[i][0];
-                        const double a1 = DUAL ? acc[i][1] + acc2[i][1] : acc[i][1];
-                        entry[(2 * i) * 32 + lane] = (step == 0) ? a0 : entry[(2 * i) * 32 + lane] + a0;
-                        entry[(2 * i + 1) * 32 + lane] = (step == 0) ? a1 : entry[(2 * i + 1) * 32 + lane] + a1;
-                    }
-#pragma unroll
-                    for (int i = 0; i < KB; ++i)
-                        entry[(2 * NPAIR + i) * 32 + lane] = (step == 0) ? cy[i] : entry[(2 * NPAIR + i) * 32 + lane] + cy[i];
-                }
-                named_bar_sync(1 + half, 128);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1u;
             }
-            if (pos == 3 && lane == 0) mbar_arrive(&red_full[buf]);
+
+            // ---- publish this warp's partial fragments (ring of PRED_DEPTH sets of W slots) ----
+            const int buf = static_cast<int>(li % PRED_DEPTH);
+            mbar_wait(&red_empty[buf], ((li / PRED_DEPTH) & 1u) ^ 1u);
+            double *slot = red + (static_cast<size_t>(buf) * W + cw) * 32 * RED;
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) {
+                slot[(2 * i) * 32 + lane] = DUAL ? acc[i][0] + acc2[i][0] : acc[i][0];
+                slot[(2 * i + 1) * 32 + lane] = DUAL ? acc[i][1] + acc2[i][1] : acc[i][1];
+            }
+#pragma unroll
+            for (int i = 0; i < KB; ++i) slot[(2 * NPAIR + i) * 32 + lane] = cy[i];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&red_full[buf]);
         }
     } else if (warp <= W + CTA_SOLVERS) {
         // ================================ SOLVERS ================================
@@ -239,65 +271,59 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramPa
             const int buf = static_cast<int>(li % PRED_DEPTH);
             mbar_wait(&red_full[buf], (li / PRED_DEPTH) & 1u);
             double acc[NPAIR][2], cy[KB];
-            const double *e0 = red + static_cast<size_t>(buf * 2) * 32 * RED, *e1 = e0 + 32 * RED;
 #pragma unroll
-            for (int i = 0; i < NPAIR; ++i) {
-                acc[i][0] = e0[(2 * i) * 32 + lane] + e1[(2 * i) * 32 + lane];
-                acc[i][1] = e0[(2 * i + 1) * 32 + lane] + e1[(2 * i + 1) * 32 + lane];
+            for (int i = 0; i < NPAIR; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+            for (int i = 0; i < KB; ++i) cy[i] = 0.0;
+            for (int cw = 0; cw < W; ++cw) {  // fixed order: deterministic sums
+                const double *slot = red + (static_cast<size_t>(buf) * W + cw) * 32 * RED;
+#pragma unroll
+                for (int i = 0; i < NPAIR; ++i) {
+                    acc[i][0] += slot[(2 * i) * 32 + lane];
+                    acc[i][1] += slot[(2 * i + 1) * 32 + lane];
+                }
+#pragma unroll
+                for (int i = 0; i < KB; ++i) cy[i] += slot[(2 * NPAIR + i) * 32 + lane];
             }
-#pragma unroll
-            for (int i = 0; i < KB; ++i) cy[i] = e0[(2 * NPAIR + i) * 32 + lane] + e1[(2 * NPAIR + i) * 32 + lane];
             __syncwarp();
             if (lane == 0) mbar_arrive(&red_empty[buf]);
             const int nfit = (lane == 0) ? static_cast<int>(p.seg_off[seg + 1] - p.seg_off[seg]) : 0;
-            gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane);  // beta -> HBM (+ flags), as gram_cta
-            const int stage = static_cast<int>(li % S);
-            if (lane < F) beta_s[stage * 16 + lane] = p.beta[seg * F + lane];  // this lane's own store
+            double bl = 0.0;
+            gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane, &bl);  // beta -> HBM (+ flags), as gram_cta; lane i keeps beta_i
+            const int bslot = static_cast<int>(li % PRED_SLOTS);
+            if (lane < 16) beta_s[bslot * 16 + lane] = (lane < F) ? bl : 0.0;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&beta_bar[stage]);
+            if (lane == 0) mbar_arrive(&beta_bar[bslot]);
         }
     } else {
         // ================================ PREDICTORS ================================
         const int pw = warp - (W + CTA_SOLVERS + 1);
+        const int pl = pw * 32 + lane;
+        constexpr int PL = NP * 32;
         const bool out_al = (reinterpret_cast<uintptr_t>(po.out) & 15u) == 0;
+        const T *ycol_g = static_cast<const T *>(p.cols[ycol]);
+        const T *wcol_g = static_cast<const T *>(p.cols[p.has_w ? wcol : ycol]);
         int64_t nr0 = 0, nr1 = 0;
         if (static_cast<int64_t>(blockIdx.x) < nseg) { nr0 = p.seg_off[blockIdx.x]; nr1 = p.seg_off[blockIdx.x + 1]; }
         uint32_t li = 0;
         for (int64_t seg = blockIdx.x; seg < nseg; seg += gridDim.x, ++li) {
             const int64_t r0 = nr0, r1 = nr1;
             if (seg + gridDim.x < nseg) { nr0 = p.seg_off[seg + gridDim.x]; nr1 = p.seg_off[seg + gridDim.x + 1]; }
-            const int stage = static_cast<int>(li % S);
-            const uint32_t par = (li / S) & 1u;
-            mbar_wait(&beta_bar[stage], par);
-            mbar_wait(&full_bar[stage], par);  // completed long ago; orders this warp's reads after the bulk copies
-            const unsigned char *sb = smem + static_cast<size_t>(stage) * stage_bytes;
-            const double *bs = beta_s + stage * 16;
+            const int bslot = static_cast<int>(li % PRED_SLOTS);
+            mbar_wait(&beta_bar[bslot], (li / PRED_SLOTS) & 1u);
             double beta[8 * KB];
 #pragma unroll
-            for (int c = 0; c < 8 * KB; ++c) beta[c] = (c < F) ? bs[c] : 0.0;
-            const double b_int = p.intercept ? bs[kd] : 0.0;
+            for (int c = 0; c < 8 * KB; ++c) beta[c] = beta_s[bslot * 16 + c];
+            const double b_int = p.intercept ? beta_s[bslot * 16 + kd] : 0.0;
+
             const int o = static_cast<int>(r0 & (A - 1));
             const int hi = o + static_cast<int>(r1 - r0);  // valid local rows are [o, hi)
-            const int64_t a_al = r0 - o;
+            const int64_t a_al = r0 - o;                   // multiple of A >= 2: vector loads / stores are aligned
             const int npair = (hi + 1) >> 1;
-            for (int pp = pw * 32 + lane; pp < npair; pp += PRED_WARPS * 32) {
+            // intercept, un-scaling, residual and the store of one row pair
+            auto emit = [&](int pp, double a0, double a1, T s0, T s1, Vec y2) {
                 const int lr = 2 * pp;
                 const bool v0 = lr >= o && lr < hi, v1 = lr + 1 >= o && lr + 1 < hi;
-                const size_t off = static_cast<size_t>(lr) * sizeof(T);
-                T s0 = T(1), s1 = T(1);
-                if (p.has_w) {
-                    const Vec w2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(wcol) * stride + off);
-                    s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                    s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
-                }
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < 8 * KB; ++c)
-                    if (c < kd) {
-                        const Vec x2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(c) * stride + off);
-                        a0 = fma(static_cast<double>(static_cast<T>(x2.x * s0)), beta[c], a0);
-                        a1 = fma(static_cast<double>(static_cast<T>(x2.y * s1)), beta[c], a1);
-                    }
                 if (p.intercept) {
                     a0 = fma(static_cast<double>(s0), b_int, a0);
                     a1 = fma(static_cast<double>(s1), b_int, a1);
@@ -307,20 +333,74 @@ __global__ void __launch_bounds__(PRED_THREADS, 1) gram_pred_kernel(const GramPa
                     a1 *= static_cast<double>(T(1) / s1);
                 }
                 if (po.residuals) {
-                    const Vec y2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(ycol) * stride + off);
                     a0 = static_cast<double>(y2.x) - a0;
                     a1 = static_cast<double>(y2.y) - a1;
                 }
                 double *dst = po.out + a_al + lr;
                 if (v0 && v1 && out_al) {
-                    *reinterpret_cast<double2 *>(dst) = make_double2(a0, a1);
+                    __stcs(reinterpret_cast<double2 *>(dst), make_double2(a0, a1));
                 } else {
                     if (v0) dst[0] = a0;
                     if (v1) dst[1] = a1;
                 }
+            };
+            auto scales = [&](int pp, T &s0, T &s1) {
+                s0 = s1 = T(1);
+                if (p.has_w) {
+                    const Vec w2 = __ldg(reinterpret_cast<const Vec *>(wcol_g + a_al + 2 * pp));
+                    s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
+                    s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                }
+            };
+            int pp = pl;
+            if (NP == 3 && KB == 1) {  // (unused with 11 predictor warps) two loads deep
+                for (; pp + PL < npair; pp += 2 * PL) {
+                    Vec xa[8], xb[8], ya, yb;
+                    ya.x = ya.y = yb.x = yb.y = T(0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < kd) {
+                            xa[c] = __ldg(reinterpret_cast<const Vec *>(static_cast<const T *>(p.cols[c]) + a_al + 2 * pp));
+                            xb[c] = __ldg(reinterpret_cast<const Vec *>(static_cast<const T *>(p.cols[c]) + a_al + 2 * (pp + PL)));
+                        }
+                    if (po.residuals) {
+                        ya = __ldg(reinterpret_cast<const Vec *>(ycol_g + a_al + 2 * pp));
+                        yb = __ldg(reinterpret_cast<const Vec *>(ycol_g + a_al + 2 * (pp + PL)));
+                    }
+                    T sa0, sa1, sb0, sb1;
+                    scales(pp, sa0, sa1);
+                    scales(pp + PL, sb0, sb1);
+                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < kd) {
+                            a0 = fma(static_cast<double>(static_cast<T>(xa[c].x * sa0)), beta[c], a0);
+                            a1 = fma(static_cast<double>(static_cast<T>(xa[c].y * sa1)), beta[c], a1);
+                            b0 = fma(static_cast<double>(static_cast<T>(xb[c].x * sb0)), beta[c], b0);
+                            b1 = fma(static_cast<double>(static_cast<T>(xb[c].y * sb1)), beta[c], b1);
+                        }
+                    emit(pp, a0, a1, sa0, sa1, ya);
+                    emit(pp + PL, b0, b1, sb0, sb1, yb);
+                }
+            }
+            for (; pp < npair; pp += PL) {
+                T s0, s1;
+                scales(pp, s0, s1);
+                Vec y2;
+                y2.x = y2.y = T(0);
+                if (po.residuals) y2 = __ldg(reinterpret_cast<const Vec *>(ycol_g + a_al + 2 * pp));
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < 8 * KB; ++c)
+                    if (c < kd) {
+                        const Vec x2 = __ldg(reinterpret_cast<const Vec *>(static_cast<const T *>(p.cols[c]) + a_al + 2 * pp));
+                        a0 = fma(static_cast<double>(static_cast<T>(x2.x * s0)), beta[c], a0);
+                        a1 = fma(static_cast<double>(static_cast<T>(x2.y * s1)), beta[c], a1);
+                    }
+                emit(pp, a0, a1, s0, s1, y2);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (lane == 0) *reinterpret_cast<volatile unsigned int *>(&progress[pw]) = li + 1;
         }
     }
 }
@@ -336,7 +416,7 @@ cudaError_t gram_pred_launch_t(const GramParams &p, const PredOut &po, unsigned 
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = smem;
     }
-    kern<<<grid, PRED_THREADS, smem, s>>>(p, po);
+    kern<<<grid, pred_threads(KB), smem, s>>>(p, po);
     return cudaGetLastError();
 }
 

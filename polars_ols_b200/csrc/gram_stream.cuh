@@ -143,7 +143,7 @@ __device__ __forceinline__ bool warp_chol_solve(double (&g)[FP], double &c, int 
 // followed by X^T y.  Fused mode: solve and write beta; otherwise (direct-FMA kernel only) dump the raw
 // partial record for the standalone solve kernel.  nfit must be warp-uniform.
 template <int KB>
-__device__ __forceinline__ void gram_finish(const GramParams &p, int nfit, int64_t seg, double *Gs, int lane) {
+__device__ __forceinline__ void gram_finish(const GramParams &p, int nfit, int64_t seg, double *Gs, int lane, double *beta_out = nullptr) {
     constexpr int FP = 8 * KB;
     constexpr int LD = FP + 1;
     const int F = p.F;
@@ -198,6 +198,7 @@ __device__ __forceinline__ void gram_finish(const GramParams &p, int nfit, int64
         p.beta[g * F + lane] = ci;
         for (int r = 0; r < p.n_peers; ++r) p.peer_beta[r][(p.peer_group_base + g) * F + lane] = ci;  // fused gather
     }
+    if (beta_out) *beta_out = ci;  // lane i < F: beta_i (gram_pred.cuh predicts from it)
     __syncwarp();
 }
 
@@ -205,7 +206,7 @@ __device__ __forceinline__ void gram_finish(const GramParams &p, int nfit, int64
 // a feature, then either solve in shared memory (fused) or write the raw Gram partial.
 template <int KB>
 __device__ __forceinline__ void gram_epilogue(const GramParams &p, double (&acc)[KB * (KB + 1) / 2][2], double (&cy)[KB],
-                                              int nfit, int64_t seg, double *Gs, int lane) {
+                                              int nfit, int64_t seg, double *Gs, int lane, double *beta_out = nullptr) {
     constexpr int FP = 8 * KB;
     const int fb = lane >> 2, q = lane & 3;
     const int F = p.F;
@@ -240,7 +241,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams &p, double (&acc)
             if (q == 0) cs[8 * bi + fb] = cy[bi];
         }
         __syncwarp();
-        gram_finish<KB>(p, nfit, seg, Gs, lane);
+        gram_finish<KB>(p, nfit, seg, Gs, lane, beta_out);
     } else {
         double *out = p.partial + static_cast<size_t>(seg) * (static_cast<size_t>(F) * F + F + 1);
         int idx = 0;
