@@ -20,8 +20,10 @@ from .least_squares import (  # noqa: F401
     RLSKwargs,
     RollingKwargs,
     SolveMethod,
+    build_expressions_from_patsy_formula,
     col,
     compute_least_squares,
+    compute_least_squares_from_formula,
     compute_multi_target_least_squares,
     compute_recursive_least_squares,
     compute_rolling_least_squares,

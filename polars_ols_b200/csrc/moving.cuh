@@ -20,6 +20,16 @@
 
 namespace b200 {
 
+// The chunk walks are latency-bound (one thread per chunk, a dependent FP64 chain and a memory round trip per row):
+// throughput follows the number of resident warps, but only while the state stays in registers.  Measured on C4
+// (rolling, k = 6, 50M rows): 162 registers / 12 warps per SM 4.87 ms; forced to 128 registers / 16 warps
+// (MOVING_MIN_BLOCKS = 4, part of the Cholesky factor in local memory) 5.75 ms; 204 registers / 8 warps with the next
+// row's loads software-pipelined 6.7 ms.  So the default stays at one block minimum (no register cap).
+#ifndef MOVING_MIN_BLOCKS
+#define MOVING_MIN_BLOCKS 1
+#endif
+constexpr int MOVING_OCC_K = 6;
+
 struct MovingParams {
     const void *cols[GRAM_MAX_COLS];  // [0,kd) features, [kd] target (cleaned: zero filled)
     const void *w;                    // weights / sqrt-weights or nullptr
@@ -85,6 +95,7 @@ struct DevSrc {
         for (int j = 0; j < K; ++j) xo[j] = (j < kd) ? static_cast<double>(static_cast<T>(x[j][r] * s)) : static_cast<double>(s);
         yo = static_cast<double>(static_cast<T>(y[r] * s));
     }
+    __device__ __forceinline__ void prefetch(int64_t) const {}
 };
 
 template <typename T, int K>
@@ -127,6 +138,18 @@ struct DevSrcT {
 #pragma unroll
         for (int j = 0; j < K; ++j) xo[j] = (j < kd) ? static_cast<double>(static_cast<T>(x[j][t] * s)) : static_cast<double>(s);
         yo = static_cast<double>(static_cast<T>(y[t] * s));
+    }
+    // L1 prefetch hint for every column of row r (the chunk loops call it MOVING_PF rows ahead: a thread walks its
+    // chunk row by row and would otherwise pay one HBM / L2 round trip per row — ncu: long_scoreboard 5.2 of 6.2
+    // stalled warps per issue slot at 12 warps per SM)
+    __device__ __forceinline__ void prefetch(int64_t r) const {
+        const int64_t t = at(r);
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j < kd) asm volatile("prefetch.global.L1 [%0];" ::"l"(x[j] + t));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(y + t));
+        if (w) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + t));
+        if (mask) asm volatile("prefetch.global.L1 [%0];" ::"l"(mask + t));
     }
 };
 
@@ -185,17 +208,29 @@ struct DevEmit {
     const MovingParams &p;
     const SrcT &src;
     __device__ __forceinline__ void operator()(int64_t r, const double (&beta)[K], bool) const {
-        const int64_t orow = p.row_index ? p.row_index[r] : r;
         if (p.mode == 2) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                p.out[orow * K + j] = beta[j];
-                if (p.out_valid) p.out_valid[orow * K + j] = (beta[j] == beta[j]) ? 1 : 0;
-            }
+            coefficients(r, beta);
             return;
         }
         double x[K], y;
         src.load(r, x, y);
+        row(r, beta, x);
+    }
+    __device__ __forceinline__ void coefficients(int64_t r, const double (&beta)[K]) const {
+        const int64_t orow = p.row_index ? p.row_index[r] : r;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            p.out[orow * K + j] = beta[j];
+            if (p.out_valid) p.out_valid[orow * K + j] = (beta[j] == beta[j]) ? 1 : 0;
+        }
+    }
+    // x = the row's (scaled) features as src.load returns them — the pipelined chunk loops already hold them
+    __device__ __forceinline__ void row(int64_t r, const double (&beta)[K], const double (&x)[K]) const {
+        if (p.mode == 2) {
+            coefficients(r, beta);
+            return;
+        }
+        const int64_t orow = p.row_index ? p.row_index[r] : r;
         double pred = 0.0;
 #pragma unroll
         for (int j = 0; j < K; ++j) pred += x[j] * beta[j];  // (features * coefficients).sum_axis(1)
@@ -225,7 +260,7 @@ __global__ void __launch_bounds__(128) rolling_prepass_kernel(const MovingParams
 }
 
 template <typename T, int K>
-__global__ void __launch_bounds__(128) rolling_main_kernel(const MovingParams p) {
+__global__ void __launch_bounds__(128, (K <= MOVING_OCC_K ? MOVING_MIN_BLOCKS : 1)) rolling_main_kernel(const MovingParams p) {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
     const DevSrcT<T, K> src = make_src_t<T, K>(p, c);
@@ -370,7 +405,7 @@ __global__ void __launch_bounds__(128) rls_scan_kernel(const MovingParams p, int
 }
 
 template <typename T, int K>
-__global__ void __launch_bounds__(128) rls_main_kernel(const MovingParams p) {
+__global__ void __launch_bounds__(128, (K <= MOVING_OCC_K ? MOVING_MIN_BLOCKS : 1)) rls_main_kernel(const MovingParams p) {
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
     const DevSrcT<T, K> src = make_src_t<T, K>(p, c);

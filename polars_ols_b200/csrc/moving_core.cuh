@@ -22,6 +22,14 @@
 
 namespace b200 {
 
+// prefetch hint `MOVING_PF` rows ahead of a chunk walk (device sources only; see DevSrcT::prefetch in moving.cuh)
+constexpr int MOVING_PF = 4;
+#if defined(__CUDA_ARCH__)
+#define B200_PREFETCH(src, r) (src).prefetch(r)
+#else
+#define B200_PREFETCH(src, r) ((void)0)
+#endif
+
 constexpr int MOVING_MAX_K = 16;  // K <= 8 lives in registers; 9..16 spills to local memory (slower, same results)
 enum : int { MOVING_RLS = 0, MOVING_ROLLING = 1 };
 
@@ -206,6 +214,7 @@ B200_HD void rolling_chunk(const Src &src, const RollingCfg &cfg, const RollingS
         } else {
             for (int64_t i = r - 1; i >= g0 && cnt < W; --i)
                 if (src.valid(i)) {
+                    if (i - MOVING_PF >= g0) B200_PREFETCH(src, i - MOVING_PF);
                     src.load(i, x, y);
                     st.add(x, y, 1.0);
                     tail = i;
@@ -215,9 +224,11 @@ B200_HD void rolling_chunk(const Src &src, const RollingCfg &cfg, const RollingS
             solve_normal<K>(st, beta);  // coefficients carried into the chunk (forward fill source)
         }
         for (; r < c1; ++r) {
+            if (r + MOVING_PF < c1) B200_PREFETCH(src, r + MOVING_PF);
             if (src.valid(r)) {
                 src.load(r, x, y);
                 if (cnt == W) {  // saturated: drop the oldest valid row
+                    B200_PREFETCH(src, tail + MOVING_PF);  // W >= 1 rows behind r + MOVING_PF: always inside the series
                     src.load(tail, xo, yo);
                     st.add(x, y, 1.0);
                     st.add(xo, yo, -1.0);
@@ -269,6 +280,7 @@ B200_HD void rolling_chunk(const Src &src, const RollingCfg &cfg, const RollingS
             const int64_t lo = (at - W + 1 > 0) ? at - W + 1 : 0;
             for (int64_t t = lo; t <= at; ++t)
                 if (valid_rel(t)) {
+                    if (t + MOVING_PF <= at) B200_PREFETCH(src, g0 + t + MOVING_PF);
                     src.load(g0 + t, x, y);
                     s.add(x, y, 1.0);
                 }
@@ -319,6 +331,10 @@ B200_HD void rolling_chunk(const Src &src, const RollingCfg &cfg, const RollingS
         build(ip, st);
     }
     for (; r < c1; ++r, ++i) {
+        if (r + MOVING_PF < c1) {
+            B200_PREFETCH(src, r + MOVING_PF);
+            if (i + MOVING_PF >= W) B200_PREFETCH(src, r + MOVING_PF - W);
+        }
         const bool vi = valid_rel(i);
         const bool sat = i >= W;
         const bool vs = sat && valid_rel(i - W);
@@ -360,6 +376,7 @@ B200_HD void rls_summarise(const Src &src, const RlsCfg &cfg, int64_t c0, int64_
     double x[K], y;
     for (int64_t r = c0; r < c1; ++r)
         if (src.valid(r)) {
+            if (r + MOVING_PF < c1) B200_PREFETCH(src, r + MOVING_PF);
             src.load(r, x, y);
             out.ab.decay(cfg.lambda);
             out.ab.add(x, y, 1.0);
@@ -434,6 +451,7 @@ B200_HD void rls_chunk(const Src &src, const RlsCfg &cfg, bool first_chunk, cons
     const double inv_lam = 1.0 / cfg.lambda;  // exact (1.0) for the expanding case
     double x[K], y;
     for (int64_t r = c0; r < c1; ++r) {
+        if (r + MOVING_PF < c1) B200_PREFETCH(src, r + MOVING_PF);
         if (src.valid(r)) {
             src.load(r, x, y);
             rls_update<K>(P, theta, x, y, cfg.lambda, inv_lam);

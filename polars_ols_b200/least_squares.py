@@ -24,7 +24,7 @@ import ctypes as C
 import logging
 import math
 from dataclasses import asdict, dataclass
-from typing import Any, Dict, List, Literal, Optional, Sequence, Set, Union, get_args
+from typing import Any, Dict, List, Literal, Optional, Sequence, Set, Tuple, Union, get_args
 
 import numpy as np
 
@@ -201,6 +201,57 @@ class Expr:
 
 def col(name: str) -> Expr:
     return Expr(name)
+
+
+class ProductExpr(Expr):
+    """Interaction term of a formula (``x3:x4``): the element-wise product of columns, named ``"x3:x4"`` as the
+    reference's ``reduce(lambda x, y: x * pl.col(y), factors, pl.lit(1)).alias(":".join(factors))``
+    (polars_ols/utils.py:108-110).  A null in any factor is a null in the product."""
+
+    def __init__(self, factors: Sequence[str]):
+        super().__init__(":".join(factors))
+        self._factors = list(factors)
+
+    def resolve(self, frame: "Frame") -> Col:
+        cols = [as_col(frame[f]) for f in self._factors]
+        values = cols[0].values
+        for c in cols[1:]:
+            values = values * c.values
+        validity = None
+        for c in cols:
+            if c.validity is not None:
+                validity = c.validity if validity is None else (validity & c.validity)
+        return Col(values, validity)
+
+
+def build_expressions_from_patsy_formula(formula: str, include_dependent_variable: bool = False) -> Tuple[List[Expr], bool]:
+    """Subset of patsy formulas the reference supports (polars_ols/utils.py:62-111): ``y ~ x1 + x2:x3 - 1`` — plain
+    columns, ``:`` interactions and the intercept switch.  patsy is not required: the grammar is parsed here.  As in
+    the reference, functions of columns (``log(x1)``) and categoricals (``C(group)``) are not supported, and the
+    intercept is added unless the formula text contains ``-1`` (utils.py:99)."""
+    text = formula.replace(" ", "")
+    if "~" in text:
+        lhs, rhs = text.split("~", 1)
+    else:
+        lhs, rhs = "", text
+    if include_dependent_variable:
+        assert lhs and "+" not in lhs and "-" not in lhs, "must provide exactly one LHS variable"
+    else:
+        assert not lhs, "can not provide LHS variables in this context"
+    add_intercept = "-1" not in text
+    exprs: List[Expr] = []
+    if include_dependent_variable:
+        exprs.append(Expr(lhs))
+    for term in rhs.replace("-", "+-").split("+"):
+        if term in ("", "1", "0", "-1", "-0"):
+            continue
+        if "C(" in term:
+            raise NotImplementedError("building patsy categories into polars expressions is not supported")
+        if any(ch in term for ch in "()*/^") or term.startswith("-"):
+            raise NotImplementedError(f"formula term {term!r}: only columns, ':' interactions and the intercept are supported")
+        factors = term.split(":")
+        exprs.append(Expr(factors[0]) if len(factors) == 1 else ProductExpr(factors))
+    return exprs, add_intercept
 
 
 ExprOrStr = Union[Expr, str, Any]
@@ -433,6 +484,20 @@ def compute_rolling_least_squares(target: ExprOrStr, *features: ExprOrStr, sampl
                  rolling_kwargs or RollingKwargs())
 
 
+def compute_least_squares_from_formula(formula: str, sample_weights: Optional[ExprOrStr] = None,
+                                       mode: OutputMode = "predictions", **kwargs) -> LsExpr:
+    """reference polars_ols/least_squares.py:412-452: `half_life` -> rls, `window_size` -> rolling, else static."""
+    expressions, add_intercept = build_expressions_from_patsy_formula(formula, include_dependent_variable=True)
+    if kwargs.get("half_life"):
+        return compute_recursive_least_squares(expressions[0], *expressions[1:], add_intercept=add_intercept,
+                                               sample_weights=sample_weights, mode=mode, rls_kwargs=RLSKwargs(**kwargs))
+    if kwargs.get("window_size"):
+        return compute_rolling_least_squares(expressions[0], *expressions[1:], add_intercept=add_intercept,
+                                             sample_weights=sample_weights, mode=mode, rolling_kwargs=RollingKwargs(**kwargs))
+    return compute_least_squares(expressions[0], *expressions[1:], add_intercept=add_intercept,
+                                 sample_weights=sample_weights, mode=mode, ols_kwargs=OLSKwargs(**kwargs))
+
+
 # ------------------------------------------------------------------------------------------------
 # the `least_squares` namespace (reference polars_ols/__init__.py:35-295)
 # ------------------------------------------------------------------------------------------------
@@ -487,6 +552,22 @@ class LeastSquares:
     def expanding_ols(self, *features: ExprOrStr, **kwargs) -> LsExpr:
         return self.rls(*features, half_life=None, **kwargs)
 
+    def from_formula(self, formula: str, **kwargs) -> LsExpr:
+        """reference polars_ols/__init__.py:263-272"""
+        features, add_intercept = build_expressions_from_patsy_formula(formula, include_dependent_variable=False)
+        if kwargs.get("half_life"):
+            return self.rls(*features, add_intercept=add_intercept, **kwargs)
+        if kwargs.get("window_size"):
+            return self.rolling_ols(*features, add_intercept=add_intercept, **kwargs)
+        return self.least_squares(*features, add_intercept=add_intercept, **kwargs)
+
     def predict(self, *features: ExprOrStr, name: Optional[str] = None, add_intercept: bool = False,
                 null_policy: NullPolicy = "zero") -> "PredictExpr":
         return predict(self._expr, *features, add_intercept=add_intercept, name=name, null_policy=null_policy)
+
+    def predict_from_formula(self, formula: str, name: Optional[str] = None) -> "PredictExpr":
+        """reference polars_ols/__init__.py:289-295"""
+        features, add_intercept = build_expressions_from_patsy_formula(formula, include_dependent_variable=False)
+        has_const = any(f.output_name == "const" for f in features)
+        add_intercept &= not has_const
+        return self.predict(*features, name=name, add_intercept=add_intercept)

@@ -824,3 +824,30 @@ def test_fused_predict_kernel(dtype, k, n_groups, model, kw, weights, intercept,
         assert res[("1", 0)][2] < res[("0", 0)][2]                              # fewer launches: no separate predict pass
     np.testing.assert_allclose(res[("1", 0)][0], res[("0", 0)][0], rtol=1e-9 if dtype == np.float64 else 1e-5, atol=1e-9)
     np.testing.assert_array_equal(res[("1", 0)][0], res[("1", 2)][0])           # stage count does not change the arithmetic
+
+
+# ----------------------------------------------------------------------------------- formula API
+def test_from_formula_matches_explicit_expressions():                      # tests/test_ols.py:362-371,437-449,456-470
+    d = _make_data(4000, 4, n_groups=5, seed=31)
+    F = Frame(d)
+    a = F.select(col("y").least_squares.from_formula("x1 + x2 - 1", mode="coefficients").over("group"))["coefficients"]
+    b = F.select(col("y").least_squares.ols("x1", "x2", mode="coefficients").over("group"))["coefficients"]
+    np.testing.assert_array_equal(a.to_numpy(), b.to_numpy())
+    # intercept + interaction term, against the oracle on the explicitly multiplied column
+    e = pls.compute_least_squares_from_formula("y ~ x1 + x3:x4", mode="predictions")
+    got = F.select(e.over("group"))["y"].to_numpy()
+    ref = S.over(S.least_squares, d["group"], d["y"], d["x1"], d["x3"] * d["x4"], add_intercept=True, mode="predictions",
+                 kwargs=S.OLSKwargs())
+    _close(got, _ref(ref), rtol=1e-6, atol=1e-8)
+    # kwargs dispatch: window_size -> rolling, half_life -> rls
+    r1 = F.select(col("y").least_squares.from_formula("x1 + x2 - 1", window_size=50, mode="coefficients").over("group"))["coefficients"]
+    r2 = F.select(col("y").least_squares.rolling_ols("x1", "x2", window_size=50, mode="coefficients").over("group"))["coefficients"]
+    np.testing.assert_array_equal(r1.to_numpy(), r2.to_numpy())
+    l1 = F.select(pls.compute_least_squares_from_formula("y ~ x1 + x2 - 1", half_life=20.0).over("group"))["y"]
+    l2 = F.select(col("y").least_squares.rls("x1", "x2", half_life=20.0).over("group"))["y"]
+    np.testing.assert_array_equal(l1.to_numpy(), l2.to_numpy())
+    # predict_from_formula
+    coef = F.select(col("y").least_squares.from_formula("x1 + x2", mode="coefficients"))["coefficients"].to_numpy()[0]
+    Fp = Frame({"coefficients": np.broadcast_to(coef, (4000, 3)).copy(), "x1": d["x1"], "x2": d["x2"]})
+    p = Fp.select(col("coefficients").least_squares.predict_from_formula("x1 + x2", name="p"))["p"].to_numpy()
+    _close(p, d["x1"] * coef[0] + d["x2"] * coef[1] + coef[2], rtol=1e-9, atol=1e-12)

@@ -218,3 +218,27 @@ def test_shard_rows_alignment_and_cover():
             sh = shard_rows(n, w)
             assert sh[0][0] == 0 and sh[-1][1] == n
             assert all(a % 64 == 0 for a, _ in sh) and all(sh[i][1] == sh[i + 1][0] for i in range(w - 1))
+
+
+def test_formula_parser_subset():
+    """polars_ols/utils.py:62-111 (patsy subset): columns, ':' interactions, '-1' switches the intercept off."""
+    import polars_ols_b200 as pls
+    ex, icpt = pls.build_expressions_from_patsy_formula("y ~ x1 + x2 + x3:x4", include_dependent_variable=True)
+    assert [e.output_name for e in ex] == ["y", "x1", "x2", "x3:x4"] and icpt
+    ex, icpt = pls.build_expressions_from_patsy_formula("x1 + x2 -1")
+    assert [e.output_name for e in ex] == ["x1", "x2"] and not icpt
+    f = pls.Frame({"x3": np.arange(4.0), "x4": (np.arange(4.0) + 1, np.array([True, False, True, True]))})
+    c = pls.build_expressions_from_patsy_formula("x3:x4")[0][0].resolve(f)
+    np.testing.assert_array_equal(c.values, [0.0, 2.0, 6.0, 12.0])
+    assert np.unpackbits(c.validity, bitorder="little")[:4].tolist() == [1, 0, 1, 1]    # null in a factor -> null
+    for bad in ("log(x1)", "C(group) + x1", "x1 * x2"):
+        with pytest.raises(NotImplementedError):
+            pls.build_expressions_from_patsy_formula(bad)
+    with pytest.raises(AssertionError):
+        pls.build_expressions_from_patsy_formula("y ~ x1")                              # LHS not allowed here
+    with pytest.raises(AssertionError):
+        pls.build_expressions_from_patsy_formula("x1 + x2", include_dependent_variable=True)
+    e = pls.col("y").least_squares.from_formula("x1 + x2 - 1", window_size=20)
+    assert e.kind == "rolling_least_squares" and not e.add_intercept
+    e = pls.compute_least_squares_from_formula("y ~ x1", half_life=3.0)
+    assert e.kind == "recursive_least_squares" and e.add_intercept
