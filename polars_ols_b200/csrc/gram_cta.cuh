@@ -163,6 +163,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                 for (int bk = 0; bk < KB; ++bk)
                     xs[bk] = sb + static_cast<size_t>((8 * bk + fb < kd) ? 8 * bk + fb : 0) * stride + 2 * q * sizeof(T);
                 const unsigned char *ys = sb + static_cast<size_t>(ycol) * stride + 2 * q * sizeof(T);
+                if (p.has_w && !p.w_is_sqrt) {
+                    // sqrt(w) ONCE per row, in place in the stage (this warp's rows only), instead of in every lane of
+                    // every fragment load: the IEEE sqrt is a ~25-instruction sequence and the 8 lanes that share a row
+                    // pair all computed it (ncu on C3: 37 % of the kernel's instructions)
+                    T *wc = reinterpret_cast<T *>(const_cast<unsigned char *>(sb) + static_cast<size_t>(wcol) * stride);
+                    for (int i = 8 * j0 + lane; i < 8 * j1; i += 32) wc[i] = static_cast<T>(sqrt(wc[i]));
+                    __syncwarp();
+                }
                 bool has_x[KB];
                 double xconst[KB];
 #pragma unroll
@@ -199,8 +207,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                     }
                     if (p.has_w) {
                         const Vec w2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(wcol) * stride + lr * sizeof(T));
-                        s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                        s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                        s0 = w2.x;
+                        s1 = w2.y;
                     }
                     const double y0 = v0 ? static_cast<double>(static_cast<T>(y2.x * s0)) : 0.0;
                     const double y1 = v1 ? static_cast<double>(static_cast<T>(y2.y * s1)) : 0.0;
@@ -246,8 +254,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                         for (; j < jend; ++j) {
                             const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
                             const Vec w2 = *reinterpret_cast<const Vec *>(ws + 8 * j * sizeof(T));
-                            const T s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                            const T s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                            const T s0 = w2.x;
+                            const T s1 = w2.y;
                             double f0[KB], f1[KB];
 #pragma unroll
                             for (int bk = 0; bk < KB; ++bk) {

@@ -112,6 +112,11 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) gram_multi_kernel(const Gram
         const unsigned char *ws = sb + static_cast<size_t>(wcol) * stride + 2 * q * sizeof(T);
         for (; g < g1; g += W) {
             const int o = static_cast<int>(p.seg_off[g] - base), hi = static_cast<int>(p.seg_off[g + 1] - base);  // local rows [o, hi)
+            if (p.has_w && !p.w_is_sqrt) {  // sqrt(w) once per row, in place, this group's rows only (see gram_cta.cuh)
+                T *wc = reinterpret_cast<T *>(const_cast<unsigned char *>(sb) + static_cast<size_t>(wcol) * stride);
+                for (int i = o + lane; i < hi; i += 32) wc[i] = static_cast<T>(sqrt(wc[i]));
+                __syncwarp();
+            }
             double acc[NPAIR][2], acc2[NPAIR][2], cy[KB];
 #pragma unroll
             for (int i = 0; i < NPAIR; ++i) acc[i][0] = acc[i][1] = acc2[i][0] = acc2[i][1] = 0.0;
@@ -145,8 +150,8 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) gram_multi_kernel(const Gram
                 }
                 if (p.has_w) {
                     const Vec w2 = *reinterpret_cast<const Vec *>(ws + 8 * j * sizeof(T));
-                    s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                    s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                    s0 = w2.x;
+                    s1 = w2.y;
                 }
                 const double y0 = v0 ? static_cast<double>(static_cast<T>(y2.x * s0)) : 0.0;
                 const double y1 = v1 ? static_cast<double>(static_cast<T>(y2.y * s1)) : 0.0;
@@ -187,8 +192,8 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1) gram_multi_kernel(const Gram
                     for (; j < jfull; ++j) {
                         const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
                         const Vec w2 = *reinterpret_cast<const Vec *>(ws + 8 * j * sizeof(T));
-                        const T s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                        const T s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                        const T s0 = w2.x;
+                        const T s1 = w2.y;
                         double f0[KB], f1[KB];
 #pragma unroll
                         for (int bk = 0; bk < KB; ++bk) {

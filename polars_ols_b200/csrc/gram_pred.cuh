@@ -173,6 +173,11 @@ __global__ void __launch_bounds__(pred_threads(KB), 1) gram_pred_kernel(const Gr
             }
             const unsigned char *ys = sb + static_cast<size_t>(ycol) * stride + 2 * q * sizeof(T);
             const unsigned char *ws = sb + static_cast<size_t>(wcol) * stride + 2 * q * sizeof(T);
+            if (p.has_w && !p.w_is_sqrt) {  // sqrt(w) once per row, in place (see gram_cta.cuh)
+                T *wc = reinterpret_cast<T *>(const_cast<unsigned char *>(sb) + static_cast<size_t>(wcol) * stride);
+                for (int i = 8 * j0 + lane; i < 8 * j1; i += 32) wc[i] = static_cast<T>(sqrt(wc[i]));
+                __syncwarp();
+            }
 
             auto mma_octet = [&](const double (&f0)[KB], const double (&f1)[KB], double y0, double y1) {
                 int idx = 0;
@@ -198,8 +203,8 @@ __global__ void __launch_bounds__(pred_threads(KB), 1) gram_pred_kernel(const Gr
                 T s0 = T(1), s1 = T(1);
                 if (p.has_w) {
                     const Vec w2 = *reinterpret_cast<const Vec *>(ws + 8 * j * sizeof(T));
-                    s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                    s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
+                    s0 = w2.x;
+                    s1 = w2.y;
                 }
                 double f0[KB], f1[KB];
 #pragma unroll
