@@ -780,6 +780,14 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         int64_t R = std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, static_cast<int64_t>((28u << 10) / row_bytes) / 8 * 8);
         R = std::max<int64_t>(R, 64);
         if (c->tile_rows > 0) R = std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, c->tile_rows);  // sweep hook
+        else if (R < 4 * gp.max_seg_rows) {
+            // medium groups (C3: 256 rows x 18 f32 columns): the 28 KB tile holds one group, but the largest tile that
+            // still leaves three stages holds four — tools/sweep_c3.py: gram_cta teams 0.73 ms, 2-3 groups per tile
+            // 0.85 ms, 4 groups per tile 0.43 ms
+            int64_t R3 = static_cast<int64_t>(budget / 3 / NC / sizeof(T)) / 8 * 8;
+            while (R3 > 64 && 3 * static_cast<size_t>(NC) * gram_col_stride<T>(static_cast<int>(R3)) > budget) R3 -= 8;
+            if (R3 >= 4 * gp.max_seg_rows) R = R3;
+        }
         const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(static_cast<int>(R));
         int S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, budget / sb));
         if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));
