@@ -851,3 +851,31 @@ def test_from_formula_matches_explicit_expressions():                      # tes
     Fp = Frame({"coefficients": np.broadcast_to(coef, (4000, 3)).copy(), "x1": d["x1"], "x2": d["x2"]})
     p = Fp.select(col("coefficients").least_squares.predict_from_formula("x1 + x2", name="p"))["p"].to_numpy()
     _close(p, d["x1"] * coef[0] + d["x2"] * coef[1] + coef[2], rtol=1e-9, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------------- C3 shape: medium groups, 4 per tile
+@pytest.mark.parametrize("mode", ["predictions", "coefficients"])
+def test_c3_shaped_medium_groups_weighted_elastic_net_f32(mode):
+    """BASELINE config 3 in small: f32 columns, sample weights, elastic net, ragged groups of ~256 rows x 16 features —
+    the shape that takes gram_multi's three-stage tiles of four groups (sqrt(w) converted in place in the stage)."""
+    rng = np.random.default_rng(3)
+    G, k = 420, 16
+    sizes = rng.integers(150, 257, size=G)
+    sizes[7] = 0
+    n = int(sizes.sum())
+    d = _make_data(n, k, seed=77, dtype=np.float32)
+    names = _xs(d)
+    w = rng.uniform(0.05, 1.0, size=n).astype(np.float32)
+    gid = np.repeat(np.arange(G), sizes)
+    F = Frame({**d, "w": w, "group": gid})
+    e = col("y").least_squares.elastic_net(*names, alpha=1e-3, l1_ratio=0.5, sample_weights="w", mode=mode).over("group")
+    r = F.select(e)["coefficients" if mode == "coefficients" else "y"]
+    if mode == "coefficients":
+        _, c, _ = S.over(S.least_squares, gid, d["y"], *_oracle_cols(d, names), sample_weights=w, per_group=True,
+                         mode="coefficients", kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.5))
+        got = r.to_numpy()
+        assert got.shape == (G - 1, k)                                          # the empty group has no key
+        _close(got, c, rtol=1e-4, atol=1e-5)
+    else:
+        ref = S.over(S.least_squares, gid, d["y"], *_oracle_cols(d, names), sample_weights=w, kwargs=S.OLSKwargs(alpha=1e-3, l1_ratio=0.5))
+        _close(r.to_numpy(), _ref(ref), rtol=1e-4, atol=1e-4)
