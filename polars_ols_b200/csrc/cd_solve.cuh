@@ -73,6 +73,64 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
         for (int t = 0; t < NPL; ++t) rinv[t] = 1.0 / (gd[t] + l2);
         // sub-warps diverge freely (different sweep counts / active sets): shuffles use the sub-warp's own mask
         const unsigned submask = (WIDTH == 32) ? FULL : (((1u << WIDTH) - 1u) << (sub * WIDTH));
+        if (NPL == 1) {
+            // One coordinate per lane (F <= WIDTH).  The sub-warps of a warp sweep in LOCK-STEP until all of them have
+            // stopped (a finished one freezes its state): the warp is busy until its slowest group is done anyway, and
+            // full-mask shuffles with a compile-time source lane cost 2 instructions where sub-warp masks cost ~12
+            // (MATCH / REDUX / BRA.DIV convergence checks — ncu: the kernel is issue-bound).  The coordinate loop is
+            // fully unrolled and only the step delta is broadcast.  Same arithmetic as the general loop below: w_new
+            // and delta = w_new - w_old come from the owner lane, q is updated from row j of G.  The stop test
+            // sqrt(d2) < tol is evaluated as d2 <= cut, cut = the largest double whose correctly rounded square root is
+            // below tol (identical decisions, no sqrt per sweep).
+            const bool any_below = p.tol > 0.0;  // tol <= 0 (or NaN): nothing is ever below it
+            double cut = p.tol * p.tol;
+            if (any_below) {  // tol * tol is within a few ulps of the boundary: both loops run 0-2 times
+                while (cut > 0.0 && sqrt(cut) >= p.tol) cut = __longlong_as_double(__double_as_longlong(cut) - 1);
+                while (cut < 1.0e300 && sqrt(__longlong_as_double(__double_as_longlong(cut) + 1)) < p.tol)
+                    cut = __longlong_as_double(__double_as_longlong(cut) + 1);
+            }
+            double q0 = q[0], w0 = 0.0;
+            const double gd0 = gd[0], ri0 = rinv[0];
+            const bool mine = sl < F;
+            const double *gcol = Gs + (mine ? sl : 0);
+            uint32_t active = (F >= 32) ? 0xffffffffu : ((1u << F) - 1u);  // NPL == 1: F <= WIDTH <= 32
+            bool done = !(live && nfit != 0.0);
+            const int sub_shift = sub * WIDTH;
+            for (int64_t sweep = 0; sweep < p.max_iter; ++sweep) {
+                if (__all_sync(FULL, done)) break;
+                const double wold = w0;
+                const uint32_t loop_set = done ? 0u : active;  // the reference iterates over a clone of the active list (:459)
+#pragma unroll
+                for (int j = 0; j < WIDTH; ++j) {
+                    const bool on = (loop_set >> j) & 1u;  // uniform inside the sub-warp (bits >= F are never set)
+                    // soft_threshold (src/least_squares.rs:373-379), branch- and fmax-free: keep = |rho| - l1 > 0 (a NaN
+                    // is not kept, like f64::max), clamp at zero when `positive`, sign of rho through the high word
+                    const double rho = fma(gd0, w0, q0);
+                    const double av = fabs(rho) - l1;
+                    bool keep = av > 0.0;
+                    if (positive) keep = keep && (rho > 0.0);
+                    const int hi = keep ? (__double2hiint(av) | (__double2hiint(rho) & static_cast<int>(0x80000000u))) : 0;
+                    const int lo = keep ? __double2loint(av) : 0;
+                    const double wn = __hiloint2double(hi, lo) * ri0;
+                    const double delta = __shfl_sync(FULL, wn - w0, j, WIDTH);
+                    if (active_set) {
+                        const unsigned small = __ballot_sync(FULL, on && sl == j && fabs(wn) < p.tol);
+                        if ((small >> sub_shift) & ((WIDTH == 32) ? 0xffffffffu : ((1u << WIDTH) - 1u))) active &= ~(1u << j);  // never re-admitted (:472-476)
+                    }
+                    w0 = (on && sl == j) ? wn : w0;
+                    if (on && mine && delta != 0.0) q0 = fma(-gcol[j * F], delta, q0);  // G symmetric: row j == column j
+                }
+                const double d = w0 - wold;
+                double d2 = mine ? d * d : 0.0;
+#pragma unroll
+                for (int o = WIDTH / 2; o > 0; o >>= 1) d2 += __shfl_xor_sync(FULL, d2, o, WIDTH);
+                if (any_below && d2 <= cut) done = true;
+            }
+            if (live) {
+                if (mine) p.beta[g * F + sl] = (nfit == 0.0) ? 0.0 : w0;  // src/expressions.rs:357-359: no rows -> zeros
+                if (sl == 0) p.flags[g] = (nfit == 0.0) ? FLAG_EMPTY : 0;
+            }
+        } else
         if (live) {
             if (nfit == 0.0) {  // src/expressions.rs:357-359: no rows -> zeros
 #pragma unroll

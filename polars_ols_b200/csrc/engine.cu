@@ -777,17 +777,19 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         // short groups: tiles of whole groups, one consumer warp per group (gram_multi.cuh)
         const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
         const size_t row_bytes = static_cast<size_t>(NC) * sizeof(T);
-        int64_t R = std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, static_cast<int64_t>((28u << 10) / row_bytes) / 8 * 8);
-        R = std::max<int64_t>(R, 64);
-        if (c->tile_rows > 0) R = std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, c->tile_rows);  // sweep hook
-        else if (R < 4 * gp.max_seg_rows) {
-            // medium groups (C3: 256 rows x 18 f32 columns): the 28 KB tile holds one group, but the largest tile that
-            // still leaves three stages holds four — tools/sweep_c3.py: gram_cta teams 0.73 ms, 2-3 groups per tile
-            // 0.85 ms, 4 groups per tile 0.43 ms
-            int64_t R3 = static_cast<int64_t>(budget / 3 / NC / sizeof(T)) / 8 * 8;
-            while (R3 > 64 && 3 * static_cast<size_t>(NC) * gram_col_stride<T>(static_cast<int>(R3)) > budget) R3 -= 8;
-            if (R3 >= 4 * gp.max_seg_rows) R = R3;
+        // Tile = the largest one that still leaves THREE stages (~75 KB): tools/sweep_tiles.py, gram_ms default-28 KB-tile
+        // -> three-stage tile: f64 k=8 n=64 0.263 -> 0.141, f32 k=16 n=64 0.542 -> 0.304, f32 k=16 n=256 (C3) 0.73 ->
+        // 0.43 (four groups per tile instead of gram_cta teams), f64 k=3 n=100 0.222 -> 0.208; half / three-quarter
+        // size tiles are slower everywhere.  Used when such a tile holds at least four groups.
+        (void)row_bytes;
+        int64_t R = static_cast<int64_t>(budget / 3 / NC / sizeof(T)) / 8 * 8;
+        while (R > 64 && 3 * static_cast<size_t>(NC) * gram_col_stride<T>(static_cast<int>(R)) > budget) R -= 8;
+        R = std::min<int64_t>(std::max<int64_t>(R, 64), 8192);
+        {   // small frames: rather one (smaller) tile per SM than a few big ones
+            const int64_t n_total = c->plan_offsets.back(), r4 = (4 * gp.max_seg_rows + 7) / 8 * 8;
+            if (n_total / R < c->sm_count) R = std::max<int64_t>(std::min<int64_t>(R, (n_total / c->sm_count + 7) / 8 * 8), std::max<int64_t>(r4, 64));
         }
+        if (c->tile_rows > 0) R = std::max<int64_t>((gp.max_seg_rows + 7) / 8 * 8, c->tile_rows);  // sweep hook
         const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(static_cast<int>(R));
         int S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, budget / sb));
         if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));
