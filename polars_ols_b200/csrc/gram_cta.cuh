@@ -45,7 +45,9 @@ __host__ __device__ inline size_t cta_fixed_smem(int KB, int F, int red_depth) {
 __host__ __device__ constexpr int cta_plain_depth(int KB) { return KB == 1 ? CTA_RED_DEPTH : CTA_SOLVERS; }
 
 // TEAMS = false compiles the plain pipeline (all consumers on every segment) with constant team / ring sizes
-template <typename T, int KB, bool TEAMS>
+// WEIGHTED = false compiles every sample-weight path out (the C2 headline shape: 0.1175 ms; with the weight code resident
+// the register allocation of the interior loop changed and the same launch took 0.1275 ms)
+template <typename T, int KB, bool TEAMS, bool WEIGHTED>
 __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramParams p) {
     using Vec = typename V2<T>::type;
     constexpr int NPAIR = KB * (KB + 1) / 2;
@@ -60,8 +62,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fb = lane >> 2, q = lane & 3;
     const int kd = p.kd, F = p.F;
-    const int ycol = kd, wcol = kd + 1, mcol = kd + 1 + (p.has_w ? 1 : 0);
-    const int NC = kd + 1 + (p.has_w ? 1 : 0) + (p.has_mask ? 1 : 0);
+    const int ycol = kd, wcol = kd + 1, mcol = kd + 1 + (WEIGHTED ? 1 : 0);
+    const int NC = kd + 1 + (WEIGHTED ? 1 : 0) + (p.has_mask ? 1 : 0);
     const int R = p.tile_rows, S = p.stages;
     const int TEAM = TEAMS ? ((p.team > 0 && p.team < W) ? p.team : W) : W;  // consumer warps per segment
     const int NT = W / TEAM;                                    // teams; segment i (CTA-local) -> team i % NT
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                 for (int bk = 0; bk < KB; ++bk)
                     xs[bk] = sb + static_cast<size_t>((8 * bk + fb < kd) ? 8 * bk + fb : 0) * stride + 2 * q * sizeof(T);
                 const unsigned char *ys = sb + static_cast<size_t>(ycol) * stride + 2 * q * sizeof(T);
-                if (p.has_w && !p.w_is_sqrt) {
+                if (WEIGHTED && !p.w_is_sqrt) {
                     // sqrt(w) ONCE per row, in place in the stage (this warp's rows only), instead of in every lane of
                     // every fragment load: the IEEE sqrt is a ~25-instruction sequence and the 8 lanes that share a row
                     // pair all computed it (ncu on C3: 37 % of the kernel's instructions)
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                         v0 = v0 && (m2.x != T(0));
                         v1 = v1 && (m2.y != T(0));
                     }
-                    if (p.has_w) {
+                    if (WEIGHTED) {
                         const Vec w2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(wcol) * stride + lr * sizeof(T));
                         s0 = w2.x;
                         s1 = w2.y;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
                     }
                     const int jfull = hi >> 3;  // octets below jfull lie entirely inside [o, hi)
                     const int jend = (j1 < jfull) ? j1 : jfull;
-                    if (!p.has_w) {
+                    if (!WEIGHTED) {
 #pragma unroll 4
                         for (; j < jend; ++j) {
                             const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
@@ -333,9 +335,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
     }
 }
 
+template <typename T, int KB, bool TEAMS, bool WEIGHTED>
+cudaError_t gram_cta_launch_w(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s);
+
 template <typename T, int KB, bool TEAMS>
 cudaError_t gram_cta_launch_t(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
-    auto kern = gram_cta_kernel<T, KB, TEAMS>;
+    if (p.has_w) return gram_cta_launch_w<T, KB, TEAMS, true>(p, grid, smem, s);
+    return gram_cta_launch_w<T, KB, TEAMS, false>(p, grid, smem, s);
+}
+
+template <typename T, int KB, bool TEAMS, bool WEIGHTED>
+cudaError_t gram_cta_launch_w(const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
+    auto kern = gram_cta_kernel<T, KB, TEAMS, WEIGHTED>;
     static size_t attr_set[64] = {};  // per device: the opt-in shared-memory size already granted to this kernel
     int dev = 0;
     cudaGetDevice(&dev);
