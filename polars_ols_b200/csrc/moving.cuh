@@ -487,29 +487,26 @@ static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const i
     return cudaGetLastError();
 }
 
-template <typename T>
-static cudaError_t launch_moving_k(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches) {
-    switch (p.F) {
-        case 1: return launch_moving_t<T, 1>(s, p, gco, launches);
-        case 2: return launch_moving_t<T, 2>(s, p, gco, launches);
-        case 3: return launch_moving_t<T, 3>(s, p, gco, launches);
-        case 4: return launch_moving_t<T, 4>(s, p, gco, launches);
-        case 5: return launch_moving_t<T, 5>(s, p, gco, launches);
-        case 6: return launch_moving_t<T, 6>(s, p, gco, launches);
-        case 7: return launch_moving_t<T, 7>(s, p, gco, launches);
-        case 8: return launch_moving_t<T, 8>(s, p, gco, launches);
-        case 9: return launch_moving_t<T, 9>(s, p, gco, launches);
-        case 10: return launch_moving_t<T, 10>(s, p, gco, launches);
-        case 11: return launch_moving_t<T, 11>(s, p, gco, launches);
-        case 12: return launch_moving_t<T, 12>(s, p, gco, launches);
-        case 13: return launch_moving_t<T, 13>(s, p, gco, launches);
-        case 14: return launch_moving_t<T, 14>(s, p, gco, launches);
-        case 15: return launch_moving_t<T, 15>(s, p, gco, launches);
-        default: return launch_moving_t<T, 16>(s, p, gco, launches);
+// Coefficient counts KLO..KHI of one dtype (one translation unit each: the K >= 9 instantiations spill and take minutes
+// to compile, so they are spread over several .cu files that nvcc builds in parallel — moving_f64_r*.cu / moving_f32_r*.cu)
+template <typename T, int KLO, int KHI>
+static cudaError_t launch_moving_range(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches) {
+    if constexpr (KLO >= KHI) {
+        return launch_moving_t<T, KHI>(s, p, gco, launches);
+    } else {
+        if (p.F <= KLO) return launch_moving_t<T, KLO>(s, p, gco, launches);
+        return launch_moving_range<T, KLO + 1, KHI>(s, p, gco, launches);
     }
 }
 
-// defined in moving_f64.cu / moving_f32.cu
+// ranges: r0 = 1..8, r1 = 9..11, r2 = 12..14, r3 = 15..16 (defined in moving_f{64,32}_r{0..3}.cu)
+#define B200_MOVING_DECL(SUFFIX) \
+    cudaError_t moving_launch_##SUFFIX(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
+B200_MOVING_DECL(f64_r0) B200_MOVING_DECL(f64_r1) B200_MOVING_DECL(f64_r2) B200_MOVING_DECL(f64_r3)
+B200_MOVING_DECL(f32_r0) B200_MOVING_DECL(f32_r1) B200_MOVING_DECL(f32_r2) B200_MOVING_DECL(f32_r3)
+#undef B200_MOVING_DECL
+
+// defined in moving_f64.cu / moving_f32.cu: dispatch on the number of coefficients
 cudaError_t moving_launch_f64(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
 cudaError_t moving_launch_f32(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
 

@@ -1,0 +1,7 @@
+// moving_f32_r0.cu — f32 instantiations of the rls / rolling kernels for 1..8 coefficients (see moving.cuh)
+#include "moving.cuh"
+namespace b200 {
+cudaError_t moving_launch_f32_r0(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches) {
+    return launch_moving_range<float, 1, 8>(s, p, gco, launches);
+}
+}  // namespace b200

@@ -242,3 +242,33 @@ def test_formula_parser_subset():
     assert e.kind == "rolling_least_squares" and not e.add_intercept
     e = pls.compute_least_squares_from_formula("y ~ x1", half_life=3.0)
     assert e.kind == "recursive_least_squares" and e.add_intercept
+
+
+def test_cd_stop_threshold_is_equivalent_to_the_sqrt_test():
+    """cd_solve.cuh replaces the reference's stop test `norm_l2(w - w_old) < tol` (src/least_squares.rs:436-444), i.e.
+    sqrt(d2) < tol, by d2 <= cut with cut = the largest double whose correctly rounded square root is below tol.
+    Restated here bit for bit (numpy's float64 sqrt is correctly rounded, like the device's): the two tests must agree
+    for every d2 around the boundary."""
+    def cut_of(tol):
+        cut = np.float64(tol) * np.float64(tol)
+        bits = lambda v: np.float64(v).view(np.int64)                      # noqa: E731
+        val = lambda b: np.int64(b).view(np.float64)                       # noqa: E731
+        while cut > 0.0 and np.sqrt(cut) >= tol:
+            cut = val(bits(cut) - 1)
+        while cut < 1.0e300 and np.sqrt(val(bits(cut) + 1)) < tol:
+            cut = val(bits(cut) + 1)
+        return cut
+
+    rng = np.random.default_rng(0)
+    tols = [1e-5, 1e-4, 1e-8, 1e-3, 0.1, 1.0, 3.0, 1e-12] + list(10.0 ** rng.uniform(-12, 2, size=200))
+    for tol in tols:
+        tol = np.float64(tol)
+        cut = cut_of(tol)
+        assert np.sqrt(cut) < tol
+        b = cut.view(np.int64)
+        for off in range(-4, 5):
+            d2 = np.int64(b + off).view(np.float64)
+            assert (np.sqrt(d2) < tol) == (d2 <= cut), (tol, off)
+        for d2 in (0.0, tol * tol * 0.5, tol * tol * 2.0, np.inf):
+            assert (np.sqrt(np.float64(d2)) < tol) == (np.float64(d2) <= cut)
+        assert not (np.float64(np.nan) <= cut)                                 # NaN never stops the sweeps, as sqrt(NaN) < tol
