@@ -793,8 +793,9 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         const size_t sb = static_cast<size_t>(NC) * gram_col_stride<T>(static_cast<int>(R));
         int S = static_cast<int>(std::min<size_t>(GRAM_MAX_STAGES, budget / sb));
         if (c->warps_per_cta > 0) S = std::min(S, std::max(2, c->warps_per_cta));
-        // one consumer warp per group only pays while a tile holds several groups (sweep, profiles/r01_sweep_team.json:
-        // 64-row groups 0.27 ms vs 0.73 ms with teams; 256-row groups fit once per tile and run 1.7-2.4x slower)
+        // one consumer warp per group only pays while a tile holds several groups (profiles/r01_sweep_team.json,
+        // r01_sweep_c3.json: 64-row groups 0.14 ms vs 0.73 ms with gram_cta teams; two or three 256-row groups per tile
+        // run slower than teams, four run 1.7x faster)
         if (S >= 3 && R <= 8192 && (c->tile_rows > 0 || R >= 4 * gp.max_seg_rows)) {
             if (!c->tile_valid || c->tile_rows_built != R) {
                 // greedy runs of consecutive groups whose rows fit one tile (A-aligned start included)
