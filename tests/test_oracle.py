@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/) before anything is checked against it.
 
-1. the reference's own published outputs (README known-answer frame, tests/golden/readme_frame.json);
+1. the reference's own published outputs (README known-answer frame, tests/golden/readme_frame.json; the executed
+   cells of its demo notebook, tests/golden/notebook_outputs.json — data regenerated from the notebook's seeded recipe);
 2. the reference's Rust unit tests (src/lib.rs:47-171) re-derived on the same data recipe;
 3. the third-party oracles the reference's tests/test_ols.py uses (numpy lstsq/solve, sklearn).
 """
@@ -17,6 +18,17 @@ GOLD = json.loads((Path(__file__).parent / "golden" / "readme_frame.json").read_
 F = {k: np.asarray(v, dtype=np.float64) for k, v in GOLD["frame"].items()}
 TOLC = GOLD["printed_abs_tol_coefficients"]
 TOLR = GOLD["printed_abs_tol_round2"]
+NB = json.loads((Path(__file__).parent / "golden" / "notebook_outputs.json").read_text())
+TOLN = NB["printed_abs_tol"]
+
+
+def notebook_frame(n_samples=2000, n_features=3, n_groups=5, noise=0.1):
+    """notebooks/polars_ols_demo.ipynb cell 1 (`_make_data`), same rng stream."""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(n_samples, n_features))
+    eps = rng.normal(size=n_samples, scale=noise)
+    return {"x": [np.ascontiguousarray(x[:, j]) for j in range(n_features)], "y": -1 * x.sum(1) + eps,
+            "group": rng.integers(0, n_groups, size=n_samples), "w": rng.uniform(0, 1, size=n_samples)}
 
 
 def _make_data(n_samples=5000, n_features=2, n_groups=None, scale=0.1, sparsity=0.0, add_missing=False):
@@ -36,6 +48,74 @@ def _make_data(n_samples=5000, n_features=2, n_groups=None, scale=0.1, sparsity=
             masks.append(m)
         out["masks"] = masks
     return out
+
+
+# ----------------------------------------------------------------------------- the reference's executed notebook
+def test_notebook_data_recipe_reproduces_the_printed_frame():
+    d = notebook_frame()
+    assert np.allclose(d["x"][0][-10:], NB["cell7_tail10"]["x1"], atol=TOLN, rtol=0)
+
+
+def test_notebook_ols_svd_and_wls_predictions():                               # cells 5, 7
+    d, g = notebook_frame(), NB["cell7_tail10"]
+    kw = S.OLSKwargs(null_policy="drop", solve_method="svd")
+    p, _ = S.over(S.least_squares, d["group"], d["y"], *d["x"], kwargs=kw)
+    assert np.allclose(np.asarray(p)[-10:], g["predictions_ols_group"], atol=TOLN, rtol=0)
+    p, _ = S.least_squares(d["y"], *d["x"], kwargs=kw)
+    assert np.allclose(p[-10:], g["predictions_ols"], atol=TOLN, rtol=0)
+    p, _ = S.least_squares(d["y"], *d["x"], sample_weights=d["w"])
+    assert np.allclose((p * (d["group"] == 2))[-10:], g["predictions_wls_masked"], atol=TOLN, rtol=0)
+
+
+def test_notebook_grouped_coefficients():                                      # cells 11, 49
+    d = notebook_frame()
+    keys, c, _ = S.over(S.least_squares, d["group"], d["y"], *d["x"], add_intercept=True, per_group=True, mode="coefficients")
+    by_key = {int(k): c[i] for i, k in enumerate(keys)}
+    for grp, want in zip(NB["cell11_head5_unnested"]["group"], NB["cell11_head5_unnested"]["coefficients"]):
+        assert np.allclose(by_key[grp], want, atol=TOLN, rtol=0)
+    keys, c, _ = S.over(S.least_squares, d["group"], d["y"], d["x"][0], d["x"][1], per_group=True, mode="coefficients")
+    for i, k in enumerate(keys):
+        assert np.allclose(c[i], NB["cell49_by_group"][str(int(k))], atol=TOLN, rtol=0)
+
+
+def test_notebook_regularised_and_collinear():                                 # cells 26, 30, 36
+    d = notebook_frame()
+    c, _ = S.least_squares(d["y"], *d["x"], sample_weights=d["w"], mode="coefficients", kwargs=S.OLSKwargs(alpha=100.0, l1_ratio=0.0))
+    assert np.allclose(c, NB["cell36"]["coef_ridge_alpha100_weighted"], atol=TOLN, rtol=0)
+    c, _ = S.least_squares(d["y"], *d["x"], mode="coefficients", kwargs=S.OLSKwargs(alpha=0.0001, l1_ratio=0.5, positive=True))
+    assert np.allclose(c, NB["cell36"]["coef_enet_non_negative"], atol=TOLN, rtol=0)   # all true coefficients are -1: NNLS -> 0
+    x1, x2 = d["x"][0], d["x"][1]
+    c, m = S.least_squares(x1 + 2 * x2, x1, x2, x2.copy(), mode="coefficients", kwargs=S.OLSKwargs(solve_method="chol"))
+    assert NB["cell30_collinear_chol"] == [None, None, None] and not m.any()             # Cholesky and LU fail -> nulls
+
+
+def test_notebook_rolling_rls_expanding():                                     # cell 47
+    d, g = notebook_frame(), NB["cell47"]
+    c, _ = S.over(S.rolling_least_squares, d["group"], d["y"], *d["x"], mode="coefficients",
+                  kwargs=S.RollingKwargs(window_size=252, min_periods=5, alpha=0.0001, null_policy="drop"))
+    c = np.asarray(c)
+    assert np.isnan(c[:5]).all() and all(v is None for row in g["rolling_ridge_coef_head5"] for v in row)
+    assert np.allclose(c[-5:], g["rolling_ridge_coef_tail5"], atol=TOLN, rtol=0)
+    c, _ = S.over(S.recursive_least_squares, d["group"], d["y"], *d["x"], mode="coefficients",
+                  kwargs=S.RLSKwargs(half_life=21.0, initial_state_mean=[-1.0, -1.0, -1.0], initial_state_covariance=10.0, null_policy="drop"))
+    c = np.asarray(c)
+    assert np.allclose(c[:5], g["rls_coef_head5"], atol=TOLN, rtol=0) and np.allclose(c[-5:], g["rls_coef_tail5"], atol=TOLN, rtol=0)
+    p, _ = S.recursive_least_squares(d["y"], *d["x"], mode="predictions", kwargs=S.RLSKwargs(half_life=None, null_policy="drop"))
+    assert np.allclose(p[:5], g["expanding_ols_pred_head5"], atol=TOLN, rtol=0)
+    assert np.allclose(p[-5:], g["expanding_ols_pred_tail5"], atol=TOLN, rtol=0)
+
+
+def test_notebook_out_of_sample_predict():                                     # cells 49, 50
+    d, t = notebook_frame(), notebook_frame(n_features=5, n_groups=1)           # df_test = _make_data(n_groups=1): group == 0
+    keys, c, _ = S.over(S.least_squares, d["group"], d["y"], d["x"][0], d["x"][1], per_group=True, mode="coefficients")
+    b = c[list(keys).index(0)]
+    n = len(t["y"])
+    p = S.predict([np.full(n, b[0]), np.full(n, b[1])], [t["x"][0], t["x"][1]], "zero")
+    assert np.allclose(_vals(p)[:5], NB["cell50_predictions_test_head5"], atol=TOLN, rtol=0)
+
+
+def _vals(values_mask):
+    return values_mask[0] if isinstance(values_mask, tuple) else values_mask
 
 
 # ----------------------------------------------------------------------------- README golden frame
