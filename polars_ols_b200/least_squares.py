@@ -20,6 +20,7 @@ There is no CPU path: without a CUDA device evaluation raises.
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
 import logging
 import math
@@ -279,12 +280,14 @@ class LsExpr:
         self._per_group = False
 
     def over(self, *keys: ExprOrStr) -> "LsExpr":
-        self._over = list(keys)
-        return self
+        new = copy.copy(self)                  # expressions are immutable, as in polars: `e.over(..)` leaves `e` ungrouped
+        new._over = list(keys)
+        return new
 
     def alias(self, name: str) -> "LsExpr":
-        self._alias = name
-        return self
+        new = copy.copy(self)
+        new._alias = name
+        return new
 
     @property
     def output_name(self) -> str:
@@ -383,8 +386,9 @@ class PredictExpr:
         self.null_policy, self.add_intercept, self.output_name = null_policy, add_intercept, name or "predictions"
 
     def alias(self, name: str) -> "PredictExpr":
-        self.output_name = name
-        return self
+        new = copy.copy(self)
+        new.output_name = name
+        return new
 
     def evaluate(self, frame: "Frame", engine: Optional[Engine] = None) -> Result:
         coef = self.coefficients._data if self.coefficients._data is not None else frame[self.coefficients._name]

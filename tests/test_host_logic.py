@@ -272,3 +272,16 @@ def test_cd_stop_threshold_is_equivalent_to_the_sqrt_test():
         for d2 in (0.0, tol * tol * 0.5, tol * tol * 2.0, np.inf):
             assert (np.sqrt(np.float64(d2)) < tol) == (np.float64(d2) <= cut)
         assert not (np.float64(np.nan) <= cut)                                 # NaN never stops the sweeps, as sqrt(NaN) < tol
+
+
+def test_expressions_are_immutable_like_polars():
+    """`.over()` / `.alias()` return new expressions (polars semantics): re-using `e` after `e.over(..)` stays ungrouped."""
+    import polars_ols_b200 as pls
+    e = pls.col("y").least_squares.ols("x1", "x2")
+    g = e.over("group")
+    a = g.alias("pred")
+    assert e._over == [] and g._over == ["group"] and a._over == ["group"]
+    assert e.output_name == "y" and g.output_name == "y" and a.output_name == "pred"
+    p = pls.col("coefficients").least_squares.predict("x1", "x2", name="p0")
+    q = p.alias("p1")
+    assert p.output_name == "p0" and q.output_name == "p1"
