@@ -14,8 +14,10 @@
  *   - LAPACK dgelsd                  -> not restated here; oracle/semantics.py calls numpy.linalg.lstsq
  *                                       (the same LAPACK routine) for the SVD paths.
  *
- * Parity pin: see oracle/README.md — checked against the reference's README known-answer frame
- * (tests/golden/readme_frame.json), the Rust unit-test cases of src/lib.rs:47-171 and the
+ * Parity pin: see oracle/README.md — checked against outputs the reference itself produced: its README
+ * known-answer frame (tests/golden/readme_frame.json) and the executed cells of its demo notebook on the
+ * notebook's own seeded data (tests/golden/notebook_outputs.json, 6 decimals: OLS / WLS / ridge / NNLS /
+ * rolling / RLS / expanding / predict); then the Rust unit-test cases of src/lib.rs:47-171 and the
  * numpy / scikit-learn oracles the reference's own tests/test_ols.py uses.
  *
  * Layout conventions follow the reference after marshalling (src/expressions.rs:22-103):
