@@ -285,3 +285,24 @@ def test_expressions_are_immutable_like_polars():
     p = pls.col("coefficients").least_squares.predict("x1", "x2", name="p0")
     q = p.alias("p1")
     assert p.output_name == "p0" and q.output_name == "p1"
+
+
+def test_cd_branch_free_soft_threshold_is_the_reference_formula():
+    """cd_solve.cuh evaluates soft_threshold (src/least_squares.rs:373-379: signum(x) * max(|x| - t, 0), then max(., 0)
+    when `positive`) as: keep = |x| - t > 0 (and x > 0 when positive); value = copysign(|x| - t, x) if keep else 0.
+    Restated with numpy: the same numbers for every input class (zeros compare equal regardless of sign; a NaN gives 0
+    in both, as f64::max ignores it)."""
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.normal(size=2000) * 10.0 ** rng.integers(-8, 4, size=2000), [0.0, -0.0, np.nan, np.inf, -np.inf, 1e-320, -1e-320]])
+    for t in (0.0, 1e-12, 1e-4, 0.5, 3.0, 1e6):
+        for positive in (False, True):
+            with np.errstate(invalid="ignore"):
+                ref = np.copysign(np.fmax(np.abs(x) - t, 0.0), x)          # f64::max == fmax: NaN is ignored
+                if positive:
+                    ref = np.fmax(ref, 0.0)
+                av = np.abs(x) - t
+                keep = av > 0.0
+                if positive:
+                    keep = keep & (x > 0.0)
+                new = np.where(keep, np.copysign(av, x), 0.0)
+            assert np.array_equal(ref + 0.0, new + 0.0), (t, positive)     # + 0.0: -0.0 and 0.0 are the same coefficient
