@@ -308,6 +308,43 @@ def main():
     e2e_value = world * G * e2e_steps / float(te.item())
     assert np.allclose(hcoef, coef.cpu().numpy(), rtol=1e-9, atol=1e-12)
 
+    # ---- e2e_api: the drop-in call itself — Frame.select(col("y").least_squares.ridge(...).over("group")) on PAGEABLE
+    # numpy columns plus an int64 key column: key upload + device group plan (b200ols_group_plan_build) + column upload
+    # through the engine's pinned staging ring + kernel + coefficients back, all inside the timed region
+    names = [f"x{i}" for i in range(K)]
+    key = np.repeat(np.arange(G, dtype=np.int64), N_PER)
+    fr = pls.Frame({"y": y, "group": key, **{nm: x[i] for i, nm in enumerate(names)}})
+    expr = pls.col("y").least_squares.ridge(*names, alpha=ALPHA, mode="coefficients").over("group")
+
+    def api_leg(frame, steps):
+        for _ in range(2):
+            frame.select(expr, engine=heng)
+        if dist:
+            dist.barrier()
+        t0_ = time.perf_counter()
+        for _ in range(steps):
+            res = frame.select(expr, engine=heng)["coefficients"]
+        dt = time.perf_counter() - t0_
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * G * steps / float(tt.item()), 1e3 * float(tt.item()) / steps, res
+
+    api_value, api_ms, res = api_leg(fr, e2e_steps)
+    assert np.allclose(res.to_numpy(), hcoef, rtol=1e-9, atol=1e-12)
+    plan_ms = heng.group_plan([key]).device_ms
+    # the same frame with its rows shuffled (tests/test_ols.py:39-40 shape: random, non-contiguous groups): the plan
+    # now sorts 10M keys and the columns are gathered on the device
+    e2e_api_shuffled = None
+    if rank == 0 and world == 1:
+        perm = np.random.default_rng(1).permutation(G * N_PER)
+        frs = pls.Frame({"y": y[perm], "group": key[perm], **{nm: x[i][perm] for i, nm in enumerate(names)}})
+        sv, sms, sres = api_leg(frs, max(3, e2e_steps // 2))
+        assert np.allclose(sres.to_numpy(), hcoef, rtol=1e-9, atol=1e-12)
+        e2e_api_shuffled = {"value": sv, "unit": UNIT, "ms_per_step": sms,
+                            "plan_device_ms": heng.group_plan([key[perm]]).device_ms}
+        del frs, perm
+
     # ---- roofline of the dominant kernel (row-streaming Gram + fused solve) ---------------------------------
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -347,6 +384,14 @@ def main():
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + hy.nbytes + offsets.nbytes),
                     "d2h_bytes_per_step": int(hcoef.nbytes), "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps},
+            "e2e_api": {"value": api_value, "unit": UNIT, "ms_per_step": api_ms, "steps": e2e_steps,
+                        "call": "Frame.select(col('y').least_squares.ridge(*x, alpha=1e-3, mode='coefficients').over('group'))",
+                        "inputs": "pageable numpy f64 columns + int64 key column; group plan on the device",
+                        "h2d_bytes_per_step": int(x.nbytes + y.nbytes + key.nbytes), "d2h_bytes_per_step": int(hcoef.nbytes + 2 * 8 * (G + 1)),
+                        "plan_device_ms": plan_ms, "shuffled_rows": e2e_api_shuffled},
+            "e2e_roofline": {"bound": "pcie", "achieved": (hx.nbytes + hy.nbytes) / (1e6 * 1e3 * float(te.item()) / e2e_steps),
+                             "peak": 63.0, "unit": "GB/s", "peak_source": "PCIe Gen5 x16, 32 GT/s x 16 lanes x 128b/130b",
+                             "frac": (hx.nbytes + hy.nbytes) / (1e6 * 1e3 * float(te.item()) / e2e_steps) / 63.0},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

@@ -106,6 +106,9 @@ typedef struct b200ols_frame {
     const int64_t *group_offsets; /* [n_groups+1], ALWAYS a host pointer (plan metadata, like this struct);
                                      NULL => one group spanning all rows */
     const int64_t *row_index;     /* [n_rows] or NULL */
+    int32_t row_index_on_device;  /* 1: row_index is a DEVICE pointer although memspace == HOST (the permutation
+                                     b200ols_group_plan_build left on the device: it never visits the host) */
+    int32_t _reserved;
 } b200ols_frame;
 
 /* serde kwargs structs of src/expressions.rs:298-330 as POD; NaN / negative encode Option::None */
@@ -187,6 +190,43 @@ B200OLS_API int b200ols_set_tuning(b200ols_ctx *ctx, int tile_rows, int warps_pe
  * per lane (0 = default).  Variants that do not cover a shape fall back to variant 0.
  * The environment variable B200OLS_VARIANT sets the initial variant of new contexts (test hook). */
 B200OLS_API int b200ols_set_variant(b200ols_ctx *ctx, int variant, int unroll);
+
+/* ---- group-index packing: `.over()` / group_by key columns -> CSR groups, on the device ------------------
+ * Replaces what polars does in front of the reference's plugin (GroupsProxy construction + the per-group gather that
+ * feeds src/expressions.rs:22-103) for the batched route: ONE call turns the key column(s) of a frame
+ * into the `group_offsets` / `row_index` of b200ols_frame.  Groups ascend by key tuple (signed / unsigned integer
+ * order; floats ascending with -0.0 == +0.0 and all NaN one group sorted last), rows inside a group keep the frame's
+ * order — i.e. exactly `numpy.unique(keys, return_inverse=True)` followed by a stable argsort of the inverse.
+ * Kernels: order-preserving radix images + varying-bit detection, LSD radix sort of (image, row) pairs over the
+ * varying 8-bit digits only (stable, warp match_any ranking), boundary flags + scan -> offsets.  Already-sorted keys
+ * (GroupsSlice) skip the sort and yield row_index == NULL.  n_rows must be < 2^31. */
+enum { B200OLS_KEY_I64 = 0, B200OLS_KEY_I32 = 1, B200OLS_KEY_U64 = 2, B200OLS_KEY_U32 = 3, B200OLS_KEY_F64 = 4, B200OLS_KEY_F32 = 5 };
+
+typedef struct b200ols_key_column {
+    const void *values; /* n_rows elements, no nulls (a null key is a key value: encode it before the call) */
+    int32_t dtype;      /* B200OLS_KEY_* */
+    int32_t _reserved;
+} b200ols_key_column;
+
+/* Filled by b200ols_group_plan_build.  Every pointer is owned by the context and stays valid until the next
+ * b200ols_group_plan_build on the same context (or b200ols_destroy). */
+typedef struct b200ols_group_plan {
+    int64_t n_rows;
+    int64_t n_groups;
+    const int64_t *group_offsets;   /* HOST [n_groups + 1] -> b200ols_frame.group_offsets */
+    const int64_t *group_first_row; /* HOST [n_groups]: original row of the first row of each group (its key values) */
+    const int64_t *row_index;       /* DEVICE [n_rows] -> b200ols_frame.row_index (+ row_index_on_device = 1 for host
+                                       frames), or NULL when the groups are contiguous row slices */
+    double device_ms;               /* device time of the planning kernels (CUDA events), uploads excluded */
+} b200ols_group_plan;
+
+/* keys[n_keys] (1 <= n_keys <= 8) live in `memspace`; host keys are uploaded (pageable buffers through the pinned ring). */
+B200OLS_API int b200ols_group_plan_build(b200ols_ctx *ctx, const b200ols_key_column *keys, int32_t n_keys, int64_t n_rows,
+                                         int32_t memspace, b200ols_group_plan *out);
+/* copies of the current plan's permutation (int64 [n_rows]; identity when the groups are contiguous) and of the group id
+ * of every original row (int32 [n_rows]: what `.over()` uses to broadcast per-group results) into `memspace` memory */
+B200OLS_API int b200ols_group_plan_row_index(b200ols_ctx *ctx, int64_t *dst, int32_t memspace);
+B200OLS_API int b200ols_group_plan_group_of_row(b200ols_ctx *ctx, int32_t *dst, int32_t memspace);
 
 /* ---- the six entry points (one per reference plugin symbol), batched over groups ------------------ */
 

@@ -31,6 +31,7 @@ EXPORTS = [
     "b200ols_rolling_least_squares_coefficients", "b200ols_last_group_flags", "b200ols_predict", "b200ols_device_alloc", "b200ols_device_free", "b200ols_ipc_export",
     "b200ols_ipc_open", "b200ols_ipc_close", "b200ols_copy_to_host", "b200ols_set_peer_gather",
     "b200ols_recursive_least_squares_state", "b200ols_least_squares_statistics", "b200ols_multi_target_least_squares",
+    "b200ols_group_plan_build", "b200ols_group_plan_row_index", "b200ols_group_plan_group_of_row",
 ]
 
 
@@ -43,8 +44,20 @@ class Frame(C.Structure):
         ("n_rows", C.c_int64), ("n_features", C.c_int32), ("dtype", C.c_int32), ("memspace", C.c_int32),
         ("add_intercept", C.c_int32), ("target", Column), ("features", C.POINTER(Column)),
         ("sample_weights", C.POINTER(Column)), ("n_groups", C.c_int64), ("group_offsets", C.c_void_p),
-        ("row_index", C.c_void_p),
+        ("row_index", C.c_void_p), ("row_index_on_device", C.c_int32), ("_reserved", C.c_int32),
     ]
+
+
+class KeyColumn(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("dtype", C.c_int32), ("_reserved", C.c_int32)]
+
+
+class GroupPlan(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_groups", C.c_int64), ("group_offsets", C.c_void_p),
+                ("group_first_row", C.c_void_p), ("row_index", C.c_void_p), ("device_ms", C.c_double)]
+
+
+KEY_I64, KEY_I32, KEY_U64, KEY_U32, KEY_F64, KEY_F32 = range(6)
 
 
 class OLSKwargs(C.Structure):
@@ -136,6 +149,9 @@ def load() -> C.CDLL:
     L.b200ols_least_squares_statistics.argtypes = [vp, C.POINTER(Frame), C.POINTER(OLSKwargs), C.POINTER(StatisticsOutput)]
     L.b200ols_multi_target_least_squares.argtypes = [vp, C.POINTER(Frame), i32, C.POINTER(Column), C.POINTER(OLSKwargs), i32,
                                                      C.POINTER(Output)]
+    L.b200ols_group_plan_build.argtypes = [vp, C.POINTER(KeyColumn), i32, i64, i32, C.POINTER(GroupPlan)]
+    L.b200ols_group_plan_row_index.argtypes = [vp, vp, i32]
+    L.b200ols_group_plan_group_of_row.argtypes = [vp, vp, i32]
     _lib = L
     return L
 

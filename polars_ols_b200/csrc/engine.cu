@@ -45,12 +45,11 @@ static __global__ void nan_mask_kernel(const double *v, uint8_t *m, int64_t n) {
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// errors
-// ------------------------------------------------------------------------------------------------
-static thread_local std::string g_last_error;
+#include "engine_ctx.h"
 
-static int fail(int code, const char *fmt, ...) {
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
     char buf[1024];
     va_list ap;
     va_start(ap, fmt);
@@ -60,172 +59,7 @@ static int fail(int code, const char *fmt, ...) {
     return code;
 }
 
-#define CU(expr)                                                                                          \
-    do {                                                                                                  \
-        cudaError_t e__ = (expr);                                                                         \
-        if (e__ != cudaSuccess)                                                                           \
-            return fail(B200OLS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
-                        __LINE__);                                                                        \
-    } while (0)
 
-#define TRY(expr)              \
-    do {                       \
-        int rc__ = (expr);     \
-        if (rc__ != 0) return rc__; \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// context
-// ------------------------------------------------------------------------------------------------
-struct b200ols_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int sm_count = 0;
-    int smem_optin = 0;
-    int64_t launches = 0;
-    int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
-    bool multi_enabled = true;      // test hook B200OLS_MULTI=0: never use gram_multi_kernel
-    int pred_lag = 4;               // test hook B200OLS_PRED_LAG: groups the stream may run ahead of the predictions (per SM)
-    bool pred_enabled = true;       // test hook B200OLS_PRED=0: never use the fused Gram -> solve -> predict kernel
-    long long fuse_min_bytes = -1;  // < 0: default; test hook B200OLS_FUSE_MIN_BYTES (0 = always fuse the solve)
-    int variant = 3, unroll = 0;  // Gram kernel variant (b200ols_set_variant); 3 = CTA-cooperative TMA pipeline
-    // bump arena in device memory, reset at the start of every call
-    char *arena = nullptr;
-    size_t arena_cap = 0, arena_off = 0;
-    bool arena_overflow = false;
-    std::vector<void *> retired;  // old arenas, freed after the next synchronise
-    // pinned host staging for small metadata (offsets, segment tables)
-    // two halves used by alternating calls; a half is recycled only after the event recorded at the end of the
-    // call that used it has completed (device-memspace calls return before their copies ran)
-    char *pinned = nullptr;
-    size_t pinned_cap = 0, pinned_off = 0, pinned_base = 0;
-    int pinned_half = 0;
-    cudaEvent_t pinned_ev[2] = {nullptr, nullptr};
-    bool pinned_ev_set[2] = {false, false};
-    // diagnostics of the last static call
-    int32_t *last_flags = nullptr;  // device pointer inside the arena
-    int64_t last_flags_n = 0;
-    // last uploaded group-offset table (steady-state loops re-use it instead of re-copying every call)
-    std::vector<int64_t> plan_offsets;
-    int64_t plan_max_rows = 0, plan_wide_group = -1;
-    int plan_F = -1;
-    int64_t *plan_dev = nullptr;
-    size_t plan_cap = 0;
-    // tile table of gram_multi_kernel (runs of whole groups) for the cached grouping
-    int64_t *tile_dev = nullptr;
-    size_t tile_cap = 0;
-    int64_t tile_count = 0, tile_rows_built = 0;
-    bool tile_valid = false;
-    // fused multi-GPU gather (b200ols_set_peer_gather)
-    int n_peers = 0;
-    double *peer_coef[8] = {};
-    int64_t peer_group_base = 0, peer_total_groups = 0;
-    // optional device-side timing of the dominant kernel
-    bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;
-    std::vector<cudaEvent_t> event_pool;
-};
-
-struct ProfScope {  // brackets a launch with events when profiling is on
-    b200ols_ctx *c;
-    cudaEvent_t a = nullptr, b = nullptr;
-    explicit ProfScope(b200ols_ctx *ctx) : c(ctx) {
-        if (!c->profiling) return;
-        auto get = [&](cudaEvent_t *ev) {
-            if (!c->event_pool.empty()) { *ev = c->event_pool.back(); c->event_pool.pop_back(); return true; }
-            return cudaEventCreate(ev) == cudaSuccess;
-        };
-        if (get(&a) && get(&b)) cudaEventRecord(a, c->stream);
-    }
-    ~ProfScope() {
-        if (a && b) {
-            cudaEventRecord(b, c->stream);
-            c->prof.emplace_back(a, b);
-        }
-    }
-};
-
-static int arena_reserve(b200ols_ctx *c, size_t bytes) {
-    if (bytes <= c->arena_cap) return 0;
-    size_t cap = std::max(bytes + (bytes >> 2), static_cast<size_t>(64) << 20);
-    void *p = nullptr;
-    CU(cudaMalloc(&p, cap));
-    if (c->arena) c->retired.push_back(c->arena);
-    c->arena = static_cast<char *>(p);
-    c->arena_cap = cap;
-    return 0;
-}
-
-template <typename U>
-static U *arena_alloc(b200ols_ctx *c, size_t count) {
-    const size_t bytes = (count * sizeof(U) + 255) & ~static_cast<size_t>(255);
-    U *p = reinterpret_cast<U *>(c->arena + c->arena_off);
-    c->arena_off += bytes;
-    if (c->arena_off > c->arena_cap) c->arena_overflow = true;  // checked by ARENA_GUARD before any launch
-    return p;
-}
-
-#define ARENA_GUARD(c)                                                                                  \
-    do {                                                                                                \
-        if ((c)->arena_overflow) {                                                                      \
-            (c)->arena_overflow = false;                                                                \
-            return fail(B200OLS_ERR_CUDA, "internal: device arena under-sized (%zu > %zu)", (c)->arena_off, \
-                        (c)->arena_cap);                                                                \
-        }                                                                                               \
-    } while (0)
-
-// `bytes` = end offset needed (c->pinned_off based).  Offsets handed out are absolute inside the buffer.
-static int pinned_reserve(b200ols_ctx *c, size_t bytes) {
-    const size_t need = bytes - c->pinned_base;  // bytes needed inside the current half
-    if (need <= c->pinned_cap / 2) return 0;
-    CU(cudaStreamSynchronize(c->stream));
-    char *old = c->pinned;
-    const size_t used = c->pinned_off - c->pinned_base;
-    size_t half = std::max(need + (need >> 1), static_cast<size_t>(2) << 20);
-    half = (half + 4095) & ~static_cast<size_t>(4095);
-    char *fresh = nullptr;
-    CU(cudaMallocHost(reinterpret_cast<void **>(&fresh), 2 * half));
-    const size_t new_base = c->pinned_half ? half : 0;
-    if (old && used) std::memcpy(fresh + new_base, old + c->pinned_base, used);
-    if (old) cudaFreeHost(old);
-    c->pinned = fresh;
-    c->pinned_cap = 2 * half;
-    c->pinned_base = new_base;
-    c->pinned_off = new_base + used;
-    c->pinned_ev_set[0] = c->pinned_ev_set[1] = false;  // everything was synchronised above
-    return 0;
-}
-
-// start of a call: switch to the other half of the pinned staging buffer
-static int pinned_begin(b200ols_ctx *c) {
-    c->pinned_half ^= 1;
-    const int h = c->pinned_half;
-    if (c->pinned_ev_set[h]) {
-        CU(cudaEventSynchronize(c->pinned_ev[h]));
-        c->pinned_ev_set[h] = false;
-    }
-    c->pinned_base = h ? c->pinned_cap / 2 : 0;
-    c->pinned_off = c->pinned_base;
-    return 0;
-}
-
-// end of a call: everything staged in this half has been enqueued
-static int pinned_end(b200ols_ctx *c) {
-    const int h = c->pinned_half;
-    if (!c->pinned_ev[h]) CU(cudaEventCreateWithFlags(&c->pinned_ev[h], cudaEventDisableTiming));
-    CU(cudaEventRecord(c->pinned_ev[h], c->stream));
-    c->pinned_ev_set[h] = true;
-    return 0;
-}
-
-static int free_retired(b200ols_ctx *c) {
-    if (c->retired.empty()) return 0;
-    CU(cudaStreamSynchronize(c->stream));
-    for (void *p : c->retired) cudaFree(p);
-    c->retired.clear();
-    return 0;
-}
 
 extern "C" int b200ols_version(void) { return B200OLS_VERSION; }
 extern "C" const char *b200ols_last_error(void) { return g_last_error.c_str(); }
@@ -277,6 +111,8 @@ extern "C" void b200ols_destroy(b200ols_ctx *c) {
     if (c->plan_dev) cudaFree(c->plan_dev);
     if (c->tile_dev) cudaFree(c->tile_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    stager_destroy(c->stager);
+    group_plan_destroy(c->gplan);
     for (int h = 0; h < 2; ++h)
         if (c->pinned_ev[h]) cudaEventDestroy(c->pinned_ev[h]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -557,6 +393,7 @@ static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool 
     const void *dev_vals[GRAM_MAX_COLS];
     const uint8_t *dev_bm[GRAM_MAX_COLS];
     const int64_t *dev_rowidx = nullptr;
+    std::vector<StageSeg> segs;  // host -> device copies of this frame (pageable sources are pipelined through the pinned ring)
     for (int cidx = 0; cidx < ncol; ++cidx) {
         dev_bm[cidx] = nullptr;
         if (f->memspace == B200OLS_DEVICE) {
@@ -564,24 +401,28 @@ static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool 
             dev_bm[cidx] = cols[cidx]->validity;
         } else {
             char *d = arena_alloc<char>(c, static_cast<size_t>(n_pad) * esz);
-            if (n > 0) CU(cudaMemcpyAsync(d, cols[cidx]->values, static_cast<size_t>(n) * esz, cudaMemcpyHostToDevice, c->stream));
+            if (n > 0) segs.push_back({cols[cidx]->values, d, static_cast<size_t>(n) * esz});
             if (n_pad > n) CU(cudaMemsetAsync(d + static_cast<size_t>(n) * esz, 0, static_cast<size_t>(n_pad - n) * esz, c->stream));
             dev_vals[cidx] = d;
             if (cols[cidx]->validity) {
                 uint8_t *b = arena_alloc<uint8_t>(c, bm_bytes);
-                CU(cudaMemcpyAsync(b, cols[cidx]->validity, bm_bytes, cudaMemcpyHostToDevice, c->stream));
+                segs.push_back({cols[cidx]->validity, b, bm_bytes});
                 dev_bm[cidx] = b;
             }
         }
     }
     if (f->row_index) {
-        if (f->memspace == B200OLS_DEVICE) {
+        if (f->memspace == B200OLS_DEVICE || f->row_index_on_device) {
             dev_rowidx = f->row_index;
         } else {
             int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(n));
-            CU(cudaMemcpyAsync(d, f->row_index, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream));
+            segs.push_back({f->row_index, d, sizeof(int64_t) * static_cast<size_t>(n)});
             dev_rowidx = d;
         }
+    }
+    if (!segs.empty()) {
+        if (c->arena_overflow) return fail(B200OLS_ERR_CUDA, "internal: device arena under-sized before staging");
+        TRY(stage_h2d(c, segs.data(), static_cast<int>(segs.size())));
     }
     for (int cidx = 0; cidx < ncol; ++cidx) {
         st->raw[cidx] = dev_vals[cidx];
@@ -595,13 +436,11 @@ static int stage_frame(b200ols_ctx *c, const b200ols_frame *f, int policy, bool 
     // 2) gather / null policy pass (only when needed)
     int fill, mask_kind;
     policy_to_prep(policy, moving, &fill, &mask_kind);
-    const bool need_prep = any_validity || dev_rowidx != nullptr;
+    bool misaligned = false;  // e.g. a torch slice x[1:]: the streaming kernels need 16-byte aligned columns -> copy pass
+    if (f->memspace == B200OLS_DEVICE)
+        for (int cidx = 0; cidx < ncol; ++cidx) misaligned = misaligned || (reinterpret_cast<uintptr_t>(dev_vals[cidx]) & 15u) != 0;
+    const bool need_prep = any_validity || dev_rowidx != nullptr || misaligned;
     if (!need_prep) {
-        if (f->memspace == B200OLS_DEVICE) {
-            for (int cidx = 0; cidx < ncol; ++cidx)
-                if ((reinterpret_cast<uintptr_t>(dev_vals[cidx]) & 15u) != 0)
-                    return fail(B200OLS_ERR_INVALID, "device column %d is not 16-byte aligned", cidx);
-        }
         for (int j = 0; j < kd; ++j) st->feat[j] = dev_vals[j];
         st->y = dev_vals[kd];
         st->w = st->has_w ? dev_vals[kd + 1] : nullptr;
@@ -1078,6 +917,7 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
     if (any_svd) bytes += 2 * static_cast<size_t>(N) * F * 8 + static_cast<size_t>(G) * F * F * 8 + 4096;             // X^T, J, V
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
+    c->arena_overflow = false;
     TRY(pinned_begin(c));
 
     // columns on the device + pointer tables
@@ -1091,7 +931,10 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
             valid[cidx] = col->validity;
         } else {
             char *d = arena_alloc<char>(c, static_cast<size_t>(N) * esz + 16);
-            if (N > 0) CU(cudaMemcpyAsync(d, col->values, static_cast<size_t>(N) * esz, cudaMemcpyHostToDevice, c->stream));
+            if (N > 0) {
+                const StageSeg sg = {col->values, d, static_cast<size_t>(N) * esz};
+                TRY(stage_h2d(c, &sg, 1));
+            }
             vals[cidx] = d;
             valid[cidx] = nullptr;
             if (col->validity) {
@@ -1113,7 +956,7 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
         bp.group_off = static_cast<const int64_t *>(d);
     }
     if (f->row_index) {
-        if (f->memspace == B200OLS_DEVICE) bp.row_index = f->row_index;
+        if (f->memspace == B200OLS_DEVICE || f->row_index_on_device) bp.row_index = f->row_index;
         else {
             int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(N));
             CU(cudaMemcpyAsync(d, f->row_index, sizeof(int64_t) * N, cudaMemcpyHostToDevice, c->stream));
@@ -1289,9 +1132,8 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
         CU(cudaGetLastError());
     }
     if (f->memspace == B200OLS_HOST) {
-        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
-        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(N), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        const StageSeg d2h[2] = {{out->values, dout, sizeof(double) * N}, {out->validity, dval, dval ? static_cast<size_t>(N) : 0}};
+        TRY(stage_d2h(c, d2h, 2));  // pageable outputs drain through the pinned ring; returns with the stream synchronised
     }
     return 0;
 }
@@ -1338,6 +1180,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     bytes += 1 << 20;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
+    c->arena_overflow = false;
     TRY(pinned_begin(c));
 
     Staged st;
@@ -1607,9 +1450,8 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         CU(cudaGetLastError());
     }
     if (f->memspace == B200OLS_HOST) {
-        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
-        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(N), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        const StageSeg d2h[2] = {{out->values, dout, sizeof(double) * N}, {out->validity, dval, dval ? static_cast<size_t>(N) : 0}};
+        TRY(stage_d2h(c, d2h, 2));  // pageable outputs drain through the pinned ring; returns with the stream synchronised
     }
     return 0;
 }
@@ -1777,6 +1619,7 @@ static int run_multi_target_impl(b200ols_ctx *c, const b200ols_frame *f0, int32_
     bytes += 1 << 20;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
+    c->arena_overflow = false;
     TRY(pinned_begin(c));
 
     Staged st;
@@ -1909,9 +1752,8 @@ static int run_multi_target_impl(b200ols_ctx *c, const b200ols_frame *f0, int32_
         CU(cudaGetLastError());
     }
     if (f->memspace == B200OLS_HOST) {
-        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * N * m, cudaMemcpyDeviceToHost, c->stream));
-        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(N) * m, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        const StageSeg d2h[2] = {{out->values, dout, sizeof(double) * N * m}, {out->validity, dval, dval ? static_cast<size_t>(N) * m : 0}};
+        TRY(stage_d2h(c, d2h, 2));  // pageable outputs drain through the pinned ring; returns with the stream synchronised
     }
     return 0;
 }
@@ -1981,6 +1823,7 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
     if (memspace == B200OLS_HOST) bytes += static_cast<size_t>(n_coef) * 2 * (static_cast<size_t>(n_rows) * 8 + bm + 1024) + static_cast<size_t>(n_rows) * 9 + 4096;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
+    c->arena_overflow = false;
     TRY(pinned_begin(c));
     c->last_flags = nullptr;
     auto stage = [&](const b200ols_column &col, size_t es, const void **v, const uint8_t **m) -> int {
@@ -1990,7 +1833,10 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
             return 0;
         }
         char *d = arena_alloc<char>(c, static_cast<size_t>(n_rows) * es + 16);
-        if (n_rows) CU(cudaMemcpyAsync(d, col.values, static_cast<size_t>(n_rows) * es, cudaMemcpyHostToDevice, c->stream));
+        if (n_rows) {
+            const StageSeg sg = {col.values, d, static_cast<size_t>(n_rows) * es};
+            TRY(stage_h2d(c, &sg, 1));
+        }
         *v = d;
         *m = nullptr;
         if (col.validity) {
@@ -2034,9 +1880,8 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
         CU(cudaGetLastError());
     }
     if (memspace == B200OLS_HOST) {
-        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * n_rows, cudaMemcpyDeviceToHost, c->stream));
-        if (dval) CU(cudaMemcpyAsync(out->validity, dval, static_cast<size_t>(n_rows), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        const StageSeg d2h[2] = {{out->values, dout, sizeof(double) * n_rows}, {out->validity, dval, dval ? static_cast<size_t>(n_rows) : 0}};
+        TRY(stage_d2h(c, d2h, 2));  // pageable outputs drain through the pinned ring; returns with the stream synchronised
     }
     if (c->pinned) pinned_end(c);
     return 0;
@@ -2170,6 +2015,7 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
     if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * (static_cast<size_t>(F) * 9 + 16) + 4096;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
+    c->arena_overflow = false;
     TRY(pinned_begin(c));
     c->last_flags = nullptr;
 
@@ -2255,9 +2101,8 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
         return 0;
     }
     if (f->memspace == B200OLS_HOST) {
-        CU(cudaMemcpyAsync(out->values, dout, sizeof(double) * out_elems, cudaMemcpyDeviceToHost, c->stream));
-        if (dval) CU(cudaMemcpyAsync(out->validity, dval, out_elems, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        const StageSeg d2h[2] = {{out->values, dout, sizeof(double) * out_elems}, {out->validity, dval, dval ? out_elems : 0}};
+        TRY(stage_d2h(c, d2h, 2));  // pageable outputs drain through the pinned ring; returns with the stream synchronised
     }
     return 0;
 }

@@ -91,6 +91,72 @@ def _float_array(a: np.ndarray) -> np.ndarray:
 
 
 @dataclass
+class DevicePtr:
+    """A raw device pointer owned by the engine (e.g. the permutation b200ols_group_plan_build leaves on the device)."""
+    ptr: int
+
+
+@dataclass
+class DevicePlan:
+    """Result of ``Engine.group_plan``: CSR groups of an `.over()` key set, planned on the device
+    (``b200ols_group_plan_build``).  ``offsets`` / ``first_row`` are host arrays; the permutation stays on the device
+    (``row_index``: DevicePtr, or None when the groups are contiguous row slices) and is valid until the engine's next plan."""
+    engine: "Engine"
+    n_rows: int
+    n_groups: int
+    offsets: np.ndarray
+    first_row: np.ndarray
+    row_index: Optional[DevicePtr]
+    device_ms: float
+    serial: int = 0
+
+    def _check(self):
+        if self.engine._plan_serial != self.serial:
+            raise RuntimeError("this group plan was superseded by a later plan on the same engine")
+
+    def row_index_numpy(self) -> np.ndarray:
+        self._check()
+        out = np.empty(self.n_rows, dtype=np.int64)
+        L.check(self.engine._lib.b200ols_group_plan_row_index(self.engine._ctx, out.ctypes.data, L.HOST))
+        return out
+
+    def group_of_row(self) -> np.ndarray:
+        """group id of every original row (int32) — the broadcast map of `.over()`"""
+        self._check()
+        out = np.empty(self.n_rows, dtype=np.int32)
+        L.check(self.engine._lib.b200ols_group_plan_group_of_row(self.engine._ctx, out.ctypes.data, L.HOST))
+        return out
+
+
+_KEY_DTYPES = {"int64": L.KEY_I64, "int32": L.KEY_I32, "uint64": L.KEY_U64, "uint32": L.KEY_U32,
+               "float64": L.KEY_F64, "float32": L.KEY_F32}
+
+
+def _key_column(k):
+    """key column -> (buffer kept alive, pointer, B200OLS_KEY_* dtype, is_device).  Small integer / bool keys are widened
+    to int32; anything else (strings, objects, datetimes) is dictionary-encoded on the host first — the codes ascend
+    with the key, so the device plan orders the groups as numpy.unique would."""
+    if _is_torch(k):
+        if k.is_cuda:
+            name = str(k.dtype).replace("torch.", "")
+            if name not in _KEY_DTYPES:
+                k = k.to(torch.int32 if name in ("int8", "int16", "uint8", "bool") else torch.int64)
+                name = str(k.dtype).replace("torch.", "")
+            k = k.contiguous()
+            return k, k.data_ptr(), _KEY_DTYPES[name], True
+        k = k.numpy()
+    k = np.asarray(k)
+    if k.dtype.name not in _KEY_DTYPES:
+        if k.dtype.kind in "iub" and k.dtype.itemsize < 4:
+            k = k.astype(np.int32)
+        else:
+            _, k = np.unique(k, return_inverse=True)
+            k = k.reshape(-1).astype(np.int64)
+    k = np.ascontiguousarray(k)
+    return k, k.ctypes.data, _KEY_DTYPES[k.dtype.name], False
+
+
+@dataclass
 class Batch:
     """All inputs of one `.over()` evaluation, as the C ABI wants them."""
     target: Col
@@ -98,7 +164,7 @@ class Batch:
     weights: Optional[Col] = None
     add_intercept: bool = False
     offsets: Optional[np.ndarray] = None    # int64 [G+1], host
-    row_index: object = None                # int64 [N] (numpy or CUDA tensor) or None
+    row_index: object = None                # int64 [N] (numpy or CUDA tensor), a DevicePtr (Engine.group_plan), or None
     n_groups: int = 1
 
     def harmonise(self) -> Tuple[int, int]:
@@ -145,6 +211,30 @@ class Engine:
         else:
             L.check(self._lib.b200ols_create_on_stream(device, C.c_void_p(stream), C.byref(self._ctx)))
         self.device = device
+        self._plan_serial = 0
+
+    def group_plan(self, keys: Sequence) -> DevicePlan:
+        """``b200ols_group_plan_build``: `.over()` key column(s) (numpy arrays or CUDA tensors) -> CSR groups, planned on
+        the device.  Groups ascend by key tuple, rows keep the frame's order inside a group."""
+        cols = [_key_column(k) for k in keys]
+        dev = [c_[3] for c_ in cols]
+        if any(dev) and not all(dev):
+            raise ValueError("all key columns must live in the same memory space (host or CUDA)")
+        n = int(cols[0][0].shape[0])
+        for c_ in cols:
+            if int(c_[0].shape[0]) != n:
+                raise ValueError("all key columns must be of equal length")
+        kc = (L.KeyColumn * len(cols))(*[L.KeyColumn(c_[1], c_[2], 0) for c_ in cols])
+        gp = L.GroupPlan()
+        L.check(self._lib.b200ols_group_plan_build(self._ctx, kc, len(cols), n, L.DEVICE if all(dev) else L.HOST, C.byref(gp)))
+        self._plan_serial += 1
+        G = int(gp.n_groups)
+        offsets = np.ctypeslib.as_array(C.cast(gp.group_offsets, C.POINTER(C.c_int64)), shape=(G + 1,)).copy()
+        first = (np.ctypeslib.as_array(C.cast(gp.group_first_row, C.POINTER(C.c_int64)), shape=(G,)).copy()
+                 if G > 0 else np.empty(0, dtype=np.int64))
+        del cols
+        return DevicePlan(self, n, G, offsets, first, DevicePtr(gp.row_index) if gp.row_index else None, float(gp.device_ms),
+                          self._plan_serial)
 
     def close(self):
         if self._ctx:
@@ -226,7 +316,10 @@ class Engine:
         else:
             fr.n_groups = 1
         ridx = b.row_index
-        if ridx is not None:
+        if isinstance(ridx, DevicePtr):
+            fr.row_index = ridx.ptr
+            fr.row_index_on_device = 1
+        elif ridx is not None:
             if memspace == L.DEVICE:
                 if not _is_torch(ridx):
                     ridx = torch.as_tensor(np.ascontiguousarray(ridx, dtype=np.int64), device=b.target.values.device)

@@ -32,6 +32,16 @@ import numpy as np
 from . import _lib as L
 from .engine import Batch, Col, Engine, as_col, get_engine, nan_or, _is_torch
 
+
+def torch_as_device(a: np.ndarray, device):
+    import torch
+    return torch.as_tensor(a, device=device)
+
+
+def torch_index(idx: np.ndarray, like):
+    import torch
+    return torch.as_tensor(idx, device=like.device)
+
 logger = logging.getLogger(__name__)
 
 __all__ = [
@@ -125,7 +135,7 @@ class Result:
     valid: Any = None
     fields: Optional[List[str]] = None      # coefficient struct field names
     keys: Optional[np.ndarray] = None       # group keys (per-group results)
-    group_of_row: Optional[np.ndarray] = None
+    group_of_row: Any = None                # [N] group id of every row, or a zero-argument callable producing it
 
     def to_numpy(self, broadcast: bool = False) -> np.ndarray:
         v = self.values.cpu().numpy() if _is_torch(self.values) else np.asarray(self.values)
@@ -136,6 +146,8 @@ class Result:
         elif self.fields is not None:
             pass  # coefficient NaN <=> null already
         if broadcast and self.group_of_row is not None:
+            if callable(self.group_of_row):          # device plan: the row -> group map is only built when asked for
+                self.group_of_row = self.group_of_row()
             v = v[self.group_of_row]
         return v
 
@@ -159,8 +171,9 @@ class Result:
 # grouping: polars' `.over()` / group_by split (reference: 3rd-party polars engine)
 # ------------------------------------------------------------------------------------------------
 def _group_plan(keys: Sequence[np.ndarray]):
-    """keys -> (unique keys, offsets [G+1], row_index [N] or None if groups are contiguous slices,
-    group_of_row [N])."""
+    """HOST statement of the group plan: keys -> (unique keys, offsets [G+1], row_index [N] or None if groups are
+    contiguous slices, group_of_row [N]).  The product plans on the device (`Engine.group_plan`, group_plan.cuh); this
+    numpy version is the specification the device plan is tested against (bit-identical offsets and permutation)."""
     if len(keys) == 1:
         k = np.asarray(keys[0])
         uniq, inv = np.unique(k, return_inverse=True)
@@ -340,18 +353,26 @@ class LsExpr:
         b, names = self.batch(frame)
         target = b.target
         keys = group_of_row = None
-        if self._over:
-            key_arrays = []
-            for k in self._over:
-                kv = frame[k] if isinstance(k, str) else parse_into_expr(k).resolve(frame).values
-                if _is_torch(kv):
-                    kv = kv.cpu().numpy()
-                key_arrays.append(np.asarray(kv))
-            keys, offsets, row_index, group_of_row = _group_plan(key_arrays)
-            b.offsets, b.row_index = offsets, row_index
         if engine is None:
             dev = target.values.device.index if target.is_device else 0
             engine = get_engine(dev or 0, torch_stream=target.is_device)
+        if self._over:
+            # `.over()`: keys -> CSR groups on the device (b200ols_group_plan_build); only the [G+1] offsets come back
+            key_arrays = []
+            for k in self._over:
+                kv = frame[k] if isinstance(k, str) else parse_into_expr(k).resolve(frame).values
+                if _is_torch(kv) and kv.is_cuda != target.is_device:
+                    kv = kv.cpu().numpy() if kv.is_cuda else kv.to(target.values.device)
+                elif not _is_torch(kv) and target.is_device:
+                    kv = torch_as_device(np.asarray(kv), target.values.device)
+                key_arrays.append(kv)
+            plan = engine.group_plan(key_arrays)
+            b.offsets, b.row_index = plan.offsets, plan.row_index
+            group_of_row = plan.group_of_row
+            if self.mode in ("coefficients", "statistics") and self.kind == "least_squares":
+                first = plan.first_row        # one representative row per group -> its key values
+                ks = [(kv[torch_index(first, kv)].cpu().numpy() if _is_torch(kv) else np.asarray(kv)[first]) for kv in key_arrays]
+                keys = ks[0] if len(ks) == 1 else np.rec.fromarrays(ks)
         if self.kind == "multi_target_least_squares":
             tcols = self.target_struct(frame)
             b.target = tcols[0][1]

@@ -27,7 +27,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     from polars_ols_b200 import _lib
     assert C.sizeof(_lib.Column) == 16
-    assert C.sizeof(_lib.Frame) == 8 + 16 + 16 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.Frame) == 8 + 16 + 16 + 8 + 8 + 8 + 8 + 8 + 8
+    assert _lib.Frame.row_index_on_device.offset == 80
+    assert C.sizeof(_lib.KeyColumn) == 16 and C.sizeof(_lib.GroupPlan) == 48
     assert C.sizeof(_lib.OLSKwargs) == 56 and C.sizeof(_lib.RLSKwargs) == 40 and C.sizeof(_lib.RollingKwargs) == 32
     assert _lib.Frame.target.offset == 24 and _lib.Frame.group_offsets.offset == 64
 
