@@ -9,6 +9,8 @@
 // final event.  The reverse direction (large prediction / coefficient outputs into pageable numpy buffers) runs
 // the same ring backwards.  Buffers that are already page-locked (b200ols_host_alloc, cudaHostRegister'd,
 // torch pinned tensors) are detected with cudaPointerGetAttributes and copied directly.
+#include <emmintrin.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <cstdlib>
@@ -18,6 +20,29 @@
 #include "engine_ctx.h"
 
 namespace b200 {
+
+// pageable -> pinned slot with non-temporal stores: the slot is read next by the DMA engine, not by this core, so the
+// destination lines need neither a read-for-ownership nor a place in the cache (one third less host DRAM traffic
+// than memcpy, which matters because the copy threads share the memory controllers with the DMA reads)
+static void copy_streaming(char *dst, const char *src, size_t n) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0) {
+        std::memcpy(dst, src, n);
+        return;
+    }
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i + 48), d);
+    }
+    _mm_sfence();
+    if (i < n) std::memcpy(dst + i, src + i, n - i);
+}
 
 struct Stager {
     int device = 0;
@@ -32,6 +57,7 @@ struct Stager {
     struct Chunk { char *host; char *dev; size_t bytes; };
     std::vector<Chunk> chunks;
     bool d2h = false;
+    bool streaming = true;  // non-temporal stores into the ring (B200OLS_STAGE_NT=0: plain memcpy)
     std::atomic<size_t> next{0};
     std::atomic<int> failed{0};
     size_t finished = 0;
@@ -54,7 +80,7 @@ struct Stager {
             cudaError_t e = cudaSuccess;
             if (gen > 0) e = cudaEventSynchronize(ev[slot]);  // the DMA that last used this slot has drained
             if (!d2h) {
-                std::memcpy(buf, ch.host, ch.bytes);
+                if (streaming) copy_streaming(buf, ch.host, ch.bytes); else std::memcpy(buf, ch.host, ch.bytes);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(ch.dev, buf, ch.bytes, cudaMemcpyHostToDevice, copy_stream);
                 if (e == cudaSuccess) e = cudaEventRecord(ev[slot], copy_stream);
             } else {
@@ -123,10 +149,12 @@ static int stager_get(b200ols_ctx *c, Stager **out) {
     int threads = static_cast<int>(std::thread::hardware_concurrency());
     threads = std::max(1, std::min(8, threads / 2));
     if (const char *v = std::getenv("B200OLS_STAGE_THREADS")) threads = std::max(1, std::min(64, std::atoi(v)));
-    size_t slot_mb = 4;
-    if (const char *v = std::getenv("B200OLS_STAGE_SLOT_MB")) slot_mb = static_cast<size_t>(std::max(1, std::min(64, std::atoi(v))));
-    s->slot_bytes = slot_mb << 20;
+    size_t slot_kb = 4096;
+    if (const char *v = std::getenv("B200OLS_STAGE_SLOT_KB")) slot_kb = static_cast<size_t>(std::max(64, std::min(65536, std::atoi(v))));
+    s->slot_bytes = slot_kb << 10;
     s->nslots = std::max(2 * threads, 8);
+    if (const char *v = std::getenv("B200OLS_STAGE_SLOTS")) s->nslots = std::max(threads + 1, std::min(256, std::atoi(v)));
+    if (const char *v = std::getenv("B200OLS_STAGE_NT")) s->streaming = std::atoi(v) != 0;
     cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->gate_ev, cudaEventDisableTiming);

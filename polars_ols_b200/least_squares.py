@@ -368,7 +368,10 @@ class LsExpr:
                 key_arrays.append(kv)
             plan = engine.group_plan(key_arrays)
             b.offsets, b.row_index = plan.offsets, plan.row_index
-            group_of_row = plan.group_of_row
+            def group_of_row(plan=plan, key_arrays=key_arrays, engine=engine):
+                # built on demand (the `.over()` broadcast); a later plan on the engine replaced the device tables -> re-plan
+                cur = plan if engine._plan_serial == plan.serial else engine.group_plan(key_arrays)
+                return cur.group_of_row()
             if self.mode in ("coefficients", "statistics") and self.kind == "least_squares":
                 first = plan.first_row        # one representative row per group -> its key values
                 ks = [(kv[torch_index(first, kv)].cpu().numpy() if _is_torch(kv) else np.asarray(kv)[first]) for kv in key_arrays]
