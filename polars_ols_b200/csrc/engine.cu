@@ -1893,14 +1893,33 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
 int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets, bool f64, int sm_count, char *ws,
                          int64_t *launches) {
     const int64_t G = p.n_groups;
-    int64_t L = moving_chunk_len(p.n_rows, sm_count, p.kind, p.window);
-    // the chunk-interleaved copies take L * n_chunks elements per column: with many series much shorter than
-    // L that pads badly, so shrink L until the padded size is at most 2N + 64G (always true at L = 64)
-    for (;;) {
-        int64_t nch = 0;
-        for (int64_t g = 0; g < G; ++g) nch += (offsets[g + 1] - offsets[g] + L - 1) / L;
-        if (L <= 64 || L * nch <= 2 * p.n_rows + 64 * G) break;
-        L >>= 1;
+    // three execution paths (moving.cuh): k <= 8 null-free frames stream through per-thread staging rings
+    // (moving_fast.cuh); k <= 8 with a row mask / min_periods > window keep the chunk-interleaved copies; 9 <= k <= 64 run
+    // one block per chunk (moving_wide.cuh)
+    static const bool fast_enabled = [] { const char *v = std::getenv("B200OLS_MOVING_FAST"); return !v || std::atoi(v) != 0; }();
+    const bool wide = p.F > 8;
+    p.fast = (!wide && fast_enabled && !p.mask && (p.kind == MOVING_RLS || p.min_periods <= p.window)) ? 1 : 0;
+    int64_t L;
+    if (p.fast) {
+        // one chunk per resident thread (a single wave: every thread carries the same work), never below 64 rows
+        const int nb = std::max(1, moving_fast_blocks_per_sm(f64, p.F, p.kind, p.kd + 1 + (p.w ? 1 : 0)));
+        const int64_t resident = static_cast<int64_t>(sm_count) * nb * 128;
+        L = std::max<int64_t>(64, (p.n_rows + resident - 1) / resident);
+        L = (L + 7) & ~static_cast<int64_t>(7);
+    } else if (wide) {
+        L = 64;
+        const int64_t want = p.n_rows / (static_cast<int64_t>(sm_count) * 16);
+        while (L < want) L <<= 1;
+    } else {
+        L = moving_chunk_len(p.n_rows, sm_count, p.kind, p.window);
+        // the chunk-interleaved copies take L * n_chunks elements per column: with many series much shorter than
+        // L that pads badly, so shrink L until the padded size is at most 2N + 64G (always true at L = 64)
+        for (;;) {
+            int64_t nch = 0;
+            for (int64_t g = 0; g < G; ++g) nch += (offsets[g + 1] - offsets[g] + L - 1) / L;
+            if (L <= 64 || L * nch <= 2 * p.n_rows + 64 * G) break;
+            L >>= 1;
+        }
     }
     std::vector<int64_t> r0, r1, gco(static_cast<size_t>(G) + 1);
     std::vector<int32_t> cg;
@@ -1934,14 +1953,14 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     int64_t *d_r1 = reinterpret_cast<int64_t *>(take(nc * 8 + 8));
     int32_t *d_cg = reinterpret_cast<int32_t *>(take(nc * 4 + 8));
     int64_t *d_gco = reinterpret_cast<int64_t *>(take((G + 1) * 8));
-    p.series_info = reinterpret_cast<int64_t *>(take(static_cast<size_t>(G) * 24 + 8));
+    p.series_info = reinterpret_cast<int64_t *>(take(static_cast<size_t>(G) * 32 + 8));
     p.summaries = reinterpret_cast<double *>(take(p.kind == MOVING_RLS ? nc * moving_rec(p.F) * 8 + 8 : 8));
     int64_t *d_s0 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
     int64_t *d_s1 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
     int64_t *d_gso = reinterpret_cast<int64_t *>(take((G + 1) * 8));
     p.sup = reinterpret_cast<double *>(take(ns * moving_rec(p.F) * 8 + 8));
     p.n_super = static_cast<int64_t>(ns);
-    {   // chunk-interleaved column copies (filled by chunk_transpose_kernel)
+    if (!p.fast && !wide) {   // chunk-interleaved column copies (filled by chunk_transpose_kernel)
         p.chunk_len = L;
         p.chunk_shift = 0;
         while ((int64_t{1} << p.chunk_shift) < L) ++p.chunk_shift;
@@ -1984,7 +2003,7 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
     if (policy < B200OLS_NULL_IGNORE || policy > B200OLS_NULL_DROP_WINDOW) return fail(B200OLS_ERR_INVALID, "Invalid null_policy detected!");
     const int F = f->n_features + (f->add_intercept ? 1 : 0);
     if (F > MOVING_MAX_K)
-        return fail(B200OLS_ERR_UNSUPPORTED, "rls/rolling with more than %d coefficients is not implemented on the device yet", MOVING_MAX_K);
+        return fail(B200OLS_ERR_UNSUPPORTED, "rls / rolling_ols with more than %d coefficients (%d) is not implemented on the device", MOVING_MAX_K, F);
     CU(cudaSetDevice(c->device));
     TRY(free_retired(c));
     const int64_t N = f->n_rows, G = f->n_groups;

@@ -69,11 +69,12 @@ struct MovingParams {
     int64_t n_super;                  // rls scan: runs of <= SCAN_SUPER chunks of one series
     const int64_t *sup_c0, *sup_c1, *group_sup_off;
     double *sup;                      // [n_super][REC]
-    int64_t *series_info;             // [G][3] rolling: mpv, n_valid, all_nan
+    int64_t *series_info;             // [G][4] rolling: mpv, n_valid, all_nan, m_warm
     // rls continued from / summarised for another time shard (single long series):
     const double *init_info;          // [G][F*F+F] information state ENTERING each series (A row-major, b) or nullptr = prior
     double *state_out;                // [G][F*F+F+1] state LEAVING each series (lower triangle of A, b) and the decay D, or nullptr
     int state_only;                   // stop after the scan (b200ols_recursive_least_squares_state)
+    int fast;                         // staged thread-private rings (moving_fast.cuh): no mask, k <= 8, no transposed copies
 };
 
 __host__ __device__ constexpr int moving_rec(int K) { return K * K + K + 1; }  // doubles per chunk record: A, b, D
@@ -254,9 +255,10 @@ __global__ void __launch_bounds__(128) rolling_prepass_kernel(const MovingParams
     if (g >= p.n_groups) return;
     const DevSrc<T, K> src = make_src<T, K>(p);
     const RollingSeries rs = rolling_prepass(src, p.group_off[g], p.group_off[g + 1], p.min_periods);
-    p.series_info[g * 3 + 0] = rs.mpv;
-    p.series_info[g * 3 + 1] = rs.n_valid;
-    p.series_info[g * 3 + 2] = rs.all_nan;
+    p.series_info[g * 4 + 0] = rs.mpv;
+    p.series_info[g * 4 + 1] = rs.n_valid;
+    p.series_info[g * 4 + 2] = rs.all_nan;
+    p.series_info[g * 4 + 3] = rs.m_warm;
 }
 
 template <typename T, int K>
@@ -268,13 +270,15 @@ __global__ void __launch_bounds__(128, (K <= MOVING_OCC_K ? MOVING_MIN_BLOCKS : 
     const int64_t g0 = p.group_off[g], g1 = p.group_off[g + 1];
     RollingSeries rs;
     if (p.series_info) {
-        rs.mpv = p.series_info[g * 3 + 0];
-        rs.n_valid = p.series_info[g * 3 + 1];
-        rs.all_nan = static_cast<int>(p.series_info[g * 3 + 2]);
+        rs.mpv = p.series_info[g * 4 + 0];
+        rs.n_valid = p.series_info[g * 4 + 1];
+        rs.all_nan = static_cast<int>(p.series_info[g * 4 + 2]);
+        rs.m_warm = p.series_info[g * 4 + 3];
     } else {  // no mask: every row is valid
         rs.mpv = p.min_periods;
         rs.n_valid = (g1 - g0 < p.min_periods) ? (g1 - g0) : p.min_periods;
         rs.all_nan = (g1 - g0) < p.min_periods;
+        rs.m_warm = p.min_periods;
     }
     RollingCfg cfg{p.window, p.min_periods, p.alpha, p.fixed_window};
     DevEmit<T, K, DevSrcT<T, K>> emit{p, src};
@@ -445,66 +449,13 @@ inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int F) {
            static_cast<size_t>(F + 3) * (static_cast<size_t>(n_rows) * 2 + static_cast<size_t>(n_groups + 1) * 64 + 4096) * 8;
 }
 
-template <typename T, int K>
-static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const int64_t *group_chunk_off_dev,
-                                   int64_t *launches) {
-    const unsigned cb = static_cast<unsigned>((p.n_chunks + 127) / 128);
-    if (p.n_chunks == 0) return cudaSuccess;
-    {   // chunk-interleaved copies of every input column (one coalesced read + write of the data)
-        TransposeParams tp;
-        int nc = 0;
-        for (int j = 0; j <= p.kd; ++j) { tp.src[nc] = p.cols[j]; tp.dst[nc] = const_cast<void *>(p.tcols[j]); ++nc; }
-        if (p.w) { tp.src[nc] = p.w; tp.dst[nc] = const_cast<void *>(p.tw); ++nc; }
-        if (p.mask) { tp.src[nc] = p.mask; tp.dst[nc] = const_cast<void *>(p.tmask); ++nc; }
-        tp.chunk_r0 = p.chunk_r0;
-        tp.chunk_r1 = p.chunk_r1;
-        tp.n_chunks = p.n_chunks;
-        tp.chunk_len = p.chunk_len;
-        const dim3 grid(static_cast<unsigned>((p.n_chunks + 31) / 32), static_cast<unsigned>((p.chunk_len + 31) / 32), static_cast<unsigned>(nc));
-        chunk_transpose_kernel<T><<<grid, 256, 0, stream>>>(tp);
-        ++*launches;
-    }
-    if (p.kind == MOVING_ROLLING) {
-        if (p.mask) {
-            rolling_prepass_kernel<T, K><<<static_cast<unsigned>((p.n_groups + 127) / 128), 128, 0, stream>>>(p);
-            ++*launches;
-        } else {
-            p.series_info = nullptr;
-        }
-        rolling_main_kernel<T, K><<<cb, 128, 0, stream>>>(p);
-        ++*launches;
-    } else {
-        rls_summary_kernel<T, K><<<cb, 128, 0, stream>>>(p);
-        const unsigned sb = static_cast<unsigned>((p.n_super * 32 + 127) / 128);
-        rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 0, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
-        rls_scan_kernel<K><<<static_cast<unsigned>((p.n_groups * 32 + 127) / 128), 128, 0, stream>>>(p, 1, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
-        *launches += 3;
-        if (p.state_only) return cudaGetLastError();
-        rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 2, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
-        rls_main_kernel<T, K><<<cb, 128, 0, stream>>>(p);
-        *launches += 2;
-    }
-    return cudaGetLastError();
-}
-
-// Coefficient counts KLO..KHI of one dtype (one translation unit each: the K >= 9 instantiations spill and take minutes
-// to compile, so they are spread over several .cu files that nvcc builds in parallel — moving_f64_r*.cu / moving_f32_r*.cu)
-template <typename T, int KLO, int KHI>
-static cudaError_t launch_moving_range(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches) {
-    if constexpr (KLO >= KHI) {
-        return launch_moving_t<T, KHI>(s, p, gco, launches);
-    } else {
-        if (p.F <= KLO) return launch_moving_t<T, KLO>(s, p, gco, launches);
-        return launch_moving_range<T, KLO + 1, KHI>(s, p, gco, launches);
-    }
-}
-
-// ranges: r0 = 1..8, r1 = 9..11, r2 = 12..14, r3 = 15..16 (defined in moving_f{64,32}_r{0..3}.cu)
-#define B200_MOVING_DECL(SUFFIX) \
-    cudaError_t moving_launch_##SUFFIX(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
-B200_MOVING_DECL(f64_r0) B200_MOVING_DECL(f64_r1) B200_MOVING_DECL(f64_r2) B200_MOVING_DECL(f64_r3)
-B200_MOVING_DECL(f32_r0) B200_MOVING_DECL(f32_r1) B200_MOVING_DECL(f32_r2) B200_MOVING_DECL(f32_r3)
-#undef B200_MOVING_DECL
+// thread-per-chunk kernels for 1..8 coefficients (moving_f{64,32}_r0.cu); 9..MOVING_WIDE_MAX_K coefficients run the
+// block-per-chunk kernels of moving_wide.cuh (moving_wide.cu)
+cudaError_t moving_launch_f64_r0(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
+cudaError_t moving_launch_f32_r0(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
+cudaError_t moving_launch_wide(cudaStream_t s, MovingParams &p, bool f64, const int64_t *gco, int64_t *launches);
+// resident thread blocks per SM of the staged (moving_fast.cuh) kernels for this shape: sizes the chunks of the fast path
+int moving_fast_blocks_per_sm(bool f64, int F, int kind, int n_cols);
 
 // defined in moving_f64.cu / moving_f32.cu: dispatch on the number of coefficients
 cudaError_t moving_launch_f64(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);

@@ -1,11 +1,17 @@
-// moving_f64.cu — f64 rls / rolling kernels: dispatch on the number of coefficients to the translation units that
-// instantiate them (moving_f64_r0..r3.cu, see moving.cuh)
+// moving_f64.cu / moving_f32.cu merged: dispatch of the rls / rolling launches on dtype and coefficient count
 #include "moving.cuh"
 namespace b200 {
+int moving_fast_blocks_f64(int F, int kind, int nc);
+int moving_fast_blocks_f32(int F, int kind, int nc);
 cudaError_t moving_launch_f64(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches) {
     if (p.F <= 8) return moving_launch_f64_r0(s, p, gco, launches);
-    if (p.F <= 11) return moving_launch_f64_r1(s, p, gco, launches);
-    if (p.F <= 14) return moving_launch_f64_r2(s, p, gco, launches);
-    return moving_launch_f64_r3(s, p, gco, launches);
+    return moving_launch_wide(s, p, true, gco, launches);
+}
+cudaError_t moving_launch_f32(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches) {
+    if (p.F <= 8) return moving_launch_f32_r0(s, p, gco, launches);
+    return moving_launch_wide(s, p, false, gco, launches);
+}
+int moving_fast_blocks_per_sm(bool f64, int F, int kind, int n_cols) {
+    return f64 ? moving_fast_blocks_f64(F, kind, n_cols) : moving_fast_blocks_f32(F, kind, n_cols);
 }
 }  // namespace b200

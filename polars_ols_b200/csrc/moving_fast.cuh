@@ -1,0 +1,336 @@
+// moving_fast.cuh — the streaming kernels of rolling_least_squares / recursive_least_squares for null-free frames
+// with k <= 8 coefficients (the C4 shape: ONE series of 50M rows x 6 features, and every `.over()` frame without
+// nulls).  Same chunk algorithms as moving_core.cuh (one thread per time chunk, window / information state rebuilt
+// exactly at the chunk start), but the rows reach the thread through a PRIVATE staging ring in shared memory:
+//
+//   * every thread walks its own chunk, so consecutive lanes read addresses a whole chunk apart.  Instead of first
+//     transposing the frame into a chunk-interleaved copy (an extra read + write pass over all inputs,
+//     chunk_transpose_kernel) and then paying one exposed HBM round trip per row, each thread issues 16-byte
+//     cp.async copies (SASS LDGSTS) for its next rows straight from the caller's SoA columns into its own slots
+//     of a shared-memory ring, `MF_DEPTH` stages ahead of the row it is working on.  A 16-byte unit is two f64
+//     (four f32) consecutive rows of one column: sectors are consumed whole within one stage or the next.
+//   * the ring is laid out [slot][column][thread] in 16-byte units: the lanes of a warp write and read consecutive
+//     units (no bank conflicts), and since a thread only ever reads what it copied itself no block barrier is
+//     needed — cp.async.wait_group orders a thread's own copies.
+//   * rolling: the row leaving the window (r - W) is a second stream through a second ring, delayed by W rows;
+//     the window sums entering a chunk are accumulated from the W rows before it through the same lead stream.
+//
+// Reference semantics restated (null-free): src/least_squares.rs:848-986 (warm-up over the first min_periods rows,
+// first coefficients at row min_periods - 1, rank-1 add / subtract + Cholesky (LU fallback) per row; both null
+// branches coincide without nulls while min_periods <= window) and :505-598 (RLS).  Frames with a row mask, with
+// min_periods > window, or with k > 8 take the general kernels of moving.cuh.
+#pragma once
+#include "moving.cuh"
+
+namespace b200 {
+
+#ifndef MF_DEPTH
+#define MF_DEPTH 1          // stages (16-byte units per column) in flight ahead of the one being consumed
+#endif
+// resident blocks per SM the register allocation aims at (ptxas -v, k = 6 f64): rolling 168 registers at 3 blocks
+// (12 warps / SM, 56 bytes of spills in the cold LU fallback); rls 240 registers at 2 blocks, heavy spills at 3
+#ifndef MF_MIN_BLOCKS_ROLLING
+#define MF_MIN_BLOCKS_ROLLING 3
+#endif
+#ifndef MF_MIN_BLOCKS_RLS
+#define MF_MIN_BLOCKS_RLS 2
+#endif
+constexpr int MF_THREADS = 128;
+constexpr int MF_LEAD_SLOTS = MF_DEPTH + 1;
+constexpr int MF_LAG_SLOTS = MF_DEPTH + 2;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// One thread's view of its staging rings.  Stage q of a stream = rows [a0 + q * RPU, a0 + (q + 1) * RPU) of every
+// column (RPU rows per 16-byte unit), kept in slot q % SLOTS.
+template <typename T, int K>
+struct FastSrc {
+    static constexpr int RPU = 16 / static_cast<int>(sizeof(T));
+    const T *col[K + 2];   // [0, kd) features, [kd] target, [kd + 1] weights
+    int nc;                // columns staged
+    int kd, has_w, w_is_sqrt;
+    uint32_t lead, lag;    // shared-memory byte address of this thread's unit 0 in each ring
+    int64_t a0;            // first staged row (multiple of RPU: the copies are 16-byte aligned)
+    int64_t n_lim;         // rows at or beyond this are never fetched (end of the frame, padded to 16 bytes)
+
+    __device__ __forceinline__ void issue(uint32_t ring, int slots, int64_t q) const {
+        if (q < 0) return;
+        const int64_t row = a0 + q * RPU;
+        if (row >= n_lim) return;
+        const uint32_t dst = ring + static_cast<uint32_t>((q % slots) * nc) * (MF_THREADS * 16u);
+#pragma unroll
+        for (int c = 0; c < K + 2; ++c)  // compile-time bound: `col` stays in registers
+            if (c < nc) cp_async16(dst + static_cast<uint32_t>(c) * (MF_THREADS * 16u), col[c] + row);
+    }
+    // scaled features (incl. intercept), scaled target, raw target and 1/sqrt(w)-able scale of staged row r
+    __device__ __forceinline__ void read(uint32_t ring, int slots, int64_t r, double (&x)[K], double &y, T &y_raw, T &s) const {
+        const int64_t off = r - a0;
+        const int64_t q = off / RPU;
+        const uint32_t e = static_cast<uint32_t>(off - q * RPU) * static_cast<uint32_t>(sizeof(T));
+        const uint32_t src = ring + static_cast<uint32_t>((q % slots) * nc) * (MF_THREADS * 16u) + e;
+        auto lds = [&](int c) -> T {
+            T v;
+            if constexpr (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(src + static_cast<uint32_t>(c) * (MF_THREADS * 16u)));
+            else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(src + static_cast<uint32_t>(c) * (MF_THREADS * 16u)));
+            return v;
+        };
+        s = T(1);
+        if (has_w) {
+            const T wv = lds(kd + 1);
+            s = w_is_sqrt ? wv : static_cast<T>(sqrt(wv));
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[j] = (j < kd) ? static_cast<double>(static_cast<T>(lds(j) * s)) : static_cast<double>(s);
+        y_raw = lds(kd);
+        y = static_cast<double>(static_cast<T>(y_raw * s));
+    }
+};
+
+template <typename T, int K>
+__device__ __forceinline__ FastSrc<T, K> make_fast_src(const MovingParams &p, unsigned char *smem) {
+    FastSrc<T, K> s;
+#pragma unroll
+    for (int j = 0; j < K + 2; ++j) s.col[j] = nullptr;
+    s.kd = p.kd;
+    s.has_w = p.w ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < K + 2; ++j) {
+        if (j <= p.kd) s.col[j] = static_cast<const T *>(p.cols[j]);
+        else if (j == p.kd + 1 && s.has_w) s.col[j] = static_cast<const T *>(p.w);
+    }
+    s.nc = p.kd + 1 + s.has_w;
+    s.w_is_sqrt = p.w_is_sqrt;
+    const uint32_t base = smem_u32(smem) + threadIdx.x * 16u;
+    s.lead = base;
+    s.lag = base + static_cast<uint32_t>(MF_LEAD_SLOTS * s.nc) * (MF_THREADS * 16u);
+    s.n_lim = p.n_rows;
+    s.a0 = 0;
+    return s;
+}
+
+__host__ __device__ inline size_t moving_fast_smem(int nc, bool rolling) {
+    return static_cast<size_t>(MF_LEAD_SLOTS + (rolling ? MF_LAG_SLOTS : 0)) * nc * MF_THREADS * 16;
+}
+
+// output of one row (same rules as DevEmit in moving.cuh): coefficients, or prediction / residual with the WLS
+// un-scaling, `fill_nan(None)` for rolling
+template <typename T, int K>
+__device__ __forceinline__ void fast_emit(const MovingParams &p, int64_t r, const double (&beta)[K], const double (&x)[K], T y_raw, T s) {
+    const int64_t orow = p.row_index ? p.row_index[r] : r;
+    if (p.mode == 2) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            p.out[orow * K + j] = beta[j];
+            if (p.out_valid) p.out_valid[orow * K + j] = (beta[j] == beta[j]) ? 1 : 0;
+        }
+        return;
+    }
+    double pred = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) pred += x[j] * beta[j];
+    if (p.w) pred *= static_cast<double>(T(1) / s);
+    bool valid = true;
+    if (p.mode == 1) {
+        double t = static_cast<double>(y_raw);
+        if (p.target != p.cols[p.kd]) t = static_cast<double>(static_cast<const T *>(p.target)[p.target_is_packed ? r : orow]);
+        pred = t - pred;
+        if (p.target_validity) valid = (p.target_validity[orow >> 3] >> (orow & 7)) & 1;
+    }
+    if (p.kind == MOVING_ROLLING) valid = valid && (pred == pred);
+    p.out[orow] = pred;
+    if (p.out_valid) p.out_valid[orow] = valid ? 1 : 0;
+}
+
+template <typename T, int K>
+__device__ __forceinline__ void fast_emit_nan(const MovingParams &p, int64_t r) {
+    const int64_t orow = p.row_index ? p.row_index[r] : r;
+    if (p.mode == 2) {
+        for (int j = 0; j < K; ++j) {
+            p.out[orow * K + j] = NAN;
+            if (p.out_valid) p.out_valid[orow * K + j] = 0;
+        }
+        return;
+    }
+    p.out[orow] = NAN;
+    if (p.out_valid) p.out_valid[orow] = 0;
+}
+
+// ---- rolling ---------------------------------------------------------------------------------------------
+// Requires: no row mask, min_periods <= window.  Chunk [c0, c1) of series [g0, g1):
+//   rows before g0 + min_periods - 1 are NaN; the state entering the first coefficient row rs of the chunk is
+//   alpha I + Gram(rows [max(g0, rs - W), rs)); then per row r: + row r, - row r - W (when r - W >= g0), solve.
+template <typename T, int K>
+__global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_fast_kernel(const MovingParams p) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
+    constexpr int RPU = FastSrc<T, K>::RPU;
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    const int64_t g = p.chunk_group[c];
+    const int64_t g0 = p.group_off[g], g1 = p.group_off[g + 1];
+    const int64_t c0 = p.chunk_r0[c], c1 = p.chunk_r1[c];
+    const int64_t W = p.window;
+    const int64_t first = g0 + p.min_periods - 1;
+    int64_t r = c0;
+    if ((g1 - g0) < p.min_periods) {  // fewer rows than min_periods: all NaN (src/least_squares.rs:893-900)
+        for (; r < c1; ++r) fast_emit_nan<T, K>(p, r);
+        return;
+    }
+    for (; r < c1 && r < first; ++r) fast_emit_nan<T, K>(p, r);
+    if (r >= c1) return;
+    const int64_t rs = r;                                  // first row of this chunk that carries coefficients
+    const int64_t s0 = (rs - W > g0) ? rs - W : g0;         // oldest row of the window entering rs
+    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    src.a0 = s0 & ~static_cast<int64_t>(RPU - 1);
+    // lag stage consumed while the lead works on stage q:  q - lagq (and q - lagq + 1 when W is not a multiple of RPU)
+    const int64_t lagq = (W + RPU - 1) / RPU;
+
+    NormalState<K> st;
+    st.clear();
+    if (p.alpha > 0.0) st.add_diag(p.alpha);
+    double beta[K], x[K], xo[K], y, yo;
+    T y_raw, s, yr2, s2;
+
+    // prologue: the stages a boundary `b` in [-MF_DEPTH, 0) would have issued
+#pragma unroll
+    for (int b = -MF_DEPTH; b < 0; ++b) {
+        src.issue(src.lead, MF_LEAD_SLOTS, b + MF_DEPTH);
+        src.issue(src.lag, MF_LAG_SLOTS, b - lagq + MF_DEPTH + 1);
+        cp_async_commit();
+    }
+    const int64_t q_end = (c1 - src.a0 + RPU - 1) / RPU;
+    for (int64_t q = 0; q < q_end; ++q) {
+        src.issue(src.lead, MF_LEAD_SLOTS, q + MF_DEPTH);
+        src.issue(src.lag, MF_LAG_SLOTS, q - lagq + MF_DEPTH + 1);
+        cp_async_commit();
+        cp_async_wait<MF_DEPTH>();  // lead stage q and lag stages <= q - lagq + 1 have landed
+#pragma unroll
+        for (int wi = 0; wi < RPU; ++wi) {
+            const int64_t row = src.a0 + q * RPU + wi;
+            if (row < s0 || row >= c1) continue;
+            src.read(src.lead, MF_LEAD_SLOTS, row, x, y, y_raw, s);
+            st.add(x, y, 1.0);
+            if (row < rs) continue;  // still accumulating the window that enters the chunk
+            if (row - W >= g0) {
+                src.read(src.lag, MF_LAG_SLOTS, row - W, xo, yo, yr2, s2);
+                st.add(xo, yo, -1.0);
+            }
+            solve_normal<K>(st, beta);
+            fast_emit<T, K>(p, row, beta, x, y_raw, s);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---- recursive least squares -------------------------------------------------------------------------------
+// pass 1: information-form summary of every chunk (A_c = sum lam^(..) x x^T, b_c, D = lam^rows), as rls_summary_kernel
+template <typename T, int K>
+__global__ void __launch_bounds__(MF_THREADS) rls_fast_summary_kernel(const MovingParams p) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
+    constexpr int RPU = FastSrc<T, K>::RPU;
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    const int64_t c0 = p.chunk_r0[c], c1 = p.chunk_r1[c];
+    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    src.a0 = c0 & ~static_cast<int64_t>(RPU - 1);
+    NormalState<K> ab;
+    ab.clear();
+    double D = 1.0, x[K], y;
+    T y_raw, s;
+#pragma unroll
+    for (int b = -MF_DEPTH; b < 0; ++b) {
+        src.issue(src.lead, MF_LEAD_SLOTS, b + MF_DEPTH);
+        cp_async_commit();
+    }
+    const int64_t q_end = (c1 - src.a0 + RPU - 1) / RPU;
+    for (int64_t q = 0; q < q_end; ++q) {
+        src.issue(src.lead, MF_LEAD_SLOTS, q + MF_DEPTH);
+        cp_async_commit();
+        cp_async_wait<MF_DEPTH>();
+#pragma unroll
+        for (int wi = 0; wi < RPU; ++wi) {
+            const int64_t row = src.a0 + q * RPU + wi;
+            if (row < c0 || row >= c1) continue;
+            src.read(src.lead, MF_LEAD_SLOTS, row, x, y, y_raw, s);
+            ab.decay(p.lambda);
+            ab.add(x, y, 1.0);
+            D *= p.lambda;
+        }
+    }
+    cp_async_wait<0>();
+    double *rec = p.summaries + c * moving_rec(K);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) rec[i * K + j] = (j <= i) ? ab.S[i][j] : 0.0;
+        rec[K * K + i] = ab.v[i];
+    }
+    rec[K * K + K] = D;
+}
+
+// pass 3 (after the scan): the covariance-form recurrence of every chunk, restarted from the information state
+// entering it (rls_chunk of moving_core.cuh, rows through the staging ring)
+template <typename T, int K>
+__global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_RLS) rls_fast_main_kernel(const MovingParams p) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
+    constexpr int RPU = FastSrc<T, K>::RPU;
+    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    const int64_t g = p.chunk_group[c];
+    const int64_t c0 = p.chunk_r0[c], c1 = p.chunk_r1[c];
+    const bool first = (c0 == p.group_off[g]) && !p.init_info;
+    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    src.a0 = c0 & ~static_cast<int64_t>(RPU - 1);
+#pragma unroll
+    for (int b = -MF_DEPTH; b < 0; ++b) {
+        src.issue(src.lead, MF_LEAD_SLOTS, b + MF_DEPTH);
+        cp_async_commit();
+    }
+    double P[K][K], theta[K];
+    if (first) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            theta[i] = p.has_mean ? p.mean[i] : 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) P[i][j] = (i == j) ? p.p0 : 0.0;
+        }
+    } else {
+        NormalState<K> t;
+        const double *rec = p.summaries + c * moving_rec(K);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) t.S[i][j] = rec[i * K + j];
+            t.v[i] = rec[K * K + i];
+        }
+        rls_restart<K>(t, P, theta);
+    }
+    const double inv_lam = 1.0 / p.lambda;
+    double x[K], y;
+    T y_raw, s;
+    const int64_t exact_end = first ? c0 + RLS_EXACT_ROWS : c0;  // prior-dominated head of a series: literal arithmetic
+    const int64_t q_end = (c1 - src.a0 + RPU - 1) / RPU;
+    for (int64_t q = 0; q < q_end; ++q) {
+        src.issue(src.lead, MF_LEAD_SLOTS, q + MF_DEPTH);
+        cp_async_commit();
+        cp_async_wait<MF_DEPTH>();
+#pragma unroll
+        for (int wi = 0; wi < RPU; ++wi) {
+            const int64_t row = src.a0 + q * RPU + wi;
+            if (row < c0 || row >= c1) continue;
+            src.read(src.lead, MF_LEAD_SLOTS, row, x, y, y_raw, s);
+            if (row < exact_end) rls_update_exact<K>(P, theta, x, y, p.lambda);
+            else rls_update<K>(P, theta, x, y, p.lambda, inv_lam);
+            fast_emit<T, K>(p, row, theta, x, y_raw, s);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace b200

@@ -75,10 +75,10 @@ def test_notebook_rolling_rls_expanding():                                     #
     assert np.allclose(c[-5:], g["rolling_ridge_coef_tail5"], atol=TOL, rtol=0)
     c = F.select(col("y").least_squares.rls("x1", "x2", "x3", half_life=21.0, initial_state_mean=[-1.0, -1.0, -1.0],
                                             initial_state_covariance=10.0, mode="coefficients").over("group"))["coefficients"].to_numpy()
-    assert np.allclose(c[:5], g["rls_coef_head5"], atol=2.0e-5, rtol=0)          # first rows of each group: prior-dominated
+    assert np.allclose(c[:5], g["rls_coef_head5"], atol=TOL, rtol=0)
     assert np.allclose(c[-5:], g["rls_coef_tail5"], atol=TOL, rtol=0)
     p = F.select(col("y").least_squares.expanding_ols("x1", "x2", "x3", mode="predictions"))["y"].to_numpy()
-    assert np.allclose(p[:5], g["expanding_ols_pred_head5"], atol=2.0e-5, rtol=0)
+    assert np.allclose(p[:5], g["expanding_ols_pred_head5"], atol=TOL, rtol=0)
     assert np.allclose(p[-5:], g["expanding_ols_pred_tail5"], atol=TOL, rtol=0)
 
 
