@@ -47,6 +47,13 @@ def make_data(seed: int):
     return x, y, offsets
 
 
+def make_config(world: int, notes: str = ""):
+    """the SAME dict (keys and values) for both arms, so that the driver's config comparison holds"""
+    return {"workload": WORKLOAD, "l2": "inputs 720 MB per step > 126 MB L2 (no flush needed)",
+            "parallelism": f"groups sharded over {world} GPU(s), weak scaling (every rank a full 10k-group batch)",
+            "inputs": "resident in HBM (value) / pinned host memory (e2e)"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -169,8 +176,10 @@ def main():
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(times),
             "warmup": a.warmup, "ms_per_step": 1e3 * t / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU restatement (port) of the reference's per-group path; the Rust "
-                       "crate cannot be built here (no cargo)"},
+            "config": make_config(a.gpus),
+            "notes": "CPU restatement (port) of the reference's per-group path (oracle/ols_oracle.c, OpenMP over groups); the "
+                     "Rust crate cannot be built here (no cargo).  One 10k-group batch per step whatever --gpus is: the "
+                     "metric is a rate (regressions/s), the GPU arm at N > 1 runs N such batches per step.",
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{len(times)} x full batch of {G} groups ({G * N_PER} rows), OpenMP over groups"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -228,6 +237,8 @@ def main():
         b = i & 1
         if world == 1 or peer is not None:
             steps_fn[b]()
+            if peer is not None:
+                peer.step_complete()    # per-step cross-rank completion (release / acquire flags over NVLink)
             return
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ev_gath[b])          # WAR: the gather issued two steps ago has consumed this buffer
@@ -268,6 +279,7 @@ def main():
     launches = eng.launch_count - launches0 + (a.steps if (world > 1 and peer is None) else 0)
     if peer is not None:
         # every rank's shard must have landed in this rank's buffer (all ranks synchronised at the barrier above)
+        assert not eng.peer_timed_out(), "a peer never signalled step completion"
         full = peer.read()
         assert np.isfinite(full).all() and (np.abs(full).sum(axis=1) > 0).all(), "peer gather incomplete"
         coef = torch.as_tensor(full[rank * G:(rank + 1) * G], device=dev)
@@ -377,10 +389,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "inputs 720 MB per step > 126 MB L2 (no flush needed)",
-                       "parallelism": f"groups sharded over {world} GPU(s), weak scaling"
-                                      + ((", coefficient chunks gathered by P2P stores from the solver warps into every rank's buffer (NVLink peer memory, fused into the kernel)" if a.gather == "peer" else ", NCCL all-gather of coefficient chunks per step (side stream, overlapped with the next step's kernel)") if world > 1 else ""),
-                       "inputs": "resident in HBM (value) / pinned host memory (e2e)"},
+            "config": make_config(world),
+            "notes": ("" if world == 1 else
+                      ("coefficient chunks gathered by P2P stores from the solver warps into every rank's buffer (NVLink peer memory, "
+                       "fused into the kernel); every step ends with a release/acquire flag exchange between all ranks INSIDE the timed "
+                       "loop (b200ols_peer_step_complete): a step is complete only when every rank's rows have landed everywhere"
+                       if a.gather == "peer" else
+                       "NCCL all-gather of coefficient chunks per step (side stream, overlapped with the next step's kernel)")),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + hy.nbytes + offsets.nbytes),
                     "d2h_bytes_per_step": int(hcoef.nbytes), "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps},

@@ -275,12 +275,22 @@ B200OLS_API int b200ols_rolling_least_squares_coefficients(b200ols_ctx *ctx, con
  * (e.g. stream sync + barrier), exactly as after a collective. */
 B200OLS_API void *b200ols_device_alloc(b200ols_ctx *ctx, size_t bytes);
 B200OLS_API void b200ols_device_free(b200ols_ctx *ctx, void *p);
+B200OLS_API int b200ols_device_memset(b200ols_ctx *ctx, void *dev_ptr, int value, size_t bytes); /* synchronous */
 B200OLS_API int b200ols_ipc_export(b200ols_ctx *ctx, const void *dev_ptr, uint8_t handle[64]);
 B200OLS_API int b200ols_ipc_open(b200ols_ctx *ctx, const uint8_t handle[64], void **dev_ptr);
 B200OLS_API int b200ols_ipc_close(b200ols_ctx *ctx, void *dev_ptr);
 B200OLS_API int b200ols_copy_to_host(b200ols_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 B200OLS_API int b200ols_set_peer_gather(b200ols_ctx *ctx, int n_peers, void *const *peer_coef, int64_t group_base,
                                         int64_t total_groups);
+/* Per-step completion of the fused gather, without a collective: peer_flags[r] = rank r's array of 8 uint64 (zeroed,
+ * in IPC-exported device memory, own rank included).  b200ols_peer_step_complete(step) enqueues one tiny kernel behind
+ * the step's kernels that release-stores `step` into slot [rank] of every peer's array and acquire-spins until all
+ * slots of its own array reached `step`: once it has retired, every rank's rows of this step are in this rank's
+ * buffer.  `step` must increase by one per call, on every rank.  b200ols_peer_timed_out: 1 when a spin gave up
+ * (a peer never signalled; ~2 s), else 0; synchronises the stream. */
+B200OLS_API int b200ols_set_peer_flags(b200ols_ctx *ctx, int n_peers, void *const *peer_flags, int rank);
+B200OLS_API int b200ols_peer_step_complete(b200ols_ctx *ctx, uint64_t step);
+B200OLS_API int b200ols_peer_timed_out(b200ols_ctx *ctx);
 
 /* "next" row: replaces _polars_plugin_predict (src/expressions.rs:706-741).
  * coefficients: n_coef Float64 child arrays of the coefficient struct Series (one value per ROW, e.g. the

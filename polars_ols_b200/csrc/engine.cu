@@ -111,6 +111,7 @@ extern "C" void b200ols_destroy(b200ols_ctx *c) {
     if (c->plan_dev) cudaFree(c->plan_dev);
     if (c->tile_dev) cudaFree(c->tile_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->flag_timeout) cudaFree(c->flag_timeout);
     stager_destroy(c->stager);
     group_plan_destroy(c->gplan);
     for (int h = 0; h < 2; ++h)
@@ -153,6 +154,13 @@ extern "C" void b200ols_device_free(b200ols_ctx *c, void *p) {
         cudaSetDevice(c->device);
         cudaFree(p);
     }
+}
+extern "C" int b200ols_device_memset(b200ols_ctx *c, void *dev_ptr, int value, size_t bytes) {
+    if (!c || !dev_ptr) return fail(B200OLS_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(dev_ptr, value, bytes, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 extern "C" int b200ols_ipc_export(b200ols_ctx *c, const void *dev_ptr, uint8_t handle[64]) {
     if (!c || !dev_ptr || !handle) return fail(B200OLS_ERR_INVALID, "NULL argument");
@@ -197,6 +205,74 @@ extern "C" int b200ols_set_peer_gather(b200ols_ctx *c, int n_peers, void *const 
     c->peer_group_base = group_base;
     c->peer_total_groups = total_groups;
     return 0;
+}
+
+// ---- per-step completion of the fused gather -------------------------------------------------------------------------
+// Every rank owns a flag array flags[8] (in its IPC-exported buffer).  After a step's kernels, one tiny kernel on the same
+// stream (so the step's peer stores are ordered before it) RELEASES `step` into slot [my rank] of every peer's array and
+// then ACQUIRE-spins until every slot of its own array has reached `step`: when it retires, all ranks' coefficient rows of
+// this step have landed in this rank's buffer — the guarantee an all-gather gives, without a collective launch.
+struct PeerFlagParams {
+    unsigned long long *peer[8];
+    int n_peers, rank;
+    unsigned long long step;
+    int *timeout_flag;
+};
+static __global__ void peer_step_complete_kernel(const PeerFlagParams p) {
+    const int r = threadIdx.x;
+    if (r >= p.n_peers) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer[r] + p.rank), "l"(p.step) : "memory");
+    const unsigned long long *mine = p.peer[p.rank] + r;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= p.step) break;
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died; do not hang the device
+            *p.timeout_flag = 1;
+            break;
+        }
+    }
+}
+
+extern "C" int b200ols_set_peer_flags(b200ols_ctx *c, int n_peers, void *const *peer_flags, int rank) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && (!peer_flags || rank < 0 || rank >= n_peers)))
+        return fail(B200OLS_ERR_INVALID, "bad peer flag table");
+    CU(cudaSetDevice(c->device));
+    c->n_flag_peers = n_peers;
+    c->flag_rank = rank;
+    for (int r = 0; r < n_peers; ++r) c->peer_flags[r] = static_cast<unsigned long long *>(peer_flags[r]);
+    if (n_peers > 0 && !c->flag_timeout) {
+        CU(cudaMalloc(reinterpret_cast<void **>(&c->flag_timeout), sizeof(int)));
+        CU(cudaMemsetAsync(c->flag_timeout, 0, sizeof(int), c->stream));
+    }
+    return 0;
+}
+
+extern "C" int b200ols_peer_step_complete(b200ols_ctx *c, uint64_t step) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (c->n_flag_peers <= 0) return fail(B200OLS_ERR_INVALID, "b200ols_set_peer_flags was not called");
+    PeerFlagParams p;
+    std::memset(&p, 0, sizeof(p));
+    for (int r = 0; r < c->n_flag_peers; ++r) p.peer[r] = c->peer_flags[r];
+    p.n_peers = c->n_flag_peers;
+    p.rank = c->flag_rank;
+    p.step = step;
+    p.timeout_flag = c->flag_timeout;
+    peer_step_complete_kernel<<<1, 32, 0, c->stream>>>(p);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200ols_peer_timed_out(b200ols_ctx *c) {
+    if (!c || !c->flag_timeout) return 0;
+    int v = 0;
+    if (cudaMemcpyAsync(&v, c->flag_timeout, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    return v;
 }
 
 // generic fallback of the fused gather: after kernels that rewrite beta (QR / SVD / CD / split groups)
@@ -1896,11 +1972,21 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     // three execution paths (moving.cuh): k <= 8 null-free frames stream through per-thread staging rings
     // (moving_fast.cuh); k <= 8 with a row mask / min_periods > window keep the chunk-interleaved copies; 9 <= k <= 64 run
     // one block per chunk (moving_wide.cuh)
-    static const bool fast_enabled = [] { const char *v = std::getenv("B200OLS_MOVING_FAST"); return !v || std::atoi(v) != 0; }();
+    // test hooks, read per call: B200OLS_MOVING_FAST=0 / B200OLS_MOVING_NBR=0 switch the staged / window-chunk kernels off,
+    // B200OLS_MOVING_NBR_MIN_CHUNKS lowers the frame size from which the window-chunk kernel is used
+    auto env_int = [](const char *name, long long dflt) { const char *v = std::getenv(name); return v ? std::atoll(v) : dflt; };
+    const bool fast_enabled = env_int("B200OLS_MOVING_FAST", 1) != 0;
     const bool wide = p.F > 8;
     p.fast = (!wide && fast_enabled && !p.mask && (p.kind == MOVING_RLS || p.min_periods <= p.window)) ? 1 : 0;
     int64_t L;
-    if (p.fast) {
+    p.nbr = 0;
+    const bool nbr_enabled = env_int("B200OLS_MOVING_NBR", 1) != 0;
+    const int64_t nbr_min_chunks = env_int("B200OLS_MOVING_NBR_MIN_CHUNKS", static_cast<long long>(sm_count) * 128);
+    if (p.fast && p.kind == MOVING_ROLLING && nbr_enabled && p.window >= 64 && p.n_rows / p.window >= nbr_min_chunks) {
+        // window-length chunks: the row leaving a window is the neighbouring thread's current row (rolling_nbr_kernel)
+        p.nbr = 1;
+        L = p.window;
+    } else if (p.fast) {
         // one chunk per resident thread (a single wave: every thread carries the same work), never below 64 rows
         const int nb = std::max(1, moving_fast_blocks_per_sm(f64, p.F, p.kind, p.kd + 1 + (p.w ? 1 : 0)));
         const int64_t resident = static_cast<int64_t>(sm_count) * nb * 128;
@@ -1954,7 +2040,7 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     int32_t *d_cg = reinterpret_cast<int32_t *>(take(nc * 4 + 8));
     int64_t *d_gco = reinterpret_cast<int64_t *>(take((G + 1) * 8));
     p.series_info = reinterpret_cast<int64_t *>(take(static_cast<size_t>(G) * 32 + 8));
-    p.summaries = reinterpret_cast<double *>(take(p.kind == MOVING_RLS ? nc * moving_rec(p.F) * 8 + 8 : 8));
+    p.summaries = reinterpret_cast<double *>(take((p.kind == MOVING_RLS || p.nbr) ? nc * moving_rec(p.F) * 8 + 8 : 8));
     int64_t *d_s0 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
     int64_t *d_s1 = reinterpret_cast<int64_t *>(take(ns * 8 + 8));
     int64_t *d_gso = reinterpret_cast<int64_t *>(take((G + 1) * 8));

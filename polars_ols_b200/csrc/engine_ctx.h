@@ -87,6 +87,10 @@ struct b200ols_ctx {
     int n_peers = 0;
     double *peer_coef[8] = {};
     int64_t peer_group_base = 0, peer_total_groups = 0;
+    // per-step completion of the fused gather (b200ols_set_peer_flags / b200ols_peer_step_complete)
+    int n_flag_peers = 0, flag_rank = 0;
+    unsigned long long *peer_flags[8] = {};
+    int *flag_timeout = nullptr;  // device: set when a spin gave up
     // optional device-side timing of the dominant kernel
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;

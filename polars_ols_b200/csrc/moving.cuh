@@ -75,6 +75,7 @@ struct MovingParams {
     double *state_out;                // [G][F*F+F+1] state LEAVING each series (lower triangle of A, b) and the decay D, or nullptr
     int state_only;                   // stop after the scan (b200ols_recursive_least_squares_state)
     int fast;                         // staged thread-private rings (moving_fast.cuh): no mask, k <= 8, no transposed copies
+    int nbr;                          // rolling, fast: chunks of exactly `window` rows, lag rows from the neighbour's slot
 };
 
 __host__ __device__ constexpr int moving_rec(int K) { return K * K + K + 1; }  // doubles per chunk record: A, b, D

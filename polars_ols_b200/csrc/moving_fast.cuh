@@ -71,7 +71,12 @@ struct FastSrc {
     }
     // scaled features (incl. intercept), scaled target, raw target and 1/sqrt(w)-able scale of staged row r
     __device__ __forceinline__ void read(uint32_t ring, int slots, int64_t r, double (&x)[K], double &y, T &y_raw, T &s) const {
-        const int64_t off = r - a0;
+        read_from(ring, slots, r, a0, x, y, y_raw, s);
+    }
+    // same, for a ring whose stage 0 starts at row `origin` (a neighbouring thread's ring in rolling_nbr_kernel)
+    __device__ __forceinline__ void read_from(uint32_t ring, int slots, int64_t r, int64_t origin, double (&x)[K], double &y, T &y_raw,
+                                              T &s) const {
+        const int64_t off = r - origin;
         const int64_t q = off / RPU;
         const uint32_t e = static_cast<uint32_t>(off - q * RPU) * static_cast<uint32_t>(sizeof(T));
         const uint32_t src = ring + static_cast<uint32_t>((q % slots) * nc) * (MF_THREADS * 16u) + e;
@@ -223,6 +228,126 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_fas
             }
             solve_normal<K>(st, beta);
             fast_emit<T, K>(p, row, beta, x, y_raw, s);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ---- rolling, window-length chunks with neighbour sharing ("nbr") ------------------------------------------------
+// The private lag stream of rolling_fast_kernel doubles the number of concurrent 16-byte streams; at 12 warps / SM the
+// lines they touch (14 streams x 57k threads x 128 B) no longer fit the L2 and every 16-byte unit costs a 64-byte DRAM
+// fetch (ncu, 10M rows: 557 B/row read for 56 B/row of input).  Here every chunk is exactly W rows long, so the row
+// leaving the window of (chunk c, row i) is (chunk c - 1, row i): the row the NEIGHBOURING thread consumes at the same
+// step, already sitting in ITS staging slot.  One lead stream per thread, the lag row is read from the neighbour's
+// slot; the window sums entering a chunk are the Gram totals of the previous chunk (chunk_totals_kernel, one coalesced
+// pass).  The block advances in lock step, one barrier per stage; thread 0 of a block only stages the chunk before the
+// block's first one.  Rows are consumed one stage behind the newest landed one because a neighbour's unit boundaries
+// may be shifted by up to a unit (W or the series start need not be multiples of the unit).
+constexpr int NB_SLOTS = MF_DEPTH + 4;
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256) chunk_totals_kernel(const MovingParams p, double *__restrict__ totals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (c >= p.n_chunks) return;
+    const int64_t r0 = p.chunk_r0[c], r1 = p.chunk_r1[c];
+    if (r1 == p.group_off[p.chunk_group[c] + 1]) return;  // last chunk of its series: nobody continues from it
+    const DevSrc<T, K> src = make_src<T, K>(p);
+    NormalState<K> st;
+    st.clear();
+    double x[K], y;
+    for (int64_t r = r0 + lane; r < r1; r += 32) {
+        src.load(r, x, y);
+        st.add(x, y, 1.0);
+    }
+    double *rec = totals + c * moving_rec(K);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double v = st.S[i][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) rec[i * K + j] = v;
+        }
+        double v = st.v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) rec[K * K + i] = v;
+    }
+}
+
+__host__ __device__ inline size_t moving_nbr_smem(int nc) { return static_cast<size_t>(NB_SLOTS) * nc * MF_THREADS * 16; }
+
+template <typename T, int K>
+__global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_nbr_kernel(const MovingParams p, const double *__restrict__ totals) {
+    extern __shared__ __align__(16) unsigned char mf_smem[];
+    constexpr int RPU = FastSrc<T, K>::RPU;
+    const int tid = threadIdx.x;
+    const int64_t ci = static_cast<int64_t>(blockIdx.x) * (MF_THREADS - 1) + tid - 1;
+    const bool has = ci >= 0 && ci < p.n_chunks;
+    const bool compute = has && tid > 0;
+    const int64_t W = p.window;
+    int64_t r0 = 0, r1 = 0, g0 = 0, g1 = 0;
+    if (has) {
+        r0 = p.chunk_r0[ci];
+        r1 = p.chunk_r1[ci];
+        const int64_t g = p.chunk_group[ci];
+        g0 = p.group_off[g];
+        g1 = p.group_off[g + 1];
+    }
+    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    src.a0 = r0 & ~static_cast<int64_t>(RPU - 1);
+    src.n_lim = r1;                                     // nobody needs rows of another chunk from this thread
+    const bool is_first = r0 == g0;                     // first chunk of its series: the window only grows
+    const int64_t origin_prev = (r0 - W) & ~static_cast<int64_t>(RPU - 1);
+    const uint32_t nbr = src.lead - 16u;                // thread tid - 1 staged chunk ci - 1
+    const bool all_nan = (g1 - g0) < p.min_periods;     // src/least_squares.rs:893-900
+    const int64_t first = g0 + p.min_periods - 1;
+
+    NormalState<K> st;
+    st.clear();
+    if (compute && !is_first) {
+        const double *rec = totals + (ci - 1) * moving_rec(K);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) st.S[i][j] = rec[i * K + j];
+            st.v[i] = rec[K * K + i];
+        }
+    }
+    if (p.alpha > 0.0) st.add_diag(p.alpha);
+    double beta[K], x[K], xo[K], y, yo;
+    T y_raw, s, yr2, s2;
+
+#pragma unroll
+    for (int b = -MF_DEPTH; b < 0; ++b) {
+        if (has) src.issue(src.lead, NB_SLOTS, b + MF_DEPTH);
+        cp_async_commit();
+    }
+    const int64_t q_end = W / RPU + 3;  // block-uniform: covers a chunk starting anywhere inside a unit + the one-behind drain
+    for (int64_t q = 0; q < q_end; ++q) {
+        if (has) src.issue(src.lead, NB_SLOTS, q + MF_DEPTH);
+        cp_async_commit();
+        cp_async_wait<MF_DEPTH>();
+        __syncthreads();  // every thread's stage q has landed; stage q - 3 may be overwritten from now on
+        if (!compute || q == 0) continue;
+#pragma unroll
+        for (int wi = 0; wi < RPU; ++wi) {
+            const int64_t row = src.a0 + (q - 1) * RPU + wi;
+            if (row < r0 || row >= r1) continue;
+            src.read(src.lead, NB_SLOTS, row, x, y, y_raw, s);
+            st.add(x, y, 1.0);
+            if (!is_first) {
+                src.read_from(nbr, NB_SLOTS, row - W, origin_prev, xo, yo, yr2, s2);
+                st.add(xo, yo, -1.0);
+            }
+            if (all_nan || row < first) {
+                fast_emit_nan<T, K>(p, row);
+            } else {
+                solve_normal<K>(st, beta);
+                fast_emit<T, K>(p, row, beta, x, y_raw, s);
+            }
         }
     }
     cp_async_wait<0>();

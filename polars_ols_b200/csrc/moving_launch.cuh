@@ -13,6 +13,15 @@ static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const i
     if (p.fast) {  // null-free frame: rows reach the threads through private cp.async staging rings (moving_fast.cuh)
         const int nc = p.kd + 1 + (p.w ? 1 : 0);
         const unsigned fb = static_cast<unsigned>((p.n_chunks + MF_THREADS - 1) / MF_THREADS);
+        if (p.kind == MOVING_ROLLING && p.nbr) {
+            const size_t smem = moving_nbr_smem(nc);
+            cudaFuncSetAttribute(rolling_nbr_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            chunk_totals_kernel<T, K><<<static_cast<unsigned>((p.n_chunks * 32 + 255) / 256), 256, 0, stream>>>(p, p.summaries);
+            const unsigned nb = static_cast<unsigned>((p.n_chunks + MF_THREADS - 2) / (MF_THREADS - 1));
+            rolling_nbr_kernel<T, K><<<nb, MF_THREADS, smem, stream>>>(p, p.summaries);
+            *launches += 2;
+            return cudaGetLastError();
+        }
         if (p.kind == MOVING_ROLLING) {
             const size_t smem = moving_fast_smem(nc, true);
             cudaFuncSetAttribute(rolling_fast_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

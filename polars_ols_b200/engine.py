@@ -445,6 +445,9 @@ class Engine:
             raise L.B200OLSError(L.ERR_CUDA, self._lib.b200ols_last_error().decode())
         return p
 
+    def zero_device(self, ptr: int, nbytes: int):
+        L.check(self._lib.b200ols_device_memset(self._ctx, C.c_void_p(ptr), 0, nbytes))
+
     def device_free(self, ptr: int):
         self._lib.b200ols_device_free(self._ctx, C.c_void_p(ptr))
 
@@ -468,6 +471,18 @@ class Engine:
     def set_peer_gather(self, peer_ptrs: Sequence[int], group_base: int, total_groups: int):
         arr = (C.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
         L.check(self._lib.b200ols_set_peer_gather(self._ctx, len(peer_ptrs), arr, group_base, total_groups))
+
+    def set_peer_flags(self, flag_ptrs: Sequence[int], rank: int):
+        arr = (C.c_void_p * max(len(flag_ptrs), 1))(*flag_ptrs)
+        L.check(self._lib.b200ols_set_peer_flags(self._ctx, len(flag_ptrs), arr, rank))
+
+    def peer_step_complete(self, step: int):
+        rc = self._lib.b200ols_peer_step_complete(self._ctx, step)
+        if rc != 0:
+            L.check(rc)
+
+    def peer_timed_out(self) -> bool:
+        return self._lib.b200ols_peer_timed_out(self._ctx) != 0
 
     def predict(self, coefficients: List[Col], features: List[Col], add_intercept: bool, null_policy: int):
         """b200ols_predict: row-wise dot of features with per-row coefficient columns."""

@@ -67,7 +67,10 @@ class PeerGather:
         if self.world > 8:
             raise ValueError("peer gather supports up to 8 ranks (one NVSwitch domain)")
         self.nbytes = total_groups * n_coef * 8
-        self.local = engine.device_alloc(self.nbytes)
+        self.flag_off = (self.nbytes + 255) // 256 * 256          # 8 uint64 completion flags behind the coefficient rows
+        self.local = engine.device_alloc(self.flag_off + 64)
+        engine.zero_device(self.local + self.flag_off, 64)
+        self.step = 0
         handles = [None] * self.world
         dist.all_gather_object(handles, engine.ipc_export(self.local), group=group)
         self.peers = [self.local if r == self.rank else engine.ipc_open(handles[r]) for r in range(self.world)]
@@ -76,9 +79,17 @@ class PeerGather:
 
     def attach(self):
         self.engine.set_peer_gather(self.peers, self.group_base, self.total_groups)
+        self.engine.set_peer_flags([p + self.flag_off for p in self.peers], self.rank)
+
+    def step_complete(self):
+        """enqueue the per-step completion behind the step's kernels: when it retires, EVERY rank's rows of this step are
+        in this rank's buffer (release / acquire flags over NVLink, no collective)"""
+        self.step += 1
+        self.engine.peer_step_complete(self.step)
 
     def detach(self):
         self.engine.set_peer_gather([], 0, 0)
+        self.engine.set_peer_flags([], 0)
 
     def read(self) -> np.ndarray:
         out = np.empty((self.total_groups, self.n_coef))
