@@ -47,6 +47,28 @@ def make_data(seed: int):
     return x, y, offsets
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """N > 1: run this rank's host threads (staging memcpys, pinned allocations by first touch) on the NUMA node its GPU
+    hangs off.  Best effort; returns a short description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return f"gpu {bdf}: no NUMA affinity reported"
+        cpus = []
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return f"gpu {bdf} -> NUMA node {node}, {len(allowed)} cpus"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+
+
 def make_config(world: int, notes: str = ""):
     """the SAME dict (keys and values) for both arms, so that the driver's config comparison holds"""
     return {"workload": WORKLOAD, "l2": "inputs 720 MB per step > 126 MB L2 (no flush needed)",
@@ -196,8 +218,12 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dist = None
+    numa = None
     if world > 1:
         import torch.distributed as dist
+        numa = bind_to_gpu_numa_node(local_rank)
+        # the staging ring's copy threads share the host with the other ranks
+        os.environ.setdefault("B200OLS_STAGE_THREADS", str(max(2, min(8, (os.cpu_count() or 16) // (2 * world)))))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -357,6 +383,70 @@ def main():
                             "plan_device_ms": heng.group_plan([key[perm]]).device_ms}
         del frs, perm
 
+    # ---- strong scaling (N > 1): ONE 10k-group frame sharded by group over the N GPUs (N PCIe links for the e2e leg) --
+    strong = None
+    if world > 1:
+        from polars_ols_b200.parallel import shard_groups
+        xs, ys, offs = (x, y, offsets) if rank == 0 else make_data(0)      # the same frame on every rank
+        g0, g1 = shard_groups(offs, world)[rank]
+        r0, r1 = int(offs[g0]), int(offs[g1])
+        loffs = np.ascontiguousarray(offs[g0:g1 + 1] - r0)
+        seng = pls.Engine(local_rank, stream)
+        sxd = torch.as_tensor(np.ascontiguousarray(xs[:, r0:r1]), device=dev)
+        syd = torch.as_tensor(np.ascontiguousarray(ys[r0:r1]), device=dev)
+        sbatch = pls.Batch(pls.Col(syd), [pls.Col(sxd[i]) for i in range(K)], offsets=loffs)
+        speer = PeerGather(seng, G, K, g0) if peer is not None else None
+        scoef = torch.empty((g1 - g0, K), dtype=torch.float64, device=dev)
+        if speer is not None:
+            speer.attach()
+        sstep = seng.prepare_least_squares(sbatch, kw, L.COEFFICIENTS, None if speer is not None else scoef)
+        sgath = torch.empty((G, K), dtype=torch.float64, device=dev)
+        sshards = shard_groups(offs, world)
+
+        def strong_step():
+            sstep()
+            if speer is not None:
+                speer.step_complete()
+            else:
+                gather_group_results(scoef, sshards, out=sgath if all(b_ - a_ == sshards[0][1] - sshards[0][0] for a_, b_ in sshards) else None)
+
+        for _ in range(a.warmup):
+            strong_step()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(a.steps):
+            strong_step()
+        s1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        if speer is not None:
+            assert not seng.peer_timed_out()
+            full = speer.read()
+            speer.close()
+            if rank == 0:   # rank 0 holds the identical frame in full: every shard must have landed, and be right
+                assert np.allclose(full, hcoef, rtol=1e-9, atol=1e-12), "strong-scaling gather differs from the single-GPU result"
+        # e2e: every rank uploads ITS shard from pinned host memory and reads its coefficient rows back
+        shx = seng.pinned_empty((K, r1 - r0)); shy = seng.pinned_empty((r1 - r0,)); shc = seng.pinned_empty((g1 - g0, K))
+        shx[:] = xs[:, r0:r1]; shy[:] = ys[r0:r1]
+        heng2 = pls.Engine(local_rank)
+        hb2 = pls.Batch(pls.Col(shy), [pls.Col(shx[i]) for i in range(K)], offsets=loffs)
+        hs2 = heng2.prepare_least_squares(hb2, kw, L.COEFFICIENTS, shc)
+        for _ in range(3):
+            hs2()
+        dist.barrier()
+        t0_ = time.perf_counter()
+        for _ in range(e2e_steps):
+            hs2()
+        tse = torch.tensor([time.perf_counter() - t0_], dtype=torch.float64, device=dev)
+        dist.all_reduce(tse, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "frame": "ONE 10k-group frame, groups sharded over the ranks by cumulative rows",
+                  "value": G * a.steps / (float(ts.item()) * 1e-3), "ms_per_step": float(ts.item()) / a.steps,
+                  "e2e": {"value": G * e2e_steps / float(tse.item()), "ms_per_step": 1e3 * float(tse.item()) / e2e_steps,
+                          "h2d_bytes_per_step_per_rank": int(shx.nbytes + shy.nbytes)}, "unit": UNIT}
+        del sxd, syd
+
     # ---- roofline of the dominant kernel (row-streaming Gram + fused solve) ---------------------------------
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -410,6 +500,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if strong is not None:
+            line["strong"] = strong
+        if numa is not None:
+            line["numa"] = numa
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

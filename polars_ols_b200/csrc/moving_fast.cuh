@@ -130,10 +130,18 @@ template <typename T, int K>
 __device__ __forceinline__ void fast_emit(const MovingParams &p, int64_t r, const double (&beta)[K], const double (&x)[K], T y_raw, T s) {
     const int64_t orow = p.row_index ? p.row_index[r] : r;
     if (p.mode == 2) {
+        // one thread owns the row: 16-byte stores where the row starts on a 16-byte boundary (every row when K is even);
+        // the validity bytes (NaN <=> null) are written by a coalesced pass after the kernel (launch_moving_t)
+        double *o = p.out + orow * K;
+        if ((K % 2 == 0) || ((orow & 1) == 0)) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            p.out[orow * K + j] = beta[j];
-            if (p.out_valid) p.out_valid[orow * K + j] = (beta[j] == beta[j]) ? 1 : 0;
+            for (int j = 0; j + 1 < K; j += 2) *reinterpret_cast<double2 *>(o + j) = make_double2(beta[j], beta[j + 1]);
+            if (K % 2) o[K - 1] = beta[K - 1];
+        } else {
+            o[0] = beta[0];
+#pragma unroll
+            for (int j = 1; j + 1 < K; j += 2) *reinterpret_cast<double2 *>(o + j) = make_double2(beta[j], beta[j + 1]);
+            if (K % 2 == 0) o[K - 1] = beta[K - 1];
         }
         return;
     }
@@ -150,21 +158,36 @@ __device__ __forceinline__ void fast_emit(const MovingParams &p, int64_t r, cons
     }
     if (p.kind == MOVING_ROLLING) valid = valid && (pred == pred);
     p.out[orow] = pred;
-    if (p.out_valid) p.out_valid[orow] = valid ? 1 : 0;
+    if (p.out_valid && p.mode == 1 && p.target_validity) p.out_valid[orow] = valid ? 1 : 0;  // else: coalesced pass afterwards
+}
+
+// validity bytes of the staged kernels' outputs in one coalesced pass: coefficient / rolling-prediction nulls are exactly
+// the NaNs (fill_nan(None)); rls predictions of a null-free frame are all valid
+static __global__ void __launch_bounds__(256) moving_validity_kernel(const double *__restrict__ v, uint8_t *__restrict__ m, int64_t n, int nan_is_null) {
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+    if (i >= n) return;
+    if (i + 8 <= n) {
+        unsigned long long bits = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double x = v[i + u];
+            bits |= static_cast<unsigned long long>((!nan_is_null || x == x) ? 1u : 0u) << (8 * u);
+        }
+        *reinterpret_cast<unsigned long long *>(m + i) = bits;
+    } else {
+        for (int64_t u = i; u < n; ++u) m[u] = (!nan_is_null || v[u] == v[u]) ? 1 : 0;
+    }
 }
 
 template <typename T, int K>
 __device__ __forceinline__ void fast_emit_nan(const MovingParams &p, int64_t r) {
     const int64_t orow = p.row_index ? p.row_index[r] : r;
     if (p.mode == 2) {
-        for (int j = 0; j < K; ++j) {
-            p.out[orow * K + j] = NAN;
-            if (p.out_valid) p.out_valid[orow * K + j] = 0;
-        }
+        for (int j = 0; j < K; ++j) p.out[orow * K + j] = NAN;
         return;
     }
     p.out[orow] = NAN;
-    if (p.out_valid) p.out_valid[orow] = 0;
+    if (p.out_valid && p.mode == 1 && p.target_validity) p.out_valid[orow] = 0;
 }
 
 // ---- rolling ---------------------------------------------------------------------------------------------

@@ -12,6 +12,19 @@ static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const i
     if (p.n_chunks == 0) return cudaSuccess;
     if (p.fast) {  // null-free frame: rows reach the threads through private cp.async staging rings (moving_fast.cuh)
         const int nc = p.kd + 1 + (p.w ? 1 : 0);
+        // validity bytes: one coalesced pass after the kernels instead of a scattered byte store per row and thread
+        // (residuals against a target with nulls are the exception: the kernels write those bytes themselves)
+        struct ValidityPass {
+            cudaStream_t s; const MovingParams &p; int64_t *launches;
+            ~ValidityPass() {
+                if (!p.out_valid || p.state_only || (p.mode == 1 && p.target_validity)) return;
+                const int64_t n = p.mode == 2 ? p.n_rows * p.F : p.n_rows;
+                if (n == 0) return;
+                const int nan_is_null = (p.mode == 2 || p.kind == MOVING_ROLLING) ? 1 : 0;
+                moving_validity_kernel<<<static_cast<unsigned>((n + 2047) / 2048), 256, 0, s>>>(p.out, p.out_valid, n, nan_is_null);
+                ++*launches;
+            }
+        } validity_pass{stream, p, launches};
         const unsigned fb = static_cast<unsigned>((p.n_chunks + MF_THREADS - 1) / MF_THREADS);
         if (p.kind == MOVING_ROLLING && p.nbr) {
             const size_t smem = moving_nbr_smem(nc);
