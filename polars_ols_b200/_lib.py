@@ -11,7 +11,9 @@ import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-SO_PATH = _HERE / "libb200ols.so"
+import os as _os
+
+SO_PATH = Path(_os.environ["B200OLS_LIBRARY"]).resolve() if _os.environ.get("B200OLS_LIBRARY") else _HERE / "libb200ols.so"
 
 # enums of include/b200ols.h
 F64, F32 = 0, 1

@@ -12,15 +12,18 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-OBJ = HERE / "build"
-SO = HERE / "libb200ols.so"
+# A/B builds (tools only): B200OLS_BUILD_TAG=x B200OLS_BUILD_FLAGS="-DFOO=1" -> build_x/ + libb200ols_x.so, loaded
+# with B200OLS_LIBRARY=polars_ols_b200/libb200ols_x.so (see _lib.py)
+_TAG = os.environ.get("B200OLS_BUILD_TAG", "")
+OBJ = HERE / ("build" + (f"_{_TAG}" if _TAG else ""))
+SO = HERE / ("libb200ols" + (f"_{_TAG}" if _TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     # FP contraction stays on in device code: explicit fma() is used where order matters
-]
+] + os.environ.get("B200OLS_BUILD_FLAGS", "").split()
 LINK = ["--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
 _INC = re.compile(r'^\s*#include\s+"([^"]+)"', re.M)
 

@@ -73,7 +73,7 @@ struct NormalState {   // S = sum x x^T (+ alpha I), v = sum x y   (lower triang
 // ~25 for rsqrt(double), which also handles denormals and infinities; this runs k times per row of a 50M-row series).
 // Accurate to ~2 ulp for normal positive d inside the f32 exponent range; anything else takes the library routine.
 B200_HD double pivot_rsqrt(double d) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(B200_PIVOT_RSQRT_LIB)
     if (d > 1.0e-30 && d < 1.0e30) {
         double y = static_cast<double>(rsqrtf(static_cast<float>(d)));
         const double h = 0.5 * d;
@@ -81,6 +81,8 @@ B200_HD double pivot_rsqrt(double d) {
         y = y * fma(-h * y, y, 1.5);
         return y;
     }
+    return rsqrt(d);
+#elif defined(__CUDA_ARCH__)
     return rsqrt(d);
 #else
     return 1.0 / sqrt(d);

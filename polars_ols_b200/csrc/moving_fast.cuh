@@ -50,7 +50,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // One thread's view of its staging rings.  Stage q of a stream = rows [a0 + q * RPU, a0 + (q + 1) * RPU) of every
 // column (RPU rows per 16-byte unit), kept in slot q % SLOTS.
-template <typename T, int K>
+template <typename T, int K, bool WT>
 struct FastSrc {
     static constexpr int RPU = 16 / static_cast<int>(sizeof(T));
     const T *col[K + 2];   // [0, kd) features, [kd] target, [kd + 1] weights
@@ -62,9 +62,13 @@ struct FastSrc {
 
     __device__ __forceinline__ void issue(uint32_t ring, int slots, int64_t q) const {
         if (q < 0) return;
+        issue_slot(ring, static_cast<int>(q % slots), q);
+    }
+    // stage q into ring slot `slot` (callers that walk the stages in order carry the slot index along)
+    __device__ __forceinline__ void issue_slot(uint32_t ring, int slot, int64_t q) const {
         const int64_t row = a0 + q * RPU;
         if (row >= n_lim) return;
-        const uint32_t dst = ring + static_cast<uint32_t>((q % slots) * nc) * (MF_THREADS * 16u);
+        const uint32_t dst = ring + static_cast<uint32_t>(slot * nc) * (MF_THREADS * 16u);
 #pragma unroll
         for (int c = 0; c < K + 2; ++c)  // compile-time bound: `col` stays in registers
             if (c < nc) cp_async16(dst + static_cast<uint32_t>(c) * (MF_THREADS * 16u), col[c] + row);
@@ -78,8 +82,11 @@ struct FastSrc {
                                               T &s) const {
         const int64_t off = r - origin;
         const int64_t q = off / RPU;
-        const uint32_t e = static_cast<uint32_t>(off - q * RPU) * static_cast<uint32_t>(sizeof(T));
-        const uint32_t src = ring + static_cast<uint32_t>((q % slots) * nc) * (MF_THREADS * 16u) + e;
+        read_slot(ring, static_cast<int>(q % slots), static_cast<int>(off - q * RPU), x, y, y_raw, s);
+    }
+    // row `elem` of the unit in ring slot `slot`
+    __device__ __forceinline__ void read_slot(uint32_t ring, int slot, int elem, double (&x)[K], double &y, T &y_raw, T &s) const {
+        const uint32_t src = ring + static_cast<uint32_t>(slot * nc) * (MF_THREADS * 16u) + static_cast<uint32_t>(elem) * static_cast<uint32_t>(sizeof(T));
         auto lds = [&](int c) -> T {
             T v;
             if constexpr (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(src + static_cast<uint32_t>(c) * (MF_THREADS * 16u)));
@@ -87,20 +94,25 @@ struct FastSrc {
             return v;
         };
         s = T(1);
-        if (has_w) {
+        if constexpr (WT) {
             const T wv = lds(kd + 1);
             s = w_is_sqrt ? wv : static_cast<T>(sqrt(wv));
-        }
 #pragma unroll
-        for (int j = 0; j < K; ++j) x[j] = (j < kd) ? static_cast<double>(static_cast<T>(lds(j) * s)) : static_cast<double>(s);
-        y_raw = lds(kd);
-        y = static_cast<double>(static_cast<T>(y_raw * s));
+            for (int j = 0; j < K; ++j) x[j] = (j < kd) ? static_cast<double>(static_cast<T>(lds(j) * s)) : static_cast<double>(s);
+            y_raw = lds(kd);
+            y = static_cast<double>(static_cast<T>(y_raw * s));
+        } else {  // unweighted instantiation: no multiply by 1 on the FP64 pipe
+#pragma unroll
+            for (int j = 0; j < K; ++j) x[j] = (j < kd) ? static_cast<double>(lds(j)) : 1.0;
+            y_raw = lds(kd);
+            y = static_cast<double>(y_raw);
+        }
     }
 };
 
-template <typename T, int K>
-__device__ __forceinline__ FastSrc<T, K> make_fast_src(const MovingParams &p, unsigned char *smem) {
-    FastSrc<T, K> s;
+template <typename T, int K, bool WT>
+__device__ __forceinline__ FastSrc<T, K, WT> make_fast_src(const MovingParams &p, unsigned char *smem) {
+    FastSrc<T, K, WT> s;
 #pragma unroll
     for (int j = 0; j < K + 2; ++j) s.col[j] = nullptr;
     s.kd = p.kd;
@@ -126,7 +138,7 @@ __host__ __device__ inline size_t moving_fast_smem(int nc, bool rolling) {
 
 // output of one row (same rules as DevEmit in moving.cuh): coefficients, or prediction / residual with the WLS
 // un-scaling, `fill_nan(None)` for rolling
-template <typename T, int K>
+template <typename T, int K, bool WT>
 __device__ __forceinline__ void fast_emit(const MovingParams &p, int64_t r, const double (&beta)[K], const double (&x)[K], T y_raw, T s) {
     const int64_t orow = p.row_index ? p.row_index[r] : r;
     if (p.mode == 2) {
@@ -148,7 +160,7 @@ __device__ __forceinline__ void fast_emit(const MovingParams &p, int64_t r, cons
     double pred = 0.0;
 #pragma unroll
     for (int j = 0; j < K; ++j) pred += x[j] * beta[j];
-    if (p.w) pred *= static_cast<double>(T(1) / s);
+    if constexpr (WT) pred *= static_cast<double>(T(1) / s);
     bool valid = true;
     if (p.mode == 1) {
         double t = static_cast<double>(y_raw);
@@ -194,10 +206,10 @@ __device__ __forceinline__ void fast_emit_nan(const MovingParams &p, int64_t r) 
 // Requires: no row mask, min_periods <= window.  Chunk [c0, c1) of series [g0, g1):
 //   rows before g0 + min_periods - 1 are NaN; the state entering the first coefficient row rs of the chunk is
 //   alpha I + Gram(rows [max(g0, rs - W), rs)); then per row r: + row r, - row r - W (when r - W >= g0), solve.
-template <typename T, int K>
+template <typename T, int K, bool WT>
 __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_fast_kernel(const MovingParams p) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
-    constexpr int RPU = FastSrc<T, K>::RPU;
+    constexpr int RPU = FastSrc<T, K, WT>::RPU;
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
     const int64_t g = p.chunk_group[c];
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_fas
     if (r >= c1) return;
     const int64_t rs = r;                                  // first row of this chunk that carries coefficients
     const int64_t s0 = (rs - W > g0) ? rs - W : g0;         // oldest row of the window entering rs
-    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    FastSrc<T, K, WT> src = make_fast_src<T, K, WT>(p, mf_smem);
     src.a0 = s0 & ~static_cast<int64_t>(RPU - 1);
     // lag stage consumed while the lead works on stage q:  q - lagq (and q - lagq + 1 when W is not a multiple of RPU)
     const int64_t lagq = (W + RPU - 1) / RPU;
@@ -250,7 +262,7 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_fas
                 st.add(xo, yo, -1.0);
             }
             solve_normal<K>(st, beta);
-            fast_emit<T, K>(p, row, beta, x, y_raw, s);
+            fast_emit<T, K, WT>(p, row, beta, x, y_raw, s);
         }
     }
     cp_async_wait<0>();
@@ -302,10 +314,10 @@ __global__ void __launch_bounds__(256) chunk_totals_kernel(const MovingParams p,
 
 __host__ __device__ inline size_t moving_nbr_smem(int nc) { return static_cast<size_t>(NB_SLOTS) * nc * MF_THREADS * 16; }
 
-template <typename T, int K>
+template <typename T, int K, bool WT>
 __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_nbr_kernel(const MovingParams p, const double *__restrict__ totals) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
-    constexpr int RPU = FastSrc<T, K>::RPU;
+    constexpr int RPU = FastSrc<T, K, WT>::RPU;
     const int tid = threadIdx.x;
     const int64_t ci = static_cast<int64_t>(blockIdx.x) * (MF_THREADS - 1) + tid - 1;
     const bool has = ci >= 0 && ci < p.n_chunks;
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_nbr
         g0 = p.group_off[g];
         g1 = p.group_off[g + 1];
     }
-    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    FastSrc<T, K, WT> src = make_fast_src<T, K, WT>(p, mf_smem);
     src.a0 = r0 & ~static_cast<int64_t>(RPU - 1);
     src.n_lim = r1;                                     // nobody needs rows of another chunk from this thread
     const bool is_first = r0 == g0;                     // first chunk of its series: the window only grows
@@ -343,49 +355,70 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_nbr
     double beta[K], x[K], xo[K], y, yo;
     T y_raw, s, yr2, s2;
 
+    // lag row of (stage q - 1, element wi) in the neighbour's numbering: stage q - 1 + dlt[wi], element el[wi]
+    // (the neighbour's units may be shifted by up to one unit: W or the series start need not be unit multiples)
+    int dlt[RPU], el[RPU];
+    {
+        const int c = static_cast<int>(src.a0 - W - origin_prev);  // in (-RPU, RPU)
+#pragma unroll
+        for (int wi = 0; wi < RPU; ++wi) {
+            const int t = wi + c + RPU;  // > 0
+            dlt[wi] = t / RPU - 1;
+            el[wi] = t % RPU;
+        }
+    }
 #pragma unroll
     for (int b = -MF_DEPTH; b < 0; ++b) {
-        if (has) src.issue(src.lead, NB_SLOTS, b + MF_DEPTH);
+        if (has) src.issue_slot(src.lead, b + MF_DEPTH, b + MF_DEPTH);
         cp_async_commit();
     }
     const int64_t q_end = W / RPU + 3;  // block-uniform: covers a chunk starting anywhere inside a unit + the one-behind drain
+    int slot_issue = MF_DEPTH % NB_SLOTS;  // slot of stage q + MF_DEPTH
+    int slot_own = NB_SLOTS - 1;           // slot of stage q - 1
+    int64_t row0 = src.a0 - RPU;           // first row of stage q - 1
     for (int64_t q = 0; q < q_end; ++q) {
-        if (has) src.issue(src.lead, NB_SLOTS, q + MF_DEPTH);
+        if (has) src.issue_slot(src.lead, slot_issue, q + MF_DEPTH);
         cp_async_commit();
         cp_async_wait<MF_DEPTH>();
         __syncthreads();  // every thread's stage q has landed; stage q - 3 may be overwritten from now on
-        if (!compute || q == 0) continue;
+        if (compute && q > 0) {
 #pragma unroll
-        for (int wi = 0; wi < RPU; ++wi) {
-            const int64_t row = src.a0 + (q - 1) * RPU + wi;
-            if (row < r0 || row >= r1) continue;
-            src.read(src.lead, NB_SLOTS, row, x, y, y_raw, s);
-            st.add(x, y, 1.0);
-            if (!is_first) {
-                src.read_from(nbr, NB_SLOTS, row - W, origin_prev, xo, yo, yr2, s2);
-                st.add(xo, yo, -1.0);
-            }
-            if (all_nan || row < first) {
-                fast_emit_nan<T, K>(p, row);
-            } else {
-                solve_normal<K>(st, beta);
-                fast_emit<T, K>(p, row, beta, x, y_raw, s);
+            for (int wi = 0; wi < RPU; ++wi) {
+                const int64_t row = row0 + wi;
+                if (row < r0 || row >= r1) continue;
+                src.read_slot(src.lead, slot_own, wi, x, y, y_raw, s);
+                st.add(x, y, 1.0);
+                if (!is_first) {
+                    int sl = slot_own + dlt[wi];
+                    sl = sl < 0 ? sl + NB_SLOTS : (sl >= NB_SLOTS ? sl - NB_SLOTS : sl);
+                    src.read_slot(nbr, sl, el[wi], xo, yo, yr2, s2);
+                    st.add(xo, yo, -1.0);
+                }
+                if (all_nan || row < first) {
+                    fast_emit_nan<T, K>(p, row);
+                } else {
+                    solve_normal<K>(st, beta);
+                    fast_emit<T, K, WT>(p, row, beta, x, y_raw, s);
+                }
             }
         }
+        slot_issue = slot_issue + 1 == NB_SLOTS ? 0 : slot_issue + 1;
+        slot_own = slot_own + 1 == NB_SLOTS ? 0 : slot_own + 1;
+        row0 += RPU;
     }
     cp_async_wait<0>();
 }
 
 // ---- recursive least squares -------------------------------------------------------------------------------
 // pass 1: information-form summary of every chunk (A_c = sum lam^(..) x x^T, b_c, D = lam^rows), as rls_summary_kernel
-template <typename T, int K>
+template <typename T, int K, bool WT>
 __global__ void __launch_bounds__(MF_THREADS) rls_fast_summary_kernel(const MovingParams p) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
-    constexpr int RPU = FastSrc<T, K>::RPU;
+    constexpr int RPU = FastSrc<T, K, WT>::RPU;
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
     const int64_t c0 = p.chunk_r0[c], c1 = p.chunk_r1[c];
-    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    FastSrc<T, K, WT> src = make_fast_src<T, K, WT>(p, mf_smem);
     src.a0 = c0 & ~static_cast<int64_t>(RPU - 1);
     NormalState<K> ab;
     ab.clear();
@@ -424,16 +457,16 @@ __global__ void __launch_bounds__(MF_THREADS) rls_fast_summary_kernel(const Movi
 
 // pass 3 (after the scan): the covariance-form recurrence of every chunk, restarted from the information state
 // entering it (rls_chunk of moving_core.cuh, rows through the staging ring)
-template <typename T, int K>
+template <typename T, int K, bool WT>
 __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_RLS) rls_fast_main_kernel(const MovingParams p) {
     extern __shared__ __align__(16) unsigned char mf_smem[];
-    constexpr int RPU = FastSrc<T, K>::RPU;
+    constexpr int RPU = FastSrc<T, K, WT>::RPU;
     const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= p.n_chunks) return;
     const int64_t g = p.chunk_group[c];
     const int64_t c0 = p.chunk_r0[c], c1 = p.chunk_r1[c];
     const bool first = (c0 == p.group_off[g]) && !p.init_info;
-    FastSrc<T, K> src = make_fast_src<T, K>(p, mf_smem);
+    FastSrc<T, K, WT> src = make_fast_src<T, K, WT>(p, mf_smem);
     src.a0 = c0 & ~static_cast<int64_t>(RPU - 1);
 #pragma unroll
     for (int b = -MF_DEPTH; b < 0; ++b) {
@@ -475,7 +508,7 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_RLS) rls_fast_main_k
             src.read(src.lead, MF_LEAD_SLOTS, row, x, y, y_raw, s);
             if (row < exact_end) rls_update_exact<K>(P, theta, x, y, p.lambda);
             else rls_update<K>(P, theta, x, y, p.lambda, inv_lam);
-            fast_emit<T, K>(p, row, theta, x, y_raw, s);
+            fast_emit<T, K, WT>(p, row, theta, x, y_raw, s);
         }
     }
     cp_async_wait<0>();

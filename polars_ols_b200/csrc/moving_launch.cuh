@@ -5,12 +5,12 @@
 
 namespace b200 {
 
-template <typename T, int K>
-static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const int64_t *group_chunk_off_dev,
-                                   int64_t *launches) {
+// null-free frame, k <= 8: rows reach the threads through private cp.async staging rings (moving_fast.cuh);
+// WT = sample weights present (the unweighted instantiation carries no scaling arithmetic)
+template <typename T, int K, bool WT>
+static cudaError_t launch_moving_fast_t(cudaStream_t stream, MovingParams &p, int64_t *launches) {
     const unsigned cb = static_cast<unsigned>((p.n_chunks + 127) / 128);
-    if (p.n_chunks == 0) return cudaSuccess;
-    if (p.fast) {  // null-free frame: rows reach the threads through private cp.async staging rings (moving_fast.cuh)
+    (void)cb;
         const int nc = p.kd + 1 + (p.w ? 1 : 0);
         // validity bytes: one coalesced pass after the kernels instead of a scattered byte store per row and thread
         // (residuals against a target with nulls are the exception: the kernels write those bytes themselves)
@@ -28,34 +28,41 @@ static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const i
         const unsigned fb = static_cast<unsigned>((p.n_chunks + MF_THREADS - 1) / MF_THREADS);
         if (p.kind == MOVING_ROLLING && p.nbr) {
             const size_t smem = moving_nbr_smem(nc);
-            cudaFuncSetAttribute(rolling_nbr_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            cudaFuncSetAttribute(rolling_nbr_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             chunk_totals_kernel<T, K><<<static_cast<unsigned>((p.n_chunks * 32 + 255) / 256), 256, 0, stream>>>(p, p.summaries);
             const unsigned nb = static_cast<unsigned>((p.n_chunks + MF_THREADS - 2) / (MF_THREADS - 1));
-            rolling_nbr_kernel<T, K><<<nb, MF_THREADS, smem, stream>>>(p, p.summaries);
+            rolling_nbr_kernel<T, K, WT><<<nb, MF_THREADS, smem, stream>>>(p, p.summaries);
             *launches += 2;
             return cudaGetLastError();
         }
         if (p.kind == MOVING_ROLLING) {
             const size_t smem = moving_fast_smem(nc, true);
-            cudaFuncSetAttribute(rolling_fast_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            rolling_fast_kernel<T, K><<<fb, MF_THREADS, smem, stream>>>(p);
+            cudaFuncSetAttribute(rolling_fast_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            rolling_fast_kernel<T, K, WT><<<fb, MF_THREADS, smem, stream>>>(p);
             ++*launches;
             return cudaGetLastError();
         }
         const size_t smem = moving_fast_smem(nc, false);
-        cudaFuncSetAttribute(rls_fast_summary_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        cudaFuncSetAttribute(rls_fast_main_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        rls_fast_summary_kernel<T, K><<<fb, MF_THREADS, smem, stream>>>(p);
+        cudaFuncSetAttribute(rls_fast_summary_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaFuncSetAttribute(rls_fast_main_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        rls_fast_summary_kernel<T, K, WT><<<fb, MF_THREADS, smem, stream>>>(p);
         const unsigned sb = static_cast<unsigned>((p.n_super * 32 + 127) / 128);
         rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 0, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
         rls_scan_kernel<K><<<static_cast<unsigned>((p.n_groups * 32 + 127) / 128), 128, 0, stream>>>(p, 1, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
         *launches += 3;
         if (p.state_only) return cudaGetLastError();
         rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 2, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
-        rls_fast_main_kernel<T, K><<<fb, MF_THREADS, smem, stream>>>(p);
+        rls_fast_main_kernel<T, K, WT><<<fb, MF_THREADS, smem, stream>>>(p);
         *launches += 2;
         return cudaGetLastError();
-    }
+}
+
+template <typename T, int K>
+static cudaError_t launch_moving_t(cudaStream_t stream, MovingParams &p, const int64_t *group_chunk_off_dev,
+                                   int64_t *launches) {
+    const unsigned cb = static_cast<unsigned>((p.n_chunks + 127) / 128);
+    if (p.n_chunks == 0) return cudaSuccess;
+    if (p.fast) return p.w ? launch_moving_fast_t<T, K, true>(stream, p, launches) : launch_moving_fast_t<T, K, false>(stream, p, launches);
     {   // chunk-interleaved copies of every input column (one coalesced read + write of the data)
         TransposeParams tp;
         int nc = 0;
@@ -111,12 +118,12 @@ static int moving_fast_blocks_t(int kind, int nc) {
     int nb = 0;
     if (kind == MOVING_ROLLING) {
         const size_t smem = moving_fast_smem(nc, true);
-        cudaFuncSetAttribute(rolling_fast_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rolling_fast_kernel<T, K>, MF_THREADS, smem);
+        cudaFuncSetAttribute(rolling_fast_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rolling_fast_kernel<T, K, false>, MF_THREADS, smem);
     } else {
         const size_t smem = moving_fast_smem(nc, false);
-        cudaFuncSetAttribute(rls_fast_main_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rls_fast_main_kernel<T, K>, MF_THREADS, smem);
+        cudaFuncSetAttribute(rls_fast_main_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rls_fast_main_kernel<T, K, false>, MF_THREADS, smem);
     }
     return nb;
 }

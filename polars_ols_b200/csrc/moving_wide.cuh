@@ -13,7 +13,7 @@
 
 namespace b200 {
 
-constexpr int WIDE_THREADS = 128;
+constexpr int MWIDE_THREADS = 128;
 
 struct WideSmem {
     double *S;     // [K*K] window sums (lower triangle authoritative) | rls: P (full)
@@ -67,17 +67,17 @@ __device__ __forceinline__ void wide_load_row(const MovingParams &p, const WideS
 // Lw <- Cholesky factor of S (strict lower part + inv[j] = 1 / L[j][j]); false on a non-positive pivot (uniform)
 __device__ inline bool wide_factor(const WideSmem &sm, int K) {
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    for (int i = ty; i < K; i += WIDE_THREADS / 16)
+    for (int i = ty; i < K; i += MWIDE_THREADS / 16)
         for (int j = tx; j < K; j += 16) sm.Lw[i * K + j] = (j <= i) ? sm.S[i * K + j] : sm.S[j * K + i];
     __syncthreads();
     for (int j = 0; j < K; ++j) {
         const double d = sm.Lw[j * K + j];
         if (!(d > 0.0)) return false;  // every thread reads the same pivot
         const double rinv = rsqrt(d);
-        for (int i = j + 1 + tid; i < K; i += WIDE_THREADS) sm.Lw[i * K + j] *= rinv;
+        for (int i = j + 1 + tid; i < K; i += MWIDE_THREADS) sm.Lw[i * K + j] *= rinv;
         if (tid == 0) sm.inv[j] = rinv;
         __syncthreads();
-        for (int ii = j + 1 + ty; ii < K; ii += WIDE_THREADS / 16) {
+        for (int ii = j + 1 + ty; ii < K; ii += MWIDE_THREADS / 16) {
             const double lij = sm.Lw[ii * K + j];
             for (int kk = j + 1 + tx; kk <= ii; kk += 16) sm.Lw[ii * K + kk] = fma(-lij, sm.Lw[kk * K + j], sm.Lw[ii * K + kk]);
         }
@@ -119,7 +119,7 @@ __device__ inline void wide_solve(const WideSmem &sm, int K) {
         return;
     }
     __syncthreads();
-    for (int e = tid; e < K * K; e += WIDE_THREADS) {
+    for (int e = tid; e < K * K; e += MWIDE_THREADS) {
         const int i = e / K, j = e - i * K;
         sm.Lw[e] = (j <= i) ? sm.S[e] : sm.S[j * K + i];
     }
@@ -177,13 +177,13 @@ struct RollingWide {
     __device__ bool valid(int64_t r) const { return p.mask ? (static_cast<const T *>(p.mask)[r] != T(0)) : true; }
     __device__ void prefetch(int64_t) const {}
     __device__ void clear() {
-        for (int e = threadIdx.x; e < K * K; e += WIDE_THREADS) sm.S[e] = 0.0;
+        for (int e = threadIdx.x; e < K * K; e += MWIDE_THREADS) sm.S[e] = 0.0;
         if (threadIdx.x < K) sm.v[threadIdx.x] = 0.0;
         __syncthreads();
     }
     __device__ void add_row(int64_t r, double sign) {
         wide_load_row<T>(p, sm, K, r);
-        for (int i = threadIdx.x >> 4; i < K; i += WIDE_THREADS / 16) {
+        for (int i = threadIdx.x >> 4; i < K; i += MWIDE_THREADS / 16) {
             const double xi = sign * sm.xs[i];
             for (int j = threadIdx.x & 15; j <= i; j += 16) sm.S[i * K + j] = fma(xi, sm.xs[j], sm.S[i * K + j]);
         }
@@ -203,7 +203,7 @@ struct RollingWide {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(WIDE_THREADS) rolling_wide_kernel(const MovingParams p) {
+__global__ void __launch_bounds__(MWIDE_THREADS) rolling_wide_kernel(const MovingParams p) {
     extern __shared__ __align__(16) unsigned char wide_raw[];
     const int K = p.F;
     const int64_t c = blockIdx.x;
@@ -245,14 +245,14 @@ __global__ void __launch_bounds__(128) rolling_wide_prepass_kernel(const MovingP
 // ---- recursive least squares ---------------------------------------------------------------------------------
 // pass 1: information-form summary of a chunk -> summaries[c] = { A (K*K, lower triangle), b (K), D }
 template <typename T>
-__global__ void __launch_bounds__(WIDE_THREADS) rls_wide_summary_kernel(const MovingParams p) {
+__global__ void __launch_bounds__(MWIDE_THREADS) rls_wide_summary_kernel(const MovingParams p) {
     extern __shared__ __align__(16) unsigned char wide_raw[];
     const int K = p.F;
     const WideSmem sm = wide_carve(wide_raw, K);
     const int64_t c = blockIdx.x;
     const int64_t c0 = p.chunk_r0[c], c1 = p.chunk_r1[c];
     const T *mask = static_cast<const T *>(p.mask);
-    for (int e = threadIdx.x; e < K * K; e += WIDE_THREADS) sm.S[e] = 0.0;
+    for (int e = threadIdx.x; e < K * K; e += MWIDE_THREADS) sm.S[e] = 0.0;
     if (threadIdx.x < K) sm.v[threadIdx.x] = 0.0;
     __syncthreads();
     double D = 1.0;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) rls_wide_summary_kernel(const Mo
     for (int64_t r = c0; r < c1; ++r) {
         if (mask && mask[r] == T(0)) continue;
         wide_load_row<T>(p, sm, K, r);
-        for (int i = threadIdx.x >> 4; i < K; i += WIDE_THREADS / 16) {
+        for (int i = threadIdx.x >> 4; i < K; i += MWIDE_THREADS / 16) {
             const double xi = sm.xs[i];
             for (int j = threadIdx.x & 15; j <= i; j += 16) sm.S[i * K + j] = fma(xi, sm.xs[j], sm.S[i * K + j] * lam);
         }
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) rls_wide_summary_kernel(const Mo
         __syncthreads();
     }
     double *rec = p.summaries + c * moving_rec(K);
-    for (int e = threadIdx.x; e < K * K; e += WIDE_THREADS) {
+    for (int e = threadIdx.x; e < K * K; e += MWIDE_THREADS) {
         const int i = e / K, j = e - i * K;
         rec[e] = (j <= i) ? sm.S[e] : 0.0;
     }
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) rls_wide_scan_kernel(const MovingParams p
 // P stays exactly symmetric (P/lambda - K_i K_j r is symmetric term by term), so P x == (x^T P)^T bit for bit and
 // one block-wide product serves both.
 template <typename T>
-__global__ void __launch_bounds__(WIDE_THREADS) rls_wide_main_kernel(const MovingParams p) {
+__global__ void __launch_bounds__(MWIDE_THREADS) rls_wide_main_kernel(const MovingParams p) {
     extern __shared__ __align__(16) unsigned char wide_raw[];
     const int K = p.F;
     const WideSmem sm = wide_carve(wide_raw, K);
@@ -323,14 +323,14 @@ __global__ void __launch_bounds__(WIDE_THREADS) rls_wide_main_kernel(const Movin
     const bool first = (c0 == p.group_off[g]) && !p.init_info;
     double *P = sm.S, *theta = sm.theta, *px = sm.t, *kg = sm.kg;
     if (first) {
-        for (int e = tid; e < K * K; e += WIDE_THREADS) P[e] = ((e / K) == (e % K)) ? p.p0 : 0.0;
+        for (int e = tid; e < K * K; e += MWIDE_THREADS) P[e] = ((e / K) == (e % K)) ? p.p0 : 0.0;
         if (tid < K) theta[tid] = p.has_mean ? p.mean[tid] : 0.0;
         __syncthreads();
     } else {
         // information state (A, b) entering the chunk (from the scan) -> theta = A^-1 b, P = A^-1: one block-cooperative
         // Cholesky, then k + 1 substitutions; the columns of P overwrite A, which the factor no longer needs
         const double *rec = p.summaries + c * moving_rec(K);
-        for (int e = tid; e < K * K; e += WIDE_THREADS) sm.S[e] = rec[e];
+        for (int e = tid; e < K * K; e += MWIDE_THREADS) sm.S[e] = rec[e];
         if (tid < K) sm.v[tid] = rec[K * K + tid];
         __syncthreads();
         const bool ok = wide_factor(sm, K);  // A = prior + PSD terms: positive definite unless the data hold NaN / inf
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) rls_wide_main_kernel(const Movin
             }
         } else {
             __syncthreads();
-            for (int e = tid; e < K * K; e += WIDE_THREADS) P[e] = NAN;
+            for (int e = tid; e < K * K; e += MWIDE_THREADS) P[e] = NAN;
             if (tid < K) theta[tid] = NAN;
             __syncthreads();
         }
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(WIDE_THREADS) rls_wide_main_kernel(const Movin
                 theta[tid] = exact ? B200_ADD(theta[tid], B200_MUL(kv, resid)) : fma(kv, resid, theta[tid]);
             }
             __syncthreads();
-            for (int e = tid; e < K * K; e += WIDE_THREADS) {
+            for (int e = tid; e < K * K; e += MWIDE_THREADS) {
                 const int i = e / K, j = e - i * K;
                 P[e] = exact ? B200_ADD(B200_DIV(P[e], lam), -B200_MUL(B200_MUL(kg[i], kg[j]), rr))
                              : fma(P[e], inv_lam, -(kg[i] * kg[j]) * rr);
@@ -408,17 +408,17 @@ static cudaError_t launch_moving_wide_t(cudaStream_t stream, MovingParams &p, co
         } else {
             p.series_info = nullptr;
         }
-        rolling_wide_kernel<T><<<grid, WIDE_THREADS, smem, stream>>>(p);
+        rolling_wide_kernel<T><<<grid, MWIDE_THREADS, smem, stream>>>(p);
         ++*launches;
         return cudaGetLastError();
     }
     cudaFuncSetAttribute(rls_wide_summary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     cudaFuncSetAttribute(rls_wide_main_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    rls_wide_summary_kernel<T><<<grid, WIDE_THREADS, smem, stream>>>(p);
+    rls_wide_summary_kernel<T><<<grid, MWIDE_THREADS, smem, stream>>>(p);
     rls_wide_scan_kernel<<<static_cast<unsigned>(p.n_groups), 256, 0, stream>>>(p, group_chunk_off_dev);
     *launches += 2;
     if (p.state_only) return cudaGetLastError();
-    rls_wide_main_kernel<T><<<grid, WIDE_THREADS, smem, stream>>>(p);
+    rls_wide_main_kernel<T><<<grid, MWIDE_THREADS, smem, stream>>>(p);
     ++*launches;
     return cudaGetLastError();
 }
