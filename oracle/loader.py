@@ -49,6 +49,8 @@ def lib() -> C.CDLL:
     L.orc_inv_lu.restype = None
     L.orc_grouped_least_squares_coefficients.argtypes = [vp, i32, vp, i64, i32, d, d, i64, d, i32, i32, vp]
     L.orc_grouped_least_squares_coefficients.restype = None
+    L.orc_grouped_least_squares_predictions.argtypes = [vp, i32, vp, vp, i64, i32, d, d, i64, d, i32, i32, vp]
+    L.orc_grouped_least_squares_predictions.restype = None
     L.orc_max_threads.argtypes = []
     L.orc_max_threads.restype = i32
     _lib = L

@@ -614,6 +614,50 @@ ORC_API void orc_grouped_least_squares_coefficients(const double *const *cols, i
     }
 }
 
+/* CPU baseline of config C3 (bench only): `pl.col("y").least_squares.elastic_net(*x, sample_weights=w, mode="predictions")
+ * .over(group)`: per group the reference multiplies target and features by sqrt(w) (polars_ols/least_squares.py:190-196),
+ * copies into row-major f64 (src/expressions.rs:22-63), solves (model as above), predicts X beta (make_predictions,
+ * src/expressions.rs:175-195) and un-scales by 1/sqrt(w) (least_squares.py:234-235).  weights may be NULL.  out [N]. */
+ORC_API void orc_grouped_least_squares_predictions(const double *const *cols, int k, const double *weights,
+                                                   const int64_t *offsets, int64_t n_groups, int model, double alpha,
+                                                   double l1_ratio, int64_t max_iter, double tol, int positive,
+                                                   int n_threads, double *out) {
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel
+    {
+        double *xb = NULL, *yb = NULL, *beta = (double *)malloc(sizeof(double) * (size_t)k);
+        int64_t cap = 0;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t g = 0; g < n_groups; ++g) {
+            const int64_t r0 = offsets[g], n = offsets[g + 1] - r0;
+            if (n == 0) continue;
+            if (n > cap) {
+                free(xb); free(yb);
+                cap = n;
+                xb = (double *)malloc(sizeof(double) * (size_t)cap * k);
+                yb = (double *)malloc(sizeof(double) * (size_t)cap);
+            }
+            for (int64_t i = 0; i < n; ++i) {
+                const double s = weights ? sqrt(weights[r0 + i]) : 1.0;
+                yb[i] = cols[0][r0 + i] * s;
+                for (int j = 0; j < k; ++j) xb[i * k + j] = cols[1 + j][r0 + i] * s;
+            }
+            if (model == 0) orc_solve_ridge(yb, xb, n, k, alpha, 0, beta);
+            else if (model == 1) orc_solve_ols_qr(yb, xb, n, k, beta);
+            else orc_solve_elastic_net(yb, xb, n, k, alpha, l1_ratio, max_iter, tol, positive, model == 3, beta);
+            for (int64_t i = 0; i < n; ++i) {
+                double p = 0.0;
+                for (int j = 0; j < k; ++j) p += xb[i * k + j] * beta[j];
+                const double s = weights ? sqrt(weights[r0 + i]) : 1.0;
+                out[r0 + i] = p * (1.0 / s);
+            }
+        }
+        free(xb); free(yb); free(beta);
+    }
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

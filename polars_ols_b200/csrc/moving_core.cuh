@@ -69,26 +69,6 @@ struct NormalState {   // S = sum x x^T (+ alpha I), v = sum x y   (lower triang
     }
 };
 
-// 1 / sqrt(d) for the Cholesky pivots: single-precision MUFU seed + two Newton steps in f64 (~10 instructions against
-// ~25 for rsqrt(double), which also handles denormals and infinities; this runs k times per row of a 50M-row series).
-// Accurate to ~2 ulp for normal positive d inside the f32 exponent range; anything else takes the library routine.
-B200_HD double pivot_rsqrt(double d) {
-#if defined(__CUDA_ARCH__) && !defined(B200_PIVOT_RSQRT_LIB)
-    if (d > 1.0e-30 && d < 1.0e30) {
-        double y = static_cast<double>(rsqrtf(static_cast<float>(d)));
-        const double h = 0.5 * d;
-        y = y * fma(-h * y, y, 1.5);
-        y = y * fma(-h * y, y, 1.5);
-        return y;
-    }
-    return rsqrt(d);
-#elif defined(__CUDA_ARCH__)
-    return rsqrt(d);
-#else
-    return 1.0 / sqrt(d);
-#endif
-}
-
 // beta = S^-1 v by Cholesky (register resident); on a non-positive pivot fall back to LU with partial
 // pivoting on a local copy (solve_normal_equations(.., None, Some(LU)), src/least_squares.rs:732-734).
 template <int K>
@@ -103,7 +83,13 @@ B200_HD void solve_normal(const NormalState<K> &st, double (&beta)[K]) {
         if (!(d > 0.0)) ok = false;
         // one reciprocal square root per column instead of K divisions (f64 division and sqrt are ~25-instruction
         // sequences on the GPU and this runs once per row); results agree with the reference's LL^T to rounding
-        const double r = pivot_rsqrt(d);
+        // one reciprocal square root per column instead of K divisions; a hand-rolled MUFU.RSQ + two Newton steps was
+        // measured against the library routine on C4 (profiles/r02_c4_variants.json): no difference, the library one stays
+#if defined(__CUDA_ARCH__)
+        const double r = rsqrt(d);
+#else
+        const double r = 1.0 / sqrt(d);
+#endif
         inv[j] = r;
         L[j][j] = d * r;
 #pragma unroll

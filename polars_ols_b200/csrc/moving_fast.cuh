@@ -280,20 +280,52 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_fas
 // may be shifted by up to a unit (W or the series start need not be multiples of the unit).
 constexpr int NB_SLOTS = MF_DEPTH + 4;
 
-template <typename T, int K>
+// One warp per chunk, lanes stride over the rows (coalesced 256-byte requests per column), four rows in flight per
+// lane.  DECAY = false: plain Gram totals of the chunk (rolling_nbr_kernel's window sums entering the next chunk).
+// DECAY = true: the information-form summary of rls (A_c = sum lam^(n-1-i) x_i x_i^T, b_c likewise, D = lam^n, as
+// rls_summarise in moving_core.cuh): row i carries the weight lam^(n-1-i); a lane starts from one exp() and steps its
+// weight by lam^-32 per row of its own.
+template <typename T, int K, bool DECAY>
 __global__ void __launch_bounds__(256) chunk_totals_kernel(const MovingParams p, double *__restrict__ totals) {
     const int lane = threadIdx.x & 31;
     const int64_t c = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (c >= p.n_chunks) return;
     const int64_t r0 = p.chunk_r0[c], r1 = p.chunk_r1[c];
-    if (r1 == p.group_off[p.chunk_group[c] + 1]) return;  // last chunk of its series: nobody continues from it
+    if (!DECAY && r1 == p.group_off[p.chunk_group[c] + 1]) return;  // last chunk of its series: nobody continues from it
     const DevSrc<T, K> src = make_src<T, K>(p);
     NormalState<K> st;
     st.clear();
-    double x[K], y;
-    for (int64_t r = r0 + lane; r < r1; r += 32) {
+    const int64_t n = r1 - r0;
+    double wgt = 1.0, step = 1.0;
+    const double ll = DECAY ? log(p.lambda) : 0.0;
+    bool direct = false;  // absurdly short half-lives: lam^-32 overflows, take every weight from exp() instead
+    if (DECAY) {
+        wgt = exp(ll * static_cast<double>(n - 1 - lane));   // lam^(n-1-i) of this lane's first row
+        step = exp(-32.0 * ll);                              // lam^-32: the next row of this lane is 32 rows later
+        direct = !(step < 1.0e300);
+    }
+    auto next_weight = [&](int64_t row_done) {
+        if (!DECAY) return;
+        if (direct) wgt = exp(ll * static_cast<double>(r1 - 1 - (row_done + 32)));
+        else wgt *= step;
+    };
+    constexpr int U = 4;
+    int64_t r = r0 + lane;
+    for (; r + 32 * (U - 1) < r1; r += 32 * U) {
+        double x[U][K], y[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) src.load(r + 32 * u, x[u], y[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            st.add(x[u], y[u], wgt);
+            next_weight(r + 32 * u);
+        }
+    }
+    for (; r < r1; r += 32) {
+        double x[K], y;
         src.load(r, x, y);
-        st.add(x, y, 1.0);
+        st.add(x, y, wgt);
+        next_weight(r);
     }
     double *rec = totals + c * moving_rec(K);
 #pragma unroll
@@ -304,12 +336,14 @@ __global__ void __launch_bounds__(256) chunk_totals_kernel(const MovingParams p,
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) rec[i * K + j] = v;
+            if (DECAY && lane == 0 && j < i) rec[j * K + i] = 0.0;
         }
         double v = st.v[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) rec[K * K + i] = v;
     }
+    if (DECAY && lane == 0) rec[K * K + K] = exp(log(p.lambda) * static_cast<double>(n));
 }
 
 __host__ __device__ inline size_t moving_nbr_smem(int nc) { return static_cast<size_t>(NB_SLOTS) * nc * MF_THREADS * 16; }
@@ -410,51 +444,7 @@ __global__ void __launch_bounds__(MF_THREADS, MF_MIN_BLOCKS_ROLLING) rolling_nbr
 }
 
 // ---- recursive least squares -------------------------------------------------------------------------------
-// pass 1: information-form summary of every chunk (A_c = sum lam^(..) x x^T, b_c, D = lam^rows), as rls_summary_kernel
-template <typename T, int K, bool WT>
-__global__ void __launch_bounds__(MF_THREADS) rls_fast_summary_kernel(const MovingParams p) {
-    extern __shared__ __align__(16) unsigned char mf_smem[];
-    constexpr int RPU = FastSrc<T, K, WT>::RPU;
-    const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (c >= p.n_chunks) return;
-    const int64_t c0 = p.chunk_r0[c], c1 = p.chunk_r1[c];
-    FastSrc<T, K, WT> src = make_fast_src<T, K, WT>(p, mf_smem);
-    src.a0 = c0 & ~static_cast<int64_t>(RPU - 1);
-    NormalState<K> ab;
-    ab.clear();
-    double D = 1.0, x[K], y;
-    T y_raw, s;
-#pragma unroll
-    for (int b = -MF_DEPTH; b < 0; ++b) {
-        src.issue(src.lead, MF_LEAD_SLOTS, b + MF_DEPTH);
-        cp_async_commit();
-    }
-    const int64_t q_end = (c1 - src.a0 + RPU - 1) / RPU;
-    for (int64_t q = 0; q < q_end; ++q) {
-        src.issue(src.lead, MF_LEAD_SLOTS, q + MF_DEPTH);
-        cp_async_commit();
-        cp_async_wait<MF_DEPTH>();
-#pragma unroll
-        for (int wi = 0; wi < RPU; ++wi) {
-            const int64_t row = src.a0 + q * RPU + wi;
-            if (row < c0 || row >= c1) continue;
-            src.read(src.lead, MF_LEAD_SLOTS, row, x, y, y_raw, s);
-            ab.decay(p.lambda);
-            ab.add(x, y, 1.0);
-            D *= p.lambda;
-        }
-    }
-    cp_async_wait<0>();
-    double *rec = p.summaries + c * moving_rec(K);
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) rec[i * K + j] = (j <= i) ? ab.S[i][j] : 0.0;
-        rec[K * K + i] = ab.v[i];
-    }
-    rec[K * K + K] = D;
-}
-
+// pass 1 (chunk summaries in information form): chunk_totals_kernel<T, K, true> above
 // pass 3 (after the scan): the covariance-form recurrence of every chunk, restarted from the information state
 // entering it (rls_chunk of moving_core.cuh, rows through the staging ring)
 template <typename T, int K, bool WT>

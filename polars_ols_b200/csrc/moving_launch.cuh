@@ -29,7 +29,7 @@ static cudaError_t launch_moving_fast_t(cudaStream_t stream, MovingParams &p, in
         if (p.kind == MOVING_ROLLING && p.nbr) {
             const size_t smem = moving_nbr_smem(nc);
             cudaFuncSetAttribute(rolling_nbr_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            chunk_totals_kernel<T, K><<<static_cast<unsigned>((p.n_chunks * 32 + 255) / 256), 256, 0, stream>>>(p, p.summaries);
+            chunk_totals_kernel<T, K, false><<<static_cast<unsigned>((p.n_chunks * 32 + 255) / 256), 256, 0, stream>>>(p, p.summaries);
             const unsigned nb = static_cast<unsigned>((p.n_chunks + MF_THREADS - 2) / (MF_THREADS - 1));
             rolling_nbr_kernel<T, K, WT><<<nb, MF_THREADS, smem, stream>>>(p, p.summaries);
             *launches += 2;
@@ -43,9 +43,8 @@ static cudaError_t launch_moving_fast_t(cudaStream_t stream, MovingParams &p, in
             return cudaGetLastError();
         }
         const size_t smem = moving_fast_smem(nc, false);
-        cudaFuncSetAttribute(rls_fast_summary_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         cudaFuncSetAttribute(rls_fast_main_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        rls_fast_summary_kernel<T, K, WT><<<fb, MF_THREADS, smem, stream>>>(p);
+        chunk_totals_kernel<T, K, true><<<static_cast<unsigned>((p.n_chunks * 32 + 255) / 256), 256, 0, stream>>>(p, p.summaries);  // pass 1: chunk summaries
         const unsigned sb = static_cast<unsigned>((p.n_super * 32 + 127) / 128);
         rls_scan_kernel<K><<<sb, 128, 0, stream>>>(p, 0, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
         rls_scan_kernel<K><<<static_cast<unsigned>((p.n_groups * 32 + 127) / 128), 128, 0, stream>>>(p, 1, p.n_super, p.sup_c0, p.sup_c1, p.group_sup_off, p.sup);
