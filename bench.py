@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C4rls", "C5"],
+                    help="BASELINE.json config; C2 (default) is the metric's own configuration, the others print the same line "
+                         "shape through tools/bench_configs.py (N = 1)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: fused P2P stores from the solver warps (default) or an NCCL all-gather per step")
     a = ap.parse_args()
@@ -185,6 +188,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.config != "C2":   # the other BASELINE.json configs: single GPU, same line shape
+        if rank != 0:
+            return 0
+        if a.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU port of this config is timed inside the GPU arm's "
+                              "cpu_baseline (python bench.py --config %s)" % a.config}))
+            return 0
+        sys.path.insert(0, str(ROOT / "tools"))
+        from bench_configs import run_config
+        print(json.dumps(run_config(a.config, steps=a.steps if a.config != "C1" else max(a.steps, 200), warmup=a.warmup,
+                                    with_cpu=not a.no_cpu_baseline)))
+        return 0
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if a.impl == "reference":

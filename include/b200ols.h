@@ -184,10 +184,9 @@ B200OLS_API int b200ols_profile_drain(b200ols_ctx *ctx, float *ms, int max);
 /* tuning knobs (0 = default): rows per shared-memory tile and consumer warps per CTA of the
  * row-streaming Gram kernel */
 B200OLS_API int b200ols_set_tuning(b200ols_ctx *ctx, int tile_rows, int warps_per_cta, int ctas_per_sm);
-/* Gram kernel variant (default 3): 0 = per-warp TMA-staged shared-memory pipeline + DMMA, 1 = direct 16-byte global loads +
- * DMMA (k <= 16), 2 = direct loads + FP64 FMA, one row per lane (k <= 8), 3 = CTA-cooperative
- * warp-specialised TMA pipeline (producer / 8 consumer / solver warps, k <= 16).  `unroll` = row blocks in flight
- * per lane (0 = default).  Variants that do not cover a shape fall back to variant 0.
+/* Gram kernel variant: 3 (default) = CTA-cooperative warp-specialised TMA pipeline (producer / consumer / solver warps;
+ * gram_cta / gram_multi / gram_wide / gram_pred), 1 = direct 16-byte global loads + DMMA for k <= 16, the one non-TMA
+ * fallback (k > 16 always takes the TMA kernel).  `unroll` = row blocks in flight per lane of variant 1 (0 = default).
  * The environment variable B200OLS_VARIANT sets the initial variant of new contexts (test hook). */
 B200OLS_API int b200ols_set_variant(b200ols_ctx *ctx, int variant, int unroll);
 

@@ -23,7 +23,6 @@
 #include "gram_pred.cuh"
 #include "gram_wide.cuh"
 #include "gram_ldg.cuh"
-#include "gram_simt.cuh"
 #include "gram_stream.cuh"
 #include "moving.cuh"
 #include "predict.cuh"
@@ -95,7 +94,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
     if (const char *v = std::getenv("B200OLS_PRED")) c->pred_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_PRED_LAG")) c->pred_lag = std::max(1, std::atoi(v));
     if (const char *v = std::getenv("B200OLS_FUSE_MIN_BYTES")) c->fuse_min_bytes = std::atoll(v);  // test hook: fused-solve threshold
-    if (c->variant < 0 || c->variant > 3) c->variant = 3;
+    if (c->variant != 1 && c->variant != 3) c->variant = 3;
     *out = c;
     return 0;
 }
@@ -322,8 +321,8 @@ extern "C" int b200ols_set_tuning(b200ols_ctx *c, int tile_rows, int warps_per_c
 
 extern "C" int b200ols_set_variant(b200ols_ctx *c, int variant, int unroll) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
-    if (variant < 0 || variant > 3)
-        return fail(B200OLS_ERR_INVALID, "variant must be 0 (per-warp TMA DMMA), 1 (direct-load DMMA), 2 (direct-load FMA, k <= 8) or 3 (CTA-cooperative TMA DMMA)");
+    if (variant != 1 && variant != 3)
+        return fail(B200OLS_ERR_INVALID, "variant must be 3 (CTA-cooperative TMA pipeline, default) or 1 (direct-load DMMA, the non-TMA fallback for k <= 16)");
     c->variant = variant;
     c->unroll = unroll;
     return 0;
@@ -665,7 +664,7 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
     const int F = gp.F;
     const int KB = (F + 7) / 8;
     const int NC = gp.kd + 1 + gp.has_w + gp.has_mask;
-    if (c->variant == 3 && KB > 2 && !gp.fused) {  // 17 <= k <= 64: block pairs split across the consumer warps
+    if (KB > 2 && !gp.fused) {  // 17 <= k <= 64: block pairs split across the consumer warps
         const size_t budget = static_cast<size_t>(c->smem_optin) - 1024;
         int R = c->tile_rows > 0 ? c->tile_rows : 96;
         int S = 0;
@@ -818,19 +817,6 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         c->launches++;
         return 0;
     }
-    if (c->variant == 2 && KB == 1) {  // direct-load FP64-FMA variant (k <= 8)
-        int warps = std::min(c->warps_per_cta > 0 ? c->warps_per_cta : 8, 16);
-        const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 2;
-        int64_t grid = std::min<int64_t>(static_cast<int64_t>(c->sm_count) * ctas, (gp.nseg + warps - 1) / warps);
-        grid = std::max<int64_t>(grid, 1);
-        const int U = c->unroll > 0 ? c->unroll : 1;
-        if (U > 1) warps = std::min(warps, 8);
-        ProfScope prof(c);
-        CU(sizeof(T) == 8 ? gram_simt_launch_f64(U, gp, static_cast<unsigned>(grid), warps, c->stream)
-                          : gram_simt_launch_f32(U, gp, static_cast<unsigned>(grid), warps, c->stream));
-        c->launches++;
-        return 0;
-    }
     if (c->variant == 1 && KB <= 2) {  // direct-load variant
         int warps = std::min(c->warps_per_cta > 0 ? c->warps_per_cta : 8, 8);
         const int ctas = c->ctas_per_sm > 0 ? c->ctas_per_sm : 3;
@@ -843,36 +829,7 @@ static int launch_gram(b200ols_ctx *c, GramParams &gp) {
         c->launches++;
         return 0;
     }
-    const size_t budget = static_cast<size_t>(c->smem_optin) - 2048;  // static mbarriers + slack
-    const int KBT = KB <= 1 ? 1 : (KB <= 2 ? 2 : (KB <= 4 ? 4 : 8));  // instantiated block counts
-    int warps = c->warps_per_cta > 0 ? c->warps_per_cta : 8;
-    warps = std::min(warps, gram_max_warps(KBT));
-    int R = c->tile_rows > 0 ? c->tile_rows : 64;
-    int S = 4;
-    auto need = [&](int r, int s, int w) {
-        return (static_cast<size_t>(s) * NC * gram_col_stride<T>(r) + gram_scratch_bytes<T>(F, gp.fused)) * w;
-    };
-    while (need(R, S, warps) > budget) {
-        if (S > 3) --S;
-        else if (R > 64) R -= 8;
-        else if (S > 2) --S;
-        else if (R > 16) R -= 8;
-        else if (warps > 1) --warps;
-        else return fail(B200OLS_ERR_UNSUPPORTED, "Gram tile does not fit in shared memory (%d columns)", NC);
-    }
-    gp.tile_rows = R;
-    gp.stages = S;
-    const size_t smem = need(R, S, warps);
-    const int ctas_per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : 1;
-    int64_t grid = std::min<int64_t>(static_cast<int64_t>(c->sm_count) * ctas_per_sm, (gp.nseg + warps - 1) / warps);
-    grid = std::max<int64_t>(grid, 1);
-    {
-        ProfScope prof(c);
-        CU(sizeof(T) == 8 ? gram_launch_f64(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream)
-                          : gram_launch_f32(KBT, gp, static_cast<unsigned>(grid), warps, smem, c->stream));
-    }
-    c->launches++;
-    return 0;
+    return fail(B200OLS_ERR_UNSUPPORTED, "no Gram kernel for %d coefficients (fused = %d)", F, gp.fused);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -3,17 +3,10 @@
 #include "gram_multi.cuh"
 #include "gram_wide.cuh"
 #include "gram_ldg.cuh"
-#include "gram_simt.cuh"
 #include "gram_stream.cuh"
 namespace b200 {
-cudaError_t gram_launch_f64(int KB, const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s) {
-    return gram_launch_any<double>(KB, p, grid, warps, smem, s);
-}
 cudaError_t gram_ldg_launch_f64(int KB, int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
     return gram_ldg_launch_any<double>(KB, U, p, grid, warps, s);
-}
-cudaError_t gram_simt_launch_f64(int U, const GramParams &p, unsigned grid, int warps, cudaStream_t s) {
-    return gram_simt_launch_any<double>(U, p, grid, warps, s);
 }
 cudaError_t gram_cta_launch_f64(int KB, const GramParams &p, unsigned grid, size_t smem, cudaStream_t s) {
     const bool teams = p.team > 0 && p.team < CTA_CONSUMERS;

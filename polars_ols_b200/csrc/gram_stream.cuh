@@ -1,22 +1,14 @@
-// gram_stream.cuh — the hot kernel: row-streaming X^T X / X^T y per (group) segment with a fused
-// k x k solve.  Replaces, for every group of a `.over()` batch at once,
+// gram_stream.cuh — shared definitions of the row-streaming Gram kernels (gram_cta.cuh, gram_multi.cuh, gram_wide.cuh,
+// gram_pred.cuh, gram_ldg.cuh): the launch parameter block, the shared-memory stage geometry and the Gram epilogues
+// (fused k x k solve or partial-record write).  They replace, for every group of a `.over()` batch at once,
 //   construct_features_array + convert_polars_to_ndarray   src/expressions.rs:22-103  (SoA -> AoS copy)
 //   x.t().dot(x), x.t().dot(y), + alpha I                  src/least_squares.rs:352-356
 //   solve_normal_equations (Cholesky -> LU)                src/least_squares.rs:277-337
 // of /root/reference.  Nothing is copied to row-major: the SoA columns are streamed once from HBM.
-//
-// Structure (one warp = one independent pipeline, persistent over its segments):
-//   * the warp's elected lanes issue 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP, the TMA
-//     engine) of the k+1(+w)(+mask) column slices of a row tile into its private shared-memory stage,
-//     completion counted on an mbarrier (complete_tx); STAGES tiles are in flight per warp;
-//   * the warp waits on the stage's mbarrier and feeds FP64 tensor-core MMAs (mma.sync.m8n8k4.f64 ->
-//     SASS DMMA): with A = X^T tile and B = X tile the A and B fragments are THE SAME register
-//     (lane holds X[row = lane&3][feature = lane>>2]), so a k<=8 group costs one 16-byte LDS per lane per
-//     8 rows; X^T y rides along as one DFMA per block;
-//   * after the last tile of a segment the 8x8 accumulator fragments go to a per-warp scratch and lane 0
-//     runs the reference's Cholesky -> LU ladder; beta goes straight to HBM (fused path), or the raw
-//     Gram partial is written for the multi-segment / elastic-net solve kernel.
-// HBM traffic = algorithmic bytes (each column element is read exactly once) + 8k bytes out per group.
+// (Round 1 also kept a per-warp TMA pipeline and an FP64-FMA row-per-lane kernel selectable; both lost to the
+// CTA-cooperative pipeline everywhere they were measured — 0.65 / 0.65 against 0.94 of the HBM peak on C2,
+// profiles/r01_sweep_variant3.json — and were removed in round 2.  The direct-load DMMA kernel of gram_ldg.cuh is the
+// one non-TMA fallback.)
 #pragma once
 #include <cuda_runtime.h>
 
@@ -263,243 +255,6 @@ __device__ __forceinline__ void gram_epilogue(const GramParams &p, double (&acc)
             if (q == 0 && 8 * bi + fb < F) out[F * F + 8 * bi + fb] = cy[bi];
         }
         if (lane == 0) out[F * F + F] = static_cast<double>(nfit);
-    }
-}
-
-template <typename T, int KB, int MAXW>
-__global__ void __launch_bounds__(MAXW * 32, 1) gram_stream_kernel(const GramParams p) {
-    using Vec = typename V2<T>::type;
-    constexpr int FP = 8 * KB;
-    constexpr int NPAIR = KB * (KB + 1) / 2;
-    constexpr int A = 16 / sizeof(T);  // tile starts are aligned down to 16 bytes
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bars[GRAM_MAX_WARPS * GRAM_MAX_STAGES];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-    const int fb = lane >> 2, q = lane & 3;
-    const int kd = p.kd, F = p.F;
-    const int ycol = kd, wcol = kd + 1, mcol = kd + 1 + (p.has_w ? 1 : 0);
-    const int NC = kd + 1 + (p.has_w ? 1 : 0) + (p.has_mask ? 1 : 0);
-    const int R = p.tile_rows, S = p.stages;
-    const uint32_t stride = gram_col_stride<T>(R);
-    const uint32_t stage_bytes = static_cast<uint32_t>(NC) * stride;
-    const uint32_t scratch_bytes = gram_scratch_bytes<T>(F, p.fused);
-    unsigned char *wbase = smem + static_cast<size_t>(warp) * (static_cast<size_t>(S) * stage_bytes + scratch_bytes);
-    double *Gs = reinterpret_cast<double *>(wbase + static_cast<size_t>(S) * stage_bytes);
-    uint64_t *bar = bars + warp * GRAM_MAX_STAGES;
-
-    if (lane == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&bar[s], 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
-
-    const int64_t nseg = p.nseg;
-    const int64_t wg = static_cast<int64_t>(blockIdx.x) * W + warp;
-    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * W;
-
-    // ---- issue cursor: runs `S` tiles ahead of the consumer over the same (segment, tile) sequence ----
-    int64_t iseg = wg, irow = 0, iend = 0;
-    if (iseg < nseg) {
-        irow = p.seg_off[iseg];
-        iend = p.seg_off[iseg + 1];
-    }
-    int istage = 0;
-    auto issue = [&]() {
-        while (iseg < nseg && irow >= iend) {
-            iseg += nwarps;
-            if (iseg < nseg) {
-                irow = p.seg_off[iseg];
-                iend = p.seg_off[iseg + 1];
-            }
-        }
-        if (iseg >= nseg) return;
-        const int64_t a = irow;
-        const int64_t b = (a + R < iend) ? a + R : iend;
-        const int64_t a_al = a & ~static_cast<int64_t>(A - 1);
-        int64_t b_al = (b + (A - 1)) & ~static_cast<int64_t>(A - 1);
-        if (b_al > p.n_rows_pad) b_al = p.n_rows_pad;
-        const uint32_t bytes = static_cast<uint32_t>(b_al - a_al) * sizeof(T);
-        unsigned char *sb = wbase + static_cast<size_t>(istage) * stage_bytes;
-        if (lane == 0) {
-            fence_proxy_async_smem();  // our generic-proxy reads of this stage are done (WAR vs async proxy)
-            mbar_arrive_expect_tx(&bar[istage], bytes * static_cast<uint32_t>(NC));
-        }
-        __syncwarp();
-        for (int c = lane; c < NC; c += 32)
-            bulk_g2s(sb + static_cast<size_t>(c) * stride, static_cast<const T *>(p.cols[c]) + a_al, bytes,
-                     &bar[istage]);
-        irow = b;
-        istage = (istage + 1 == S) ? 0 : istage + 1;
-    };
-    for (int s = 0; s < S; ++s) issue();
-
-    int cstage = 0;
-    uint32_t phase = 0;
-
-    for (int64_t seg = wg; seg < nseg; seg += nwarps) {
-        const int64_t r0 = p.seg_off[seg], r1 = p.seg_off[seg + 1];
-        constexpr bool DUAL = KB <= 2;  // two independent DMMA chains while the accumulators are few
-        double acc[NPAIR][2], acc2[DUAL ? NPAIR : 1][2];
-        double cy[KB];
-#pragma unroll
-        for (int i = 0; i < NPAIR; ++i) acc[i][0] = acc[i][1] = 0.0;
-#pragma unroll
-        for (int i = 0; i < (DUAL ? NPAIR : 1); ++i) acc2[i][0] = acc2[i][1] = 0.0;
-#pragma unroll
-        for (int i = 0; i < KB; ++i) cy[i] = 0.0;
-        int nfit = 0;
-        const bool plain = !p.has_mask && !p.has_w;  // warp-uniform: mask-free interior loop allowed
-
-        for (int64_t row = r0; row < r1; row += R) {
-            const int64_t b = (row + R < r1) ? row + R : r1;
-            const int o = static_cast<int>(row & (A - 1));
-            const int hi = o + static_cast<int>(b - row);  // valid local rows are [o, hi)
-            mbar_wait(&bar[cstage], phase);
-            const unsigned char *sb = wbase + static_cast<size_t>(cstage) * stage_bytes;
-            const unsigned char *xs[KB];
-#pragma unroll
-            for (int bk = 0; bk < KB; ++bk) xs[bk] = sb + static_cast<size_t>(8 * bk + fb) * stride + 2 * q * sizeof(T);
-            const unsigned char *ys = sb + static_cast<size_t>(ycol) * stride + 2 * q * sizeof(T);
-
-            // predicated octet (segment edges, weights, row mask)
-            auto masked_octet = [&](int j) {
-                const int lr = 8 * j + 2 * q;
-                bool v0 = (lr >= o) && (lr < hi);
-                bool v1 = (lr + 1 >= o) && (lr + 1 < hi);
-                const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
-                T s0 = T(1), s1 = T(1);
-                if (p.has_mask) {
-                    const Vec m2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(mcol) * stride + lr * sizeof(T));
-                    v0 = v0 && (m2.x != T(0));
-                    v1 = v1 && (m2.y != T(0));
-                }
-                if (p.has_w) {
-                    const Vec w2 = *reinterpret_cast<const Vec *>(sb + static_cast<size_t>(wcol) * stride + lr * sizeof(T));
-                    // polars: sqrt_w = w.sqrt() in the column dtype (polars_ols/least_squares.py:193)
-                    s0 = p.w_is_sqrt ? w2.x : static_cast<T>(sqrt(w2.x));
-                    s1 = p.w_is_sqrt ? w2.y : static_cast<T>(sqrt(w2.y));
-                }
-                // target * sqrt_w and feature * sqrt_w are evaluated in the column dtype, then cast to f64
-                const double y0 = v0 ? static_cast<double>(static_cast<T>(y2.x * s0)) : 0.0;
-                const double y1 = v1 ? static_cast<double>(static_cast<T>(y2.y * s1)) : 0.0;
-                if (fb == 0) nfit += (v0 ? 1 : 0) + (v1 ? 1 : 0);
-                double f0[KB], f1[KB];
-#pragma unroll
-                for (int bk = 0; bk < KB; ++bk) {
-                    const int f = 8 * bk + fb;
-                    T x0 = T(0), x1 = T(0);
-                    if (f < kd) {
-                        const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
-                        x0 = x2.x;
-                        x1 = x2.y;
-                    } else if (f == kd && p.intercept) {
-                        x0 = T(1);
-                        x1 = T(1);
-                    }
-                    f0[bk] = v0 ? static_cast<double>(static_cast<T>(x0 * s0)) : 0.0;
-                    f1[bk] = v1 ? static_cast<double>(static_cast<T>(x1 * s1)) : 0.0;
-                }
-                int idx = 0;
-#pragma unroll
-                for (int bi = 0; bi < KB; ++bi) {
-#pragma unroll
-                    for (int bj = bi; bj < KB; ++bj) {
-                        dmma_m8n8k4(acc[idx][0], acc[idx][1], f0[bi], f0[bj]);
-                        if (DUAL) dmma_m8n8k4(acc2[idx][0], acc2[idx][1], f1[bi], f1[bj]);
-                        else dmma_m8n8k4(acc[idx][0], acc[idx][1], f1[bi], f1[bj]);
-                        ++idx;
-                    }
-                    cy[bi] = fma(f0[bi], y0, cy[bi]);
-                    cy[bi] = fma(f1[bi], y1, cy[bi]);
-                }
-            };
-
-            const int noct = (hi + 7) >> 3;
-            if (!plain) {
-                for (int j = 0; j < noct; ++j) masked_octet(j);
-            } else {
-                int j = 0;
-                if (o != 0) {
-                    masked_octet(0);
-                    j = 1;
-                }
-                const int jfull = hi >> 3;  // octets [j, jfull) lie entirely inside [o, hi)
-#pragma unroll 4
-                for (; j < jfull; ++j) {
-                    const Vec y2 = *reinterpret_cast<const Vec *>(ys + 8 * j * sizeof(T));
-                    double f0[KB], f1[KB];
-#pragma unroll
-                    for (int bk = 0; bk < KB; ++bk) {
-                        const int f = 8 * bk + fb;
-                        if (f < kd) {
-                            const Vec x2 = *reinterpret_cast<const Vec *>(xs[bk] + 8 * j * sizeof(T));
-                            f0[bk] = static_cast<double>(x2.x);
-                            f1[bk] = static_cast<double>(x2.y);
-                        } else {
-                            f0[bk] = f1[bk] = (f == kd && p.intercept) ? 1.0 : 0.0;
-                        }
-                    }
-                    const double y0 = static_cast<double>(y2.x), y1 = static_cast<double>(y2.y);
-                    int idx = 0;
-#pragma unroll
-                    for (int bi = 0; bi < KB; ++bi) {
-#pragma unroll
-                        for (int bj = bi; bj < KB; ++bj) {
-                            dmma_m8n8k4(acc[idx][0], acc[idx][1], f0[bi], f0[bj]);
-                            if (DUAL) dmma_m8n8k4(acc2[idx][0], acc2[idx][1], f1[bi], f1[bj]);
-                        else dmma_m8n8k4(acc[idx][0], acc[idx][1], f1[bi], f1[bj]);
-                            ++idx;
-                        }
-                        cy[bi] = fma(f0[bi], y0, cy[bi]);
-                        cy[bi] = fma(f1[bi], y1, cy[bi]);
-                    }
-                }
-                if (j < noct) masked_octet(j);
-            }
-            __syncwarp();
-            issue();  // refill the stage we just drained
-            if (++cstage == S) {
-                cstage = 0;
-                phase ^= 1u;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < (DUAL ? NPAIR : 0); ++i) {
-            acc[i][0] += acc2[i][0];
-            acc[i][1] += acc2[i][1];
-        }
-        if (plain) nfit = (lane == 0) ? static_cast<int>(r1 - r0) : 0;
-
-        gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane);
-    }
-}
-
-// max consumer warps per CTA for a given number of 8-feature blocks (register budget: the 8x8 f64
-// accumulator fragments of all block pairs live in registers)
-__host__ __device__ constexpr int gram_max_warps(int KB) { return KB <= 2 ? 16 : (KB <= 4 ? 8 : 4); }
-
-// defined in gram_f64.cu / gram_f32.cu (one translation unit per dtype keeps the build parallel)
-cudaError_t gram_launch_f64(int KB, const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s);
-cudaError_t gram_launch_f32(int KB, const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s);
-
-template <typename T, int KB>
-cudaError_t gram_launch_t(const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s) {
-    auto kern = gram_stream_kernel<T, KB, gram_max_warps(KB)>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    kern<<<grid, warps * 32, smem, s>>>(p);
-    return cudaGetLastError();
-}
-
-template <typename T>
-cudaError_t gram_launch_any(int KB, const GramParams &p, unsigned grid, int warps, size_t smem, cudaStream_t s) {
-    switch (KB) {
-        case 1: return gram_launch_t<T, 1>(p, grid, warps, smem, s);
-        case 2: return gram_launch_t<T, 2>(p, grid, warps, smem, s);
-        case 4: return gram_launch_t<T, 4>(p, grid, warps, smem, s);
-        default: return gram_launch_t<T, 8>(p, grid, warps, smem, s);
     }
 }
 
