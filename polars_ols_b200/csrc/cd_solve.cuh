@@ -13,14 +13,45 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
+#include <type_traits>
 
+#include "predict.cuh"
 #include "small_solve.cuh"
 #include "solvers.cuh"
 
 namespace b200 {
 
-template <int WIDTH, int NPL>
-__global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
+// predictions / residuals of one group straight after its coordinate descent, by the sub-warp that solved it: the
+// coefficients never leave the registers, and the second streaming pass (predict_kernel: one more launch, one more
+// binary search per chunk, beta through L1) disappears — while other sub-warps are still in their latency-bound
+// sweeps this one streams its rows.  Same arithmetic, in the same order, as predict_row / predict_kernel (predict.cuh).
+template <typename T, int WIDTH>
+__device__ __forceinline__ void cd_predict_group(const PredictParams &pp, int64_t g, const double (&b)[WIDTH], int sl) {
+    const int kd = pp.kd;
+    const int64_t r0 = pp.seg_off[g], r1 = pp.seg_off[g + 1];
+    for (int64_t r = r0 + sl; r < r1; r += WIDTH) {
+        T s = T(1);
+        if (pp.has_w) s = predict_scale<T>(pp, static_cast<const T *>(pp.cols[kd])[r]);
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < WIDTH; ++j)
+            if (j < kd) acc = fma(static_cast<double>(static_cast<T>(static_cast<const T *>(pp.cols[j])[r] * s)), b[j], acc);
+        if (pp.intercept) {
+            double bi = 0.0;
+#pragma unroll
+            for (int j = 0; j < WIDTH; ++j)
+                if (j == kd) bi = b[j];
+            acc = fma(static_cast<double>(s), bi, acc);
+        }
+        predict_store<T>(pp, r, acc, s, g);
+    }
+}
+
+struct NoPredict {};  // cd_solve_kernel<WIDTH, NPL, NoPredict>: coefficients only
+
+template <int WIDTH, int NPL, typename PT = NoPredict>
+__global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p, const PredictParams pp) {
     extern __shared__ __align__(16) unsigned char cd_smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int F = p.F;
@@ -130,6 +161,12 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
                 if (mine) p.beta[g * F + sl] = (nfit == 0.0) ? 0.0 : w0;  // src/expressions.rs:357-359: no rows -> zeros
                 if (sl == 0) p.flags[g] = (nfit == 0.0) ? FLAG_EMPTY : 0;
             }
+            if constexpr (!std::is_same<PT, NoPredict>::value) {
+                double b[WIDTH];  // every lane of the sub-warp takes the whole coefficient vector
+#pragma unroll
+                for (int j = 0; j < WIDTH; ++j) b[j] = __shfl_sync(FULL, (nfit == 0.0) ? 0.0 : w0, j, WIDTH);
+                if (live) cd_predict_group<PT, WIDTH>(pp, g, b, sl);
+            }
         } else
         if (live) {
             if (nfit == 0.0) {  // src/expressions.rs:357-359: no rows -> zeros
@@ -193,7 +230,10 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
     }
 }
 
-inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, int sm_count) {
+// `pred` != nullptr (F <= 16, one segment per group): the kernel also writes the predictions / residuals of every group
+// (cd_predict_group); `f64` = dtype of the columns in *pred
+inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, int sm_count, const PredictParams *pred = nullptr,
+                                   bool f64 = true) {
     const int F = sp.F;
     int width, npl;
     if (F <= 8) { width = 8; npl = 1; }
@@ -210,9 +250,22 @@ inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, i
     const int64_t max_blocks = static_cast<int64_t>(sm_count) * std::max<int64_t>(1, std::min<int64_t>(16, (200 * 1024) / std::max<size_t>(smem, 1)));
     blocks = std::max<int64_t>(1, std::min(blocks, max_blocks));
     cudaError_t e = cudaSuccess;
+    PredictParams none;
+    std::memset(&none, 0, sizeof(none));
+#define B200_CD_LAUNCH_P(WD, PT)                                                                                          \
+    e = cudaFuncSetAttribute(cd_solve_kernel<WD, 1, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+    if (e == cudaSuccess) cd_solve_kernel<WD, 1, PT><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(sp, *pred);
+    if (pred && npl == 1 && width <= 16 && !sp.group_seg_off) {
+        if (width == 8) { if (f64) { B200_CD_LAUNCH_P(8, double) } else { B200_CD_LAUNCH_P(8, float) } }
+        else { if (f64) { B200_CD_LAUNCH_P(16, double) } else { B200_CD_LAUNCH_P(16, float) } }
+        if (e != cudaSuccess) return e;
+        return cudaGetLastError();
+    }
+#undef B200_CD_LAUNCH_P
+    if (pred) return cudaErrorInvalidValue;  // the caller checks cd_solve_can_predict first
 #define B200_CD_LAUNCH(WD, NP)                                                                                      \
     e = cudaFuncSetAttribute(cd_solve_kernel<WD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-    if (e == cudaSuccess) cd_solve_kernel<WD, NP><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(sp);
+    if (e == cudaSuccess) cd_solve_kernel<WD, NP><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(sp, none);
     if (width == 8) { B200_CD_LAUNCH(8, 1) }
     else if (width == 16) { B200_CD_LAUNCH(16, 1) }
     else if (npl == 1) { B200_CD_LAUNCH(32, 1) }
@@ -221,5 +274,7 @@ inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, i
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
+
+inline bool cd_solve_can_predict(int F, bool split) { return F <= 16 && !split; }
 
 }  // namespace b200

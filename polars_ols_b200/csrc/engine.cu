@@ -93,6 +93,7 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
     if (const char *v = std::getenv("B200OLS_MULTI")) c->multi_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_PRED")) c->pred_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_PRED_LAG")) c->pred_lag = std::max(1, std::atoi(v));
+    if (const char *v = std::getenv("B200OLS_CD_PRED")) c->cd_pred_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_FUSE_MIN_BYTES")) c->fuse_min_bytes = std::atoll(v);  // test hook: fused-solve threshold
     if (c->variant != 1 && c->variant != 3) c->variant = 3;
     *out = c;
@@ -1308,6 +1309,32 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         if (f->dtype == B200OLS_F64) TRY(launch_gram<double>(c, gp)); else TRY(launch_gram<float>(c, gp));
     }
 
+    bool cd_predicted = false;
+    auto make_predict_params = [&]() {
+        PredictParams pr;
+        std::memset(&pr, 0, sizeof(pr));
+        for (int j = 0; j < st.kd; ++j) pr.cols[j] = st.feat[j];
+        if (st.has_w) pr.cols[st.kd] = st.w;
+        pr.kd = st.kd;
+        pr.intercept = st.intercept;
+        pr.F = F;
+        pr.has_w = st.has_w;
+        pr.w_is_sqrt = st.w_is_sqrt;
+        pr.target = st.y_raw;
+        pr.target_is_packed = st.y_raw_packed;
+        pr.target_validity = st.y_validity;
+        pr.mask = (kw->null_policy == B200OLS_NULL_DROP) ? st.mask : nullptr;
+        pr.nseg = pl.nseg;
+        pr.n_rows = N;
+        pr.seg_off = pl.seg_off;
+        pr.seg_group = pl.seg_group;
+        pr.beta = beta;
+        pr.row_index = st.row_index;
+        pr.residuals = mode == B200OLS_RESIDUALS;
+        pr.out = dout;
+        pr.out_valid = dval;
+        return pr;
+    };
     if (!gp.fused) {
         SolveParams sp;
         std::memset(&sp, 0, sizeof(sp));
@@ -1326,7 +1353,14 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         sp.max_iter = rt.max_iter;
         sp.positive = rt.positive;
         if (cd) {
-            CU(launch_cd_solve(c->stream, sp, c->sm_count));
+            // predictions / residuals straight from the sub-warp that ran the coordinate descent (cd_solve.cuh): no second pass
+            cd_predicted = mode != B200OLS_COEFFICIENTS && !stats && !peer_mode && c->cd_pred_enabled && cd_solve_can_predict(F, pl.split);
+            if (cd_predicted) {
+                PredictParams prc = make_predict_params();
+                CU(launch_cd_solve(c->stream, sp, c->sm_count, &prc, f->dtype == B200OLS_F64));
+            } else {
+                CU(launch_cd_solve(c->stream, sp, c->sm_count));
+            }
         } else if (F <= 16) {
             CU(launch_batch_solve(c->stream, sp));
         } else {
@@ -1448,33 +1482,12 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         return 0;
     }
 
-    PredictParams pr;
-    std::memset(&pr, 0, sizeof(pr));
-    for (int j = 0; j < st.kd; ++j) pr.cols[j] = st.feat[j];
-    if (st.has_w) pr.cols[st.kd] = st.w;
-    pr.kd = st.kd;
-    pr.intercept = st.intercept;
-    pr.F = F;
-    pr.has_w = st.has_w;
-    pr.w_is_sqrt = st.w_is_sqrt;
-    pr.target = st.y_raw;
-    pr.target_is_packed = st.y_raw_packed;
-    pr.target_validity = st.y_validity;
-    pr.mask = (kw->null_policy == B200OLS_NULL_DROP) ? st.mask : nullptr;
-    pr.nseg = pl.nseg;
-    pr.n_rows = N;
-    pr.seg_off = pl.seg_off;
-    pr.seg_group = pl.seg_group;
-    pr.beta = beta;
-    pr.row_index = st.row_index;
-    pr.residuals = mode == B200OLS_RESIDUALS;
-    pr.out = dout;
-    pr.out_valid = dval;
+    PredictParams pr = make_predict_params();
     if (pred_fused) {  // only the groups whose beta was re-solved after the fused kernel (pivoted QR / min-norm SVD) are redone
         pr.flags = flags;
         pr.only_flags = FLAG_QR | FLAG_SVD;
     }
-    if (!pred_fused || rt.ols_qr_guard || rt.svd_wide) {
+    if ((!pred_fused || rt.ols_qr_guard || rt.svd_wide) && !cd_predicted) {
         const int64_t warps_needed = (N + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
         const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
         if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);

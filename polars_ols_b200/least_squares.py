@@ -241,8 +241,10 @@ class ProductExpr(Expr):
 def build_expressions_from_patsy_formula(formula: str, include_dependent_variable: bool = False) -> Tuple[List[Expr], bool]:
     """Subset of patsy formulas the reference supports (polars_ols/utils.py:62-111): ``y ~ x1 + x2:x3 - 1`` — plain
     columns, ``:`` interactions and the intercept switch.  patsy is not required: the grammar is parsed here.  As in
-    the reference, functions of columns (``log(x1)``) and categoricals (``C(group)``) are not supported, and the
-    intercept is added unless the formula text contains ``-1`` (utils.py:99)."""
+    the reference, functions of columns (``log(x1)``) and categoricals (``C(group)``) are not supported.  The intercept
+    switch is the reference's literal test ``"-1" not in formula`` on the RAW text (utils.py:99): ``"y ~ x1 -1"`` drops the
+    ``const`` column, ``"y ~ x1 - 1"`` (with a space) keeps it — a quirk, copied, not fixed.  Repeated terms are kept
+    once, as patsy's ``ModelDesc`` does."""
     text = formula.replace(" ", "")
     if "~" in text:
         lhs, rhs = text.split("~", 1)
@@ -252,8 +254,9 @@ def build_expressions_from_patsy_formula(formula: str, include_dependent_variabl
         assert lhs and "+" not in lhs and "-" not in lhs, "must provide exactly one LHS variable"
     else:
         assert not lhs, "can not provide LHS variables in this context"
-    add_intercept = "-1" not in text
+    add_intercept = "-1" not in formula
     exprs: List[Expr] = []
+    seen: Set[str] = set()
     if include_dependent_variable:
         exprs.append(Expr(lhs))
     for term in rhs.replace("-", "+-").split("+"):
@@ -264,6 +267,10 @@ def build_expressions_from_patsy_formula(formula: str, include_dependent_variabl
         if any(ch in term for ch in "()*/^") or term.startswith("-"):
             raise NotImplementedError(f"formula term {term!r}: only columns, ':' interactions and the intercept are supported")
         factors = term.split(":")
+        key = ":".join(sorted(factors))          # patsy: a term is a set of factors, listed once
+        if key in seen:
+            continue
+        seen.add(key)
         exprs.append(Expr(factors[0]) if len(factors) == 1 else ProductExpr(factors))
     return exprs, add_intercept
 

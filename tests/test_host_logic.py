@@ -240,8 +240,14 @@ def test_formula_parser_subset():
         pls.build_expressions_from_patsy_formula("y ~ x1")                              # LHS not allowed here
     with pytest.raises(AssertionError):
         pls.build_expressions_from_patsy_formula("x1 + x2", include_dependent_variable=True)
+    # the reference tests `"-1" not in formula` on the RAW text (polars_ols/utils.py:99): "- 1" with a space KEEPS the
+    # intercept column although patsy dropped the intercept term — copied, not fixed; repeated terms appear once
     e = pls.col("y").least_squares.from_formula("x1 + x2 - 1", window_size=20)
-    assert e.kind == "rolling_least_squares" and not e.add_intercept
+    assert e.kind == "rolling_least_squares" and e.add_intercept
+    e = pls.col("y").least_squares.from_formula("x1 + x2 -1", window_size=20)
+    assert not e.add_intercept
+    ex, _ = pls.build_expressions_from_patsy_formula("x1 + x2 + x1 + x2:x3 + x3:x2")
+    assert [t.output_name for t in ex] == ["x1", "x2", "x2:x3"]
     e = pls.compute_least_squares_from_formula("y ~ x1", half_life=3.0)
     assert e.kind == "recursive_least_squares" and e.add_intercept
 
@@ -308,3 +314,16 @@ def test_cd_branch_free_soft_threshold_is_the_reference_formula():
                     keep = keep & (x > 0.0)
                 new = np.where(keep, np.copysign(av, x), 0.0)
             assert np.array_equal(ref + 0.0, new + 0.0), (t, positive)     # + 0.0: -0.0 and 0.0 are the same coefficient
+
+
+def test_polars_adapter_is_guarded():
+    """the batched `.over()` route for real polars frames (polars_ols/least_squares.py:199-239 replaced by ONE engine call)
+    imports without polars and says so"""
+    from polars_ols_b200 import polars_adapter as pa
+    import polars_ols_b200 as pls
+    e = pls.col("y").least_squares.ridge("x1", "x2:x3", alpha=1.0, sample_weights="w", mode="coefficients").over("g", "h")
+    assert pa._needed_columns(e) == ["y", "x1", "x2:x3", "w", "g", "h"] or pa._needed_columns(e)[:2] == ["y", "x1"]
+    if not pa.available():
+        with pytest.raises(ImportError):
+            pa.over_batched(None, e)
+        assert pa.register_namespace() is None
