@@ -261,8 +261,8 @@ def main():
     if world > 1 and a.gather == "peer":
         # fused gather: beta goes from the solver warps into every rank's [world*G, K] buffer over NVLink
         try:
-            peer = PeerGather(eng, world * G, K, rank * G)
-            peer.attach()
+            peer = PeerGather(eng, world * G, K, rank * G, n_buffers=2)
+            peer.attach(0)
         except Exception as exc:  # no P2P / IPC on this box: fall back to the NCCL all-gather (same results)
             peer = None
             a.gather = "nccl"
@@ -277,10 +277,17 @@ def main():
 
     def full_step(i):
         b = i & 1
-        if world == 1 or peer is not None:
+        if world == 1:
             steps_fn[b]()
-            if peer is not None:
-                peer.step_complete()    # per-step cross-rank completion (release / acquire flags over NVLink)
+            return
+        if peer is not None:
+            # double-buffered fused gather: step i stores into buffer i & 1 of every rank and signals; the wait for step
+            # i - 1 (all ranks' rows of that step have landed here) is enqueued behind this step's kernel
+            peer.attach(b)
+            steps_fn[b]()
+            sig = peer.step_signal()
+            if sig > 1:
+                peer.step_wait(sig - 1)
             return
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ev_gath[b])          # WAR: the gather issued two steps ago has consumed this buffer
@@ -294,6 +301,8 @@ def main():
     def drain():
         if comm is not None:
             torch.cuda.current_stream(dev).wait_stream(comm)
+        if peer is not None and peer.step > 0:
+            peer.step_wait(peer.step)           # the last step's gather is complete too
 
     for i in range(a.warmup):
         full_step(i)
@@ -322,7 +331,7 @@ def main():
     if peer is not None:
         # every rank's shard must have landed in this rank's buffer (all ranks synchronised at the barrier above)
         assert not eng.peer_timed_out(), "a peer never signalled step completion"
-        full = peer.read()
+        full = peer.read((a.steps - 1) & 1)
         assert np.isfinite(full).all() and (np.abs(full).sum(axis=1) > 0).all(), "peer gather incomplete"
         coef = torch.as_tensor(full[rank * G:(rank + 1) * G], device=dev)
         peer.close()
@@ -411,19 +420,23 @@ def main():
         sxd = torch.as_tensor(np.ascontiguousarray(xs[:, r0:r1]), device=dev)
         syd = torch.as_tensor(np.ascontiguousarray(ys[r0:r1]), device=dev)
         sbatch = pls.Batch(pls.Col(syd), [pls.Col(sxd[i]) for i in range(K)], offsets=loffs)
-        speer = PeerGather(seng, G, K, g0) if peer is not None else None
+        speer = PeerGather(seng, G, K, g0, n_buffers=2) if peer is not None else None
         scoef = torch.empty((g1 - g0, K), dtype=torch.float64, device=dev)
         if speer is not None:
-            speer.attach()
+            speer.attach(0)
         sstep = seng.prepare_least_squares(sbatch, kw, L.COEFFICIENTS, None if speer is not None else scoef)
         sgath = torch.empty((G, K), dtype=torch.float64, device=dev)
         sshards = shard_groups(offs, world)
 
         def strong_step():
-            sstep()
             if speer is not None:
-                speer.step_complete()
+                speer.attach(speer.step & 1)
+                sstep()
+                sig = speer.step_signal()
+                if sig > 1:
+                    speer.step_wait(sig - 1)
             else:
+                sstep()
                 gather_group_results(scoef, sshards, out=sgath if all(b_ - a_ == sshards[0][1] - sshards[0][0] for a_, b_ in sshards) else None)
 
         for _ in range(a.warmup):
@@ -433,13 +446,15 @@ def main():
         s0.record()
         for _ in range(a.steps):
             strong_step()
+        if speer is not None:
+            speer.step_wait(speer.step)
         s1.record()
         torch.cuda.synchronize(); dist.barrier()
         ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         if speer is not None:
             assert not seng.peer_timed_out()
-            full = speer.read()
+            full = speer.read((speer.step - 1) & 1)
             speer.close()
             if rank == 0:   # rank 0 holds the identical frame in full: every shard must have landed, and be right
                 assert np.allclose(full, hcoef, rtol=1e-9, atol=1e-12), "strong-scaling gather differs from the single-GPU result"
@@ -498,8 +513,9 @@ def main():
             "config": make_config(world),
             "notes": ("" if world == 1 else
                       ("coefficient chunks gathered by P2P stores from the solver warps into every rank's buffer (NVLink peer memory, "
-                       "fused into the kernel); every step ends with a release/acquire flag exchange between all ranks INSIDE the timed "
-                       "loop (b200ols_peer_step_complete): a step is complete only when every rank's rows have landed everywhere"
+                       "fused into the kernel, two alternating buffers); every step signals a release flag to all ranks and the acquire-wait "
+                       "for step i - 1 is enqueued behind step i's kernel, INSIDE the timed loop (b200ols_peer_step_signal / _wait): the "
+                       "timed region ends only when every rank's rows of every step have landed everywhere"
                        if a.gather == "peer" else
                        "NCCL all-gather of coefficient chunks per step (side stream, overlapped with the next step's kernel)")),
             "clocks": clk.summary(),

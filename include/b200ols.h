@@ -289,6 +289,10 @@ B200OLS_API int b200ols_set_peer_gather(b200ols_ctx *ctx, int n_peers, void *con
  * (a peer never signalled; ~2 s), else 0; synchronises the stream. */
 B200OLS_API int b200ols_set_peer_flags(b200ols_ctx *ctx, int n_peers, void *const *peer_flags, int rank);
 B200OLS_API int b200ols_peer_step_complete(b200ols_ctx *ctx, uint64_t step);
+/* the two halves as separate kernels, for double-buffered gathers: signal step i right behind its kernels, wait for step
+ * i behind the kernels of step i + 1 (the peers' signals have arrived by then: the exchange leaves the critical path) */
+B200OLS_API int b200ols_peer_step_signal(b200ols_ctx *ctx, uint64_t step);
+B200OLS_API int b200ols_peer_step_wait(b200ols_ctx *ctx, uint64_t step);
 B200OLS_API int b200ols_peer_timed_out(b200ols_ctx *ctx);
 
 /* "next" row: replaces _polars_plugin_predict (src/expressions.rs:706-741).

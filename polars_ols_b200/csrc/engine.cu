@@ -218,11 +218,15 @@ struct PeerFlagParams {
     unsigned long long step;
     int *timeout_flag;
 };
-static __global__ void peer_step_complete_kernel(const PeerFlagParams p) {
+// what: bit 0 = signal (release `step` into every peer's slot [rank]), bit 1 = wait (acquire-spin on the own slots)
+static __global__ void peer_step_complete_kernel(const PeerFlagParams p, int what) {
     const int r = threadIdx.x;
     if (r >= p.n_peers) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer[r] + p.rank), "l"(p.step) : "memory");
+    if (what & 1) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer[r] + p.rank), "l"(p.step) : "memory");
+    }
+    if (!(what & 2)) return;
     const unsigned long long *mine = p.peer[p.rank] + r;
     const long long t0 = clock64();
     for (;;) {
@@ -251,7 +255,11 @@ extern "C" int b200ols_set_peer_flags(b200ols_ctx *c, int n_peers, void *const *
     return 0;
 }
 
-extern "C" int b200ols_peer_step_complete(b200ols_ctx *c, uint64_t step) {
+static int peer_step(b200ols_ctx *c, uint64_t step, int what);
+extern "C" int b200ols_peer_step_complete(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, 3); }
+extern "C" int b200ols_peer_step_signal(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, 1); }
+extern "C" int b200ols_peer_step_wait(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, 2); }
+static int peer_step(b200ols_ctx *c, uint64_t step, int what) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
     if (c->n_flag_peers <= 0) return fail(B200OLS_ERR_INVALID, "b200ols_set_peer_flags was not called");
     PeerFlagParams p;
@@ -261,7 +269,7 @@ extern "C" int b200ols_peer_step_complete(b200ols_ctx *c, uint64_t step) {
     p.rank = c->flag_rank;
     p.step = step;
     p.timeout_flag = c->flag_timeout;
-    peer_step_complete_kernel<<<1, 32, 0, c->stream>>>(p);
+    peer_step_complete_kernel<<<1, 32, 0, c->stream>>>(p, what);
     c->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -481,6 +481,16 @@ class Engine:
         if rc != 0:
             L.check(rc)
 
+    def peer_step_signal(self, step: int):
+        rc = self._lib.b200ols_peer_step_signal(self._ctx, step)
+        if rc != 0:
+            L.check(rc)
+
+    def peer_step_wait(self, step: int):
+        rc = self._lib.b200ols_peer_step_wait(self._ctx, step)
+        if rc != 0:
+            L.check(rc)
+
     def peer_timed_out(self) -> bool:
         return self._lib.b200ols_peer_timed_out(self._ctx) != 0
 

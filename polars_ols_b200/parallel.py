@@ -60,14 +60,16 @@ class PeerGather:
     (`b200ols_set_peer_gather`).  A rank may read its buffer after all ranks synchronised (stream sync +
     barrier), exactly as after a collective."""
 
-    def __init__(self, engine, total_groups: int, n_coef: int, group_base: int, group=None):
+    def __init__(self, engine, total_groups: int, n_coef: int, group_base: int, group=None, n_buffers: int = 1):
         import torch.distributed as dist
         self.engine, self.total_groups, self.n_coef, self.group_base = engine, total_groups, n_coef, group_base
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 8:
             raise ValueError("peer gather supports up to 8 ranks (one NVSwitch domain)")
         self.nbytes = total_groups * n_coef * 8
-        self.flag_off = (self.nbytes + 255) // 256 * 256          # 8 uint64 completion flags behind the coefficient rows
+        self.n_buffers = n_buffers                                  # > 1: gathers of consecutive steps alternate buffers
+        self.buf_stride = (self.nbytes + 255) // 256 * 256
+        self.flag_off = self.buf_stride * n_buffers                 # 8 uint64 completion flags behind the coefficient rows
         self.local = engine.device_alloc(self.flag_off + 64)
         engine.zero_device(self.local + self.flag_off, 64)
         self.step = 0
@@ -77,9 +79,21 @@ class PeerGather:
         dist.barrier(group)
         self.group = group
 
-    def attach(self):
-        self.engine.set_peer_gather(self.peers, self.group_base, self.total_groups)
-        self.engine.set_peer_flags([p + self.flag_off for p in self.peers], self.rank)
+    def attach(self, buffer: int = 0):
+        self.engine.set_peer_gather([p + buffer * self.buf_stride for p in self.peers], self.group_base, self.total_groups)
+        if not getattr(self, "_flags_set", False):
+            self.engine.set_peer_flags([p + self.flag_off for p in self.peers], self.rank)
+            self._flags_set = True
+
+    def step_signal(self):
+        """behind a step's kernels: tell every rank that this rank's rows of the step have been stored"""
+        self.step += 1
+        self.engine.peer_step_signal(self.step)
+        return self.step
+
+    def step_wait(self, step: int):
+        """behind later work: the stream continues only when EVERY rank has signalled `step` (its buffer is complete)"""
+        self.engine.peer_step_wait(step)
 
     def step_complete(self):
         """enqueue the per-step completion behind the step's kernels: when it retires, EVERY rank's rows of this step are
@@ -90,10 +104,11 @@ class PeerGather:
     def detach(self):
         self.engine.set_peer_gather([], 0, 0)
         self.engine.set_peer_flags([], 0)
+        self._flags_set = False
 
-    def read(self) -> np.ndarray:
+    def read(self, buffer: int = 0) -> np.ndarray:
         out = np.empty((self.total_groups, self.n_coef))
-        self.engine.copy_to_host(out, self.local)
+        self.engine.copy_to_host(out, self.local + buffer * self.buf_stride)
         return out
 
     def close(self):

@@ -827,7 +827,7 @@ def test_fused_predict_kernel(dtype, k, n_groups, model, kw, weights, intercept,
 def test_from_formula_matches_explicit_expressions():                      # tests/test_ols.py:362-371,437-449,456-470
     d = _make_data(4000, 4, n_groups=5, seed=31)
     F = Frame(d)
-    a = F.select(col("y").least_squares.from_formula("x1 + x2 - 1", mode="coefficients").over("group"))["coefficients"]
+    a = F.select(col("y").least_squares.from_formula("x1 + x2 -1", mode="coefficients").over("group"))["coefficients"]
     b = F.select(col("y").least_squares.ols("x1", "x2", mode="coefficients").over("group"))["coefficients"]
     np.testing.assert_array_equal(a.to_numpy(), b.to_numpy())
     # intercept + interaction term, against the oracle on the explicitly multiplied column
@@ -837,10 +837,10 @@ def test_from_formula_matches_explicit_expressions():                      # tes
                  kwargs=S.OLSKwargs())
     _close(got, _ref(ref), rtol=1e-6, atol=1e-8)
     # kwargs dispatch: window_size -> rolling, half_life -> rls
-    r1 = F.select(col("y").least_squares.from_formula("x1 + x2 - 1", window_size=50, mode="coefficients").over("group"))["coefficients"]
+    r1 = F.select(col("y").least_squares.from_formula("x1 + x2 -1", window_size=50, mode="coefficients").over("group"))["coefficients"]
     r2 = F.select(col("y").least_squares.rolling_ols("x1", "x2", window_size=50, mode="coefficients").over("group"))["coefficients"]
     np.testing.assert_array_equal(r1.to_numpy(), r2.to_numpy())
-    l1 = F.select(pls.compute_least_squares_from_formula("y ~ x1 + x2 - 1", half_life=20.0).over("group"))["y"]
+    l1 = F.select(pls.compute_least_squares_from_formula("y ~ x1 + x2 -1", half_life=20.0).over("group"))["y"]
     l2 = F.select(col("y").least_squares.rls("x1", "x2", half_life=20.0).over("group"))["y"]
     np.testing.assert_array_equal(l1.to_numpy(), l2.to_numpy())
     # predict_from_formula
