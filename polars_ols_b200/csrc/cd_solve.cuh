@@ -28,24 +28,58 @@ namespace b200 {
 // sweeps this one streams its rows.  Same arithmetic, in the same order, as predict_row / predict_kernel (predict.cuh).
 template <typename T, int WIDTH>
 __device__ __forceinline__ void cd_predict_group(const PredictParams &pp, int64_t g, const double (&b)[WIDTH], int sl) {
+    using Vec = typename PV<T>::type;
+    constexpr int VN = PV<T>::N;  // rows per lane and iteration: one 16-byte load per column
     const int kd = pp.kd;
     const int64_t r0 = pp.seg_off[g], r1 = pp.seg_off[g + 1];
-    for (int64_t r = r0 + sl; r < r1; r += WIDTH) {
+    double bi = 0.0;  // intercept coefficient
+#pragma unroll
+    for (int j = 0; j < WIDTH; ++j)
+        if (j == kd) bi = b[j];
+    auto one_row = [&](int64_t r) {
         T s = T(1);
         if (pp.has_w) s = predict_scale<T>(pp, static_cast<const T *>(pp.cols[kd])[r]);
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < WIDTH; ++j)
             if (j < kd) acc = fma(static_cast<double>(static_cast<T>(static_cast<const T *>(pp.cols[j])[r] * s)), b[j], acc);
-        if (pp.intercept) {
-            double bi = 0.0;
-#pragma unroll
-            for (int j = 0; j < WIDTH; ++j)
-                if (j == kd) bi = b[j];
-            acc = fma(static_cast<double>(s), bi, acc);
-        }
+        if (pp.intercept) acc = fma(static_cast<double>(s), bi, acc);
         predict_store<T>(pp, r, acc, s, g);
+    };
+    const int64_t a0 = (r0 + VN - 1) / VN * VN;                  // first 16-byte aligned row of the group
+    for (int64_t r = r0 + sl; r < a0 && r < r1; r += WIDTH) one_row(r);
+    int64_t r = a0 + static_cast<int64_t>(sl) * VN;
+    for (; r + VN <= r1; r += WIDTH * VN) {                      // WIDTH lanes x VN rows per iteration, all loads independent
+        T sv[VN];
+        double acc[VN];
+#pragma unroll
+        for (int v = 0; v < VN; ++v) { sv[v] = T(1); acc[v] = 0.0; }
+        if (pp.has_w) {
+            const Vec w4 = *reinterpret_cast<const Vec *>(static_cast<const T *>(pp.cols[kd]) + r);
+            const T *wp = reinterpret_cast<const T *>(&w4);
+#pragma unroll
+            for (int v = 0; v < VN; ++v) sv[v] = predict_scale<T>(pp, wp[v]);
+        }
+#pragma unroll
+        for (int j = 0; j < WIDTH; ++j) {
+            if (j < kd) {
+                const Vec x4 = *reinterpret_cast<const Vec *>(static_cast<const T *>(pp.cols[j]) + r);
+                const T *xp = reinterpret_cast<const T *>(&x4);
+#pragma unroll
+                for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(static_cast<T>(xp[v] * sv[v])), b[j], acc[v]);
+            }
+        }
+        if (pp.intercept) {
+#pragma unroll
+            for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(sv[v]), bi, acc[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < VN; ++v) predict_store<T>(pp, r + v, acc[v], sv[v], g);
     }
+    // rows after the last whole vector: lane `sl` of the tail iteration may hold a partial vector; the remaining rows
+    // [tail, r1) are fewer than WIDTH * VN
+    const int64_t nvec = (r1 > a0) ? (r1 - a0) / VN : 0;
+    for (int64_t t = a0 + nvec * VN + sl; t < r1; t += WIDTH) one_row(t);
 }
 
 struct NoPredict {};  // cd_solve_kernel<WIDTH, NPL, NoPredict>: coefficients only
