@@ -267,6 +267,20 @@ def _all_gather_object(obj, group=None):
     return out
 
 
+def _all_gather_array(arr: np.ndarray, group=None):
+    """the path's one exchange for a time-sharded rls: k*k + k + 1 doubles per rank.  One tensor all-gather (NCCL on the
+    GPU box, gloo in the CPU tests) instead of a pickled object collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    t = torch.as_tensor(a.reshape(-1), device=dev)
+    out = torch.empty(world * t.numel(), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return list(out.cpu().numpy().reshape((world,) + a.shape))
+
+
 def time_sharded(expr, frame, rank: int, world_size: int, engine=None, exchange=None, group=None):
     """Evaluate an rls / rolling_ols expression (no `.over()`) on this rank's time shard of one long series.
 
@@ -299,7 +313,7 @@ def time_sharded(expr, frame, rank: int, world_size: int, engine=None, exchange=
         zero = np.zeros((1, F * F + F))
         ckw, keep = expr.rls_c_kwargs(F, zero)
         local = engine.recursive_least_squares_state(sub, ckw, keep)[0]          # this shard's affine map
-        maps = np.stack((exchange or (lambda o: _all_gather_object(o, group)))(local))
+        maps = np.stack((exchange or (lambda o: _all_gather_array(o, group)))(local))
         info = None
         if rank > 0:
             # quirk A.5.1: the prior mean is honoured in coefficients mode only (src/expressions.rs:604-610 vs :636)

@@ -130,6 +130,10 @@ def _gloo_worker(rank, world, port, q):
     out = torch.empty((6, 2), dtype=torch.float64)
     full_eq = gather_group_results(loc, eq, out=out)
     assert full_eq.data_ptr() == out.data_ptr() and full_eq[:, 0].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    # the one exchange of a time-sharded rls: every rank's k*k + k + 1 state map, one tensor all-gather
+    from polars_ols_b200.parallel import _all_gather_array
+    maps = _all_gather_array(np.arange(7, dtype=np.float64) + 10 * rank)
+    assert len(maps) == world and all(np.array_equal(maps[r], np.arange(7) + 10.0 * r) for r in range(world))
     q.put((rank, full[:, 0].tolist()))
     dist.destroy_process_group()
 
