@@ -285,9 +285,7 @@ def main():
             # i - 1 (all ranks' rows of that step have landed here) is enqueued behind this step's kernel
             peer.attach(b)
             steps_fn[b]()
-            sig = peer.step_signal()
-            if sig > 1:
-                peer.step_wait(sig - 1)
+            peer.step_signal_wait_previous()     # one tiny kernel: release-signal step i, acquire-wait step i - 1
             return
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ev_gath[b])          # WAR: the gather issued two steps ago has consumed this buffer
@@ -432,9 +430,7 @@ def main():
             if speer is not None:
                 speer.attach(speer.step & 1)
                 sstep()
-                sig = speer.step_signal()
-                if sig > 1:
-                    speer.step_wait(sig - 1)
+                speer.step_signal_wait_previous()
             else:
                 sstep()
                 gather_group_results(scoef, sshards, out=sgath if all(b_ - a_ == sshards[0][1] - sshards[0][0] for a_, b_ in sshards) else None)
@@ -514,7 +510,7 @@ def main():
             "notes": ("" if world == 1 else
                       ("coefficient chunks gathered by P2P stores from the solver warps into every rank's buffer (NVLink peer memory, "
                        "fused into the kernel, two alternating buffers); every step signals a release flag to all ranks and the acquire-wait "
-                       "for step i - 1 is enqueued behind step i's kernel, INSIDE the timed loop (b200ols_peer_step_signal / _wait): the "
+                       "for step i - 1 rides in the same tiny kernel behind step i's kernel, INSIDE the timed loop (b200ols_peer_step_signal_wait): the "
                        "timed region ends only when every rank's rows of every step have landed everywhere"
                        if a.gather == "peer" else
                        "NCCL all-gather of coefficient chunks per step (side stream, overlapped with the next step's kernel)")),

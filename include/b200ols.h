@@ -293,6 +293,8 @@ B200OLS_API int b200ols_peer_step_complete(b200ols_ctx *ctx, uint64_t step);
  * i behind the kernels of step i + 1 (the peers' signals have arrived by then: the exchange leaves the critical path) */
 B200OLS_API int b200ols_peer_step_signal(b200ols_ctx *ctx, uint64_t step);
 B200OLS_API int b200ols_peer_step_wait(b200ols_ctx *ctx, uint64_t step);
+/* both in ONE launch: signal `signal_step`, then wait for `wait_step` (0 = nothing to wait for yet) */
+B200OLS_API int b200ols_peer_step_signal_wait(b200ols_ctx *ctx, uint64_t signal_step, uint64_t wait_step);
 B200OLS_API int b200ols_peer_timed_out(b200ols_ctx *ctx);
 
 /* "next" row: replaces _polars_plugin_predict (src/expressions.rs:706-741).

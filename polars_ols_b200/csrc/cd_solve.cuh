@@ -13,79 +13,14 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
-#include <cstring>
-#include <type_traits>
 
-#include "predict.cuh"
 #include "small_solve.cuh"
 #include "solvers.cuh"
 
 namespace b200 {
 
-// predictions / residuals of one group straight after its coordinate descent, by the sub-warp that solved it: the
-// coefficients never leave the registers, and the second streaming pass (predict_kernel: one more launch, one more
-// binary search per chunk, beta through L1) disappears — while other sub-warps are still in their latency-bound
-// sweeps this one streams its rows.  Same arithmetic, in the same order, as predict_row / predict_kernel (predict.cuh).
-template <typename T, int WIDTH>
-__device__ __forceinline__ void cd_predict_group(const PredictParams &pp, int64_t g, const double (&b)[WIDTH], int sl) {
-    using Vec = typename PV<T>::type;
-    constexpr int VN = PV<T>::N;  // rows per lane and iteration: one 16-byte load per column
-    const int kd = pp.kd;
-    const int64_t r0 = pp.seg_off[g], r1 = pp.seg_off[g + 1];
-    double bi = 0.0;  // intercept coefficient
-#pragma unroll
-    for (int j = 0; j < WIDTH; ++j)
-        if (j == kd) bi = b[j];
-    auto one_row = [&](int64_t r) {
-        T s = T(1);
-        if (pp.has_w) s = predict_scale<T>(pp, static_cast<const T *>(pp.cols[kd])[r]);
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < WIDTH; ++j)
-            if (j < kd) acc = fma(static_cast<double>(static_cast<T>(static_cast<const T *>(pp.cols[j])[r] * s)), b[j], acc);
-        if (pp.intercept) acc = fma(static_cast<double>(s), bi, acc);
-        predict_store<T>(pp, r, acc, s, g);
-    };
-    const int64_t a0 = (r0 + VN - 1) / VN * VN;                  // first 16-byte aligned row of the group
-    for (int64_t r = r0 + sl; r < a0 && r < r1; r += WIDTH) one_row(r);
-    int64_t r = a0 + static_cast<int64_t>(sl) * VN;
-    for (; r + VN <= r1; r += WIDTH * VN) {                      // WIDTH lanes x VN rows per iteration, all loads independent
-        T sv[VN];
-        double acc[VN];
-#pragma unroll
-        for (int v = 0; v < VN; ++v) { sv[v] = T(1); acc[v] = 0.0; }
-        if (pp.has_w) {
-            const Vec w4 = *reinterpret_cast<const Vec *>(static_cast<const T *>(pp.cols[kd]) + r);
-            const T *wp = reinterpret_cast<const T *>(&w4);
-#pragma unroll
-            for (int v = 0; v < VN; ++v) sv[v] = predict_scale<T>(pp, wp[v]);
-        }
-#pragma unroll
-        for (int j = 0; j < WIDTH; ++j) {
-            if (j < kd) {
-                const Vec x4 = *reinterpret_cast<const Vec *>(static_cast<const T *>(pp.cols[j]) + r);
-                const T *xp = reinterpret_cast<const T *>(&x4);
-#pragma unroll
-                for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(static_cast<T>(xp[v] * sv[v])), b[j], acc[v]);
-            }
-        }
-        if (pp.intercept) {
-#pragma unroll
-            for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(sv[v]), bi, acc[v]);
-        }
-#pragma unroll
-        for (int v = 0; v < VN; ++v) predict_store<T>(pp, r + v, acc[v], sv[v], g);
-    }
-    // rows after the last whole vector: lane `sl` of the tail iteration may hold a partial vector; the remaining rows
-    // [tail, r1) are fewer than WIDTH * VN
-    const int64_t nvec = (r1 > a0) ? (r1 - a0) / VN : 0;
-    for (int64_t t = a0 + nvec * VN + sl; t < r1; t += WIDTH) one_row(t);
-}
-
-struct NoPredict {};  // cd_solve_kernel<WIDTH, NPL, NoPredict>: coefficients only
-
-template <int WIDTH, int NPL, typename PT = NoPredict>
-__global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p, const PredictParams pp) {
+template <int WIDTH, int NPL>
+__global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
     extern __shared__ __align__(16) unsigned char cd_smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int F = p.F;
@@ -195,12 +130,6 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p, cons
                 if (mine) p.beta[g * F + sl] = (nfit == 0.0) ? 0.0 : w0;  // src/expressions.rs:357-359: no rows -> zeros
                 if (sl == 0) p.flags[g] = (nfit == 0.0) ? FLAG_EMPTY : 0;
             }
-            if constexpr (!std::is_same<PT, NoPredict>::value) {
-                double b[WIDTH];  // every lane of the sub-warp takes the whole coefficient vector
-#pragma unroll
-                for (int j = 0; j < WIDTH; ++j) b[j] = __shfl_sync(FULL, (nfit == 0.0) ? 0.0 : w0, j, WIDTH);
-                if (live) cd_predict_group<PT, WIDTH>(pp, g, b, sl);
-            }
         } else
         if (live) {
             if (nfit == 0.0) {  // src/expressions.rs:357-359: no rows -> zeros
@@ -264,10 +193,7 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p, cons
     }
 }
 
-// `pred` != nullptr (F <= 16, one segment per group): the kernel also writes the predictions / residuals of every group
-// (cd_predict_group); `f64` = dtype of the columns in *pred
-inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, int sm_count, const PredictParams *pred = nullptr,
-                                   bool f64 = true) {
+inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, int sm_count) {
     const int F = sp.F;
     int width, npl;
     if (F <= 8) { width = 8; npl = 1; }
@@ -284,22 +210,9 @@ inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, i
     const int64_t max_blocks = static_cast<int64_t>(sm_count) * std::max<int64_t>(1, std::min<int64_t>(16, (200 * 1024) / std::max<size_t>(smem, 1)));
     blocks = std::max<int64_t>(1, std::min(blocks, max_blocks));
     cudaError_t e = cudaSuccess;
-    PredictParams none;
-    std::memset(&none, 0, sizeof(none));
-#define B200_CD_LAUNCH_P(WD, PT)                                                                                          \
-    e = cudaFuncSetAttribute(cd_solve_kernel<WD, 1, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-    if (e == cudaSuccess) cd_solve_kernel<WD, 1, PT><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(sp, *pred);
-    if (pred && npl == 1 && width <= 16 && !sp.group_seg_off) {
-        if (width == 8) { if (f64) { B200_CD_LAUNCH_P(8, double) } else { B200_CD_LAUNCH_P(8, float) } }
-        else { if (f64) { B200_CD_LAUNCH_P(16, double) } else { B200_CD_LAUNCH_P(16, float) } }
-        if (e != cudaSuccess) return e;
-        return cudaGetLastError();
-    }
-#undef B200_CD_LAUNCH_P
-    if (pred) return cudaErrorInvalidValue;  // the caller checks cd_solve_can_predict first
 #define B200_CD_LAUNCH(WD, NP)                                                                                      \
     e = cudaFuncSetAttribute(cd_solve_kernel<WD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-    if (e == cudaSuccess) cd_solve_kernel<WD, NP><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(sp, none);
+    if (e == cudaSuccess) cd_solve_kernel<WD, NP><<<static_cast<unsigned>(blocks), warps * 32, smem, stream>>>(sp);
     if (width == 8) { B200_CD_LAUNCH(8, 1) }
     else if (width == 16) { B200_CD_LAUNCH(16, 1) }
     else if (npl == 1) { B200_CD_LAUNCH(32, 1) }
@@ -308,7 +221,5 @@ inline cudaError_t launch_cd_solve(cudaStream_t stream, const SolveParams &sp, i
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
-
-inline bool cd_solve_can_predict(int F, bool split) { return F <= 16 && !split; }
 
 }  // namespace b200

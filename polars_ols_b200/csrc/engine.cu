@@ -93,7 +93,6 @@ extern "C" int b200ols_create_on_stream(int device, void *cuda_stream, b200ols_c
     if (const char *v = std::getenv("B200OLS_MULTI")) c->multi_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_PRED")) c->pred_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_PRED_LAG")) c->pred_lag = std::max(1, std::atoi(v));
-    if (const char *v = std::getenv("B200OLS_CD_PRED")) c->cd_pred_enabled = std::atoi(v) != 0;
     if (const char *v = std::getenv("B200OLS_FUSE_MIN_BYTES")) c->fuse_min_bytes = std::atoll(v);  // test hook: fused-solve threshold
     if (c->variant != 1 && c->variant != 3) c->variant = 3;
     *out = c;
@@ -215,7 +214,8 @@ extern "C" int b200ols_set_peer_gather(b200ols_ctx *c, int n_peers, void *const 
 struct PeerFlagParams {
     unsigned long long *peer[8];
     int n_peers, rank;
-    unsigned long long step;
+    unsigned long long step;       // value to signal
+    unsigned long long wait_step;  // value to wait for (may trail `step`: double-buffered gathers)
     int *timeout_flag;
 };
 // what: bit 0 = signal (release `step` into every peer's slot [rank]), bit 1 = wait (acquire-spin on the own slots)
@@ -232,7 +232,7 @@ static __global__ void peer_step_complete_kernel(const PeerFlagParams p, int wha
     for (;;) {
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-        if (v >= p.step) break;
+        if (v >= p.wait_step) break;
         if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died; do not hang the device
             *p.timeout_flag = 1;
             break;
@@ -255,11 +255,14 @@ extern "C" int b200ols_set_peer_flags(b200ols_ctx *c, int n_peers, void *const *
     return 0;
 }
 
-static int peer_step(b200ols_ctx *c, uint64_t step, int what);
-extern "C" int b200ols_peer_step_complete(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, 3); }
-extern "C" int b200ols_peer_step_signal(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, 1); }
-extern "C" int b200ols_peer_step_wait(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, 2); }
-static int peer_step(b200ols_ctx *c, uint64_t step, int what) {
+static int peer_step(b200ols_ctx *c, uint64_t step, uint64_t wait_step, int what);
+extern "C" int b200ols_peer_step_complete(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, step, 3); }
+extern "C" int b200ols_peer_step_signal(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, step, 1); }
+extern "C" int b200ols_peer_step_wait(b200ols_ctx *c, uint64_t step) { return peer_step(c, step, step, 2); }
+extern "C" int b200ols_peer_step_signal_wait(b200ols_ctx *c, uint64_t signal_step, uint64_t wait_step) {
+    return peer_step(c, signal_step, wait_step, wait_step > 0 ? 3 : 1);
+}
+static int peer_step(b200ols_ctx *c, uint64_t step, uint64_t wait_step, int what) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
     if (c->n_flag_peers <= 0) return fail(B200OLS_ERR_INVALID, "b200ols_set_peer_flags was not called");
     PeerFlagParams p;
@@ -268,6 +271,7 @@ static int peer_step(b200ols_ctx *c, uint64_t step, int what) {
     p.n_peers = c->n_flag_peers;
     p.rank = c->flag_rank;
     p.step = step;
+    p.wait_step = wait_step;
     p.timeout_flag = c->flag_timeout;
     peer_step_complete_kernel<<<1, 32, 0, c->stream>>>(p, what);
     c->launches++;
@@ -1317,7 +1321,6 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         if (f->dtype == B200OLS_F64) TRY(launch_gram<double>(c, gp)); else TRY(launch_gram<float>(c, gp));
     }
 
-    bool cd_predicted = false;
     auto make_predict_params = [&]() {
         PredictParams pr;
         std::memset(&pr, 0, sizeof(pr));
@@ -1361,14 +1364,10 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         sp.max_iter = rt.max_iter;
         sp.positive = rt.positive;
         if (cd) {
-            // predictions / residuals straight from the sub-warp that ran the coordinate descent (cd_solve.cuh): no second pass
-            cd_predicted = mode != B200OLS_COEFFICIENTS && !stats && !peer_mode && c->cd_pred_enabled && cd_solve_can_predict(F, pl.split);
-            if (cd_predicted) {
-                PredictParams prc = make_predict_params();
-                CU(launch_cd_solve(c->stream, sp, c->sm_count, &prc, f->dtype == B200OLS_F64));
-            } else {
-                CU(launch_cd_solve(c->stream, sp, c->sm_count));
-            }
+            // (Round 2 tried to write the predictions from the sub-warp that ran the coordinate descent — no predict pass,
+            // coefficients never leave the registers.  Bit-identical, but slower on C3: 1.82 ms with scalar loads, 1.52 ms
+            // with 16-byte loads against 1.31 ms for CD + predict_kernel; profiles/r02_c3_experiments.json.  Removed.)
+            CU(launch_cd_solve(c->stream, sp, c->sm_count));
         } else if (F <= 16) {
             CU(launch_batch_solve(c->stream, sp));
         } else {
@@ -1495,7 +1494,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         pr.flags = flags;
         pr.only_flags = FLAG_QR | FLAG_SVD;
     }
-    if ((!pred_fused || rt.ols_qr_guard || rt.svd_wide) && !cd_predicted) {
+    if (!pred_fused || rt.ols_qr_guard || rt.svd_wide) {
         const int64_t warps_needed = (N + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
         const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
         if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);

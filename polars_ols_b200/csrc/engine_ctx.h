@@ -53,7 +53,6 @@ struct b200ols_ctx {
     int tile_rows = 0, warps_per_cta = 0, ctas_per_sm = 0;
     bool multi_enabled = true;      // test hook B200OLS_MULTI=0: never use gram_multi_kernel
     int pred_lag = 4;               // test hook B200OLS_PRED_LAG: groups the stream may run ahead of the predictions (per SM)
-    bool cd_pred_enabled = true;    // test hook B200OLS_CD_PRED=0: elastic-net predictions by a separate predict_kernel pass
     bool pred_enabled = true;       // test hook B200OLS_PRED=0: never use the fused Gram -> solve -> predict kernel
     long long fuse_min_bytes = -1;  // < 0: default; test hook B200OLS_FUSE_MIN_BYTES (0 = always fuse the solve)
     int variant = 3, unroll = 0;  // Gram kernel variant (b200ols_set_variant); 3 = CTA-cooperative TMA pipeline

@@ -91,6 +91,12 @@ class PeerGather:
         self.engine.peer_step_signal(self.step)
         return self.step
 
+    def step_signal_wait_previous(self):
+        """one launch behind a step's kernels: signal this step, wait until every rank has signalled the PREVIOUS one"""
+        self.step += 1
+        self.engine.peer_step_signal_wait(self.step, self.step - 1)
+        return self.step
+
     def step_wait(self, step: int):
         """behind later work: the stream continues only when EVERY rank has signalled `step` (its buffer is complete)"""
         self.engine.peer_step_wait(step)
