@@ -45,11 +45,12 @@ def test_c3_full_size_wls_elastic_net_predictions():
     pred = eng.least_squares(b, kw, L.PREDICTIONS, want_validity=False)[0]
     coef = eng.least_squares(b, kw, L.COEFFICIENTS)[0]
     assert bool(torch.isfinite(pred).all()) and bool(torch.isfinite(coef).all())
-    # property over ALL groups: predictions == X beta with the coefficients of the coefficients-mode call (f32 inputs, f64 math)
+    # property over ALL groups: predictions == X beta with the coefficients of the coefficients-mode call.  The engine (as the
+    # reference's polars expressions) rounds x * sqrt(w) to f32 before the f64 dot product, this check does not: 1e-6 relative
     chk = torch.zeros(G * per, dtype=torch.float64, device=dev)
     for j in range(k):
         chk += x[j].to(torch.float64) * coef[:, j].repeat_interleave(per)
-    assert float((chk - pred).abs().max()) < 1e-9 * float(pred.abs().max() + 1)
+    assert float((chk - pred).abs().max()) < 1e-6 * float(pred.abs().max() + 1)
     for g in (0, 1, G // 3, G // 2, G - 2, G - 1):                      # sample against the oracle (f32 tolerance 1e-4)
         sl = slice(g * per, (g + 1) * per)
         ref = S.least_squares(y[sl].cpu().numpy(), *[x[i, sl].cpu().numpy() for i in range(k)], sample_weights=w[sl].cpu().numpy(),
