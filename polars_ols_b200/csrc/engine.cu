@@ -1943,7 +1943,7 @@ extern "C" int b200ols_predict(b200ols_ctx *c, int64_t n_rows, int32_t n_coef, i
 // ------------------------------------------------------------------------------------------------
 // moving-window models: rls / rolling (moving.cuh)
 // ------------------------------------------------------------------------------------------------
-int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets, bool f64, int sm_count, char *ws,
+int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets, bool f64, int sm_count, char *ws, size_t ws_bytes,
                          int64_t *launches) {
     const int64_t G = p.n_groups;
     // three execution paths (moving.cuh): k <= 8 null-free frames stream through per-thread staging rings
@@ -2036,7 +2036,7 @@ int b200::launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *off
     p.sup_c0 = d_s0;
     p.sup_c1 = d_s1;
     p.group_sup_off = d_gso;
-    if (off > moving_workspace_bytes(p.n_rows, G, p.F)) return fail(B200OLS_ERR_CUDA, "internal: moving workspace under-sized");
+    if (off > ws_bytes) return fail(B200OLS_ERR_CUDA, "internal: moving workspace under-sized (%zu > %zu)", off, ws_bytes);
     // pageable -> device async copies are staged by the driver before the call returns
     if (nc) {
         CU(cudaMemcpyAsync(d_r0, r0.data(), nc * 8, cudaMemcpyHostToDevice, stream));
@@ -2093,7 +2093,14 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
         mp.fixed_window = !(policy == B200OLS_NULL_DROP || policy == B200OLS_NULL_DROP_ZERO || policy == B200OLS_NULL_DROP_Y_ZERO_X);  // :947-950
     }
 
-    size_t bytes = stage_bytes_bound(f) + (static_cast<size_t>(G) + 8) * 64 + moving_workspace_bytes(N, G, F) + (1 << 20);
+    // the chunk-interleaved copies (2 x the frame) are only reserved when this call can take the kernels that read them
+    bool any_bitmap = f->target.validity != nullptr || (f->sample_weights && f->sample_weights->validity);
+    for (int j = 0; j < f->n_features; ++j) any_bitmap = any_bitmap || f->features[j].validity != nullptr;
+    const bool may_mask = any_bitmap && policy != B200OLS_NULL_ZERO && policy != B200OLS_NULL_IGNORE;
+    const bool fast_off = [] { const char *v = std::getenv("B200OLS_MOVING_FAST"); return v && std::atoi(v) == 0; }();
+    const bool transposed = F <= 8 && (may_mask || fast_off || (kind == MOVING_ROLLING && mp.min_periods > mp.window));
+    const size_t ws_bytes = moving_workspace_bytes(N, G, F, transposed);
+    size_t bytes = stage_bytes_bound(f) + (static_cast<size_t>(G) + 8) * 64 + ws_bytes + (1 << 20);
     if (f->memspace == B200OLS_HOST) bytes += static_cast<size_t>(N) * (static_cast<size_t>(F) * 9 + 16) + 4096;
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
@@ -2153,11 +2160,11 @@ static int run_moving_impl(b200ols_ctx *c, const b200ols_frame *f, int kind, con
     }
     mp.out = dout;
     mp.out_valid = dval;
-    char *ws = arena_alloc<char>(c, moving_workspace_bytes(N, G, F));
+    char *ws = arena_alloc<char>(c, ws_bytes);
     ARENA_GUARD(c);
     {
         ProfScope prof(c);
-        TRY(launch_moving(c->stream, mp, st.offsets.data(), f->dtype == B200OLS_F64, c->sm_count, ws, &c->launches));
+        TRY(launch_moving(c->stream, mp, st.offsets.data(), f->dtype == B200OLS_F64, c->sm_count, ws, ws_bytes, &c->launches));
     }
     if (state_host) {
         // state leaving each series: dense [A (F x F, symmetric), b (F), D]

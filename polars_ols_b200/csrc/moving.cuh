@@ -441,13 +441,16 @@ inline int64_t moving_chunk_len(int64_t n_rows, int sm_count, int kind, int64_t 
     return L;
 }
 
-inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int F) {
+// `transposed`: the call may take the round-1 kernels that read chunk-interleaved column copies (k <= 8 with a row mask or
+// min_periods > window); the staged and block-per-chunk kernels read the caller's columns in place
+inline size_t moving_workspace_bytes(int64_t n_rows, int64_t n_groups, int F, bool transposed = true) {
     const size_t max_chunks = static_cast<size_t>(n_rows / 64 + n_groups + 2);
     const size_t max_super = max_chunks / 256 + static_cast<size_t>(n_groups) + 2;
-    return max_chunks * (moving_rec(F) * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (3 * 8 + 8 + 8) +
-           max_super * (moving_rec(F) * 8 + 16) + 16384 +
-           // chunk-interleaved column copies: (F + 3) columns x padded rows (every series pads < one chunk)
-           static_cast<size_t>(F + 3) * (static_cast<size_t>(n_rows) * 2 + static_cast<size_t>(n_groups + 1) * 64 + 4096) * 8;
+    size_t b = max_chunks * (moving_rec(F) * 8 + 8 + 8 + 4) + static_cast<size_t>(n_groups + 2) * (4 * 8 + 8 + 8) +
+               max_super * (moving_rec(F) * 8 + 16) + 16384;
+    // chunk-interleaved column copies: (F + 3) columns x padded rows (every series pads < one chunk)
+    if (transposed) b += static_cast<size_t>(F + 3) * (static_cast<size_t>(n_rows) * 2 + static_cast<size_t>(n_groups + 1) * 64 + 4096) * 8;
+    return b;
 }
 
 // thread-per-chunk kernels for 1..8 coefficients (moving_f{64,32}_r0.cu); 9..MOVING_WIDE_MAX_K coefficients run the
@@ -463,7 +466,7 @@ cudaError_t moving_launch_f64(cudaStream_t s, MovingParams &p, const int64_t *gc
 cudaError_t moving_launch_f32(cudaStream_t s, MovingParams &p, const int64_t *gco, int64_t *launches);
 
 // builds the chunk table on the host (group offsets are host metadata), uploads it into `ws` and launches
-int launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets_host, bool f64, int sm_count, char *ws,
+int launch_moving(cudaStream_t stream, MovingParams &p, const int64_t *offsets_host, bool f64, int sm_count, char *ws, size_t ws_bytes,
                   int64_t *launches);
 
 }  // namespace b200
