@@ -284,8 +284,8 @@ def main():
             # double-buffered fused gather: step i stores into buffer i & 1 of every rank and signals; the wait for step
             # i - 1 (all ranks' rows of that step have landed here) is enqueued behind this step's kernel
             peer.attach(b)
+            peer.arm_step()      # the kernel's last solver warp release-signals step i and acquire-waits step i - 1
             steps_fn[b]()
-            peer.step_signal_wait_previous()     # one tiny kernel: release-signal step i, acquire-wait step i - 1
             return
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ev_gath[b])          # WAR: the gather issued two steps ago has consumed this buffer
@@ -429,8 +429,8 @@ def main():
         def strong_step():
             if speer is not None:
                 speer.attach(speer.step & 1)
+                speer.arm_step()
                 sstep()
-                speer.step_signal_wait_previous()
             else:
                 sstep()
                 gather_group_results(scoef, sshards, out=sgath if all(b_ - a_ == sshards[0][1] - sshards[0][0] for a_, b_ in sshards) else None)
@@ -510,7 +510,7 @@ def main():
             "notes": ("" if world == 1 else
                       ("coefficient chunks gathered by P2P stores from the solver warps into every rank's buffer (NVLink peer memory, "
                        "fused into the kernel, two alternating buffers); every step signals a release flag to all ranks and the acquire-wait "
-                       "for step i - 1 rides in the same tiny kernel behind step i's kernel, INSIDE the timed loop (b200ols_peer_step_signal_wait): the "
+                       "for step i - 1 are done by the Gram kernel's last solver warp itself, INSIDE the timed loop (b200ols_peer_arm_step): the "
                        "timed region ends only when every rank's rows of every step have landed everywhere"
                        if a.gather == "peer" else
                        "NCCL all-gather of coefficient chunks per step (side stream, overlapped with the next step's kernel)")),

@@ -295,6 +295,10 @@ B200OLS_API int b200ols_peer_step_signal(b200ols_ctx *ctx, uint64_t step);
 B200OLS_API int b200ols_peer_step_wait(b200ols_ctx *ctx, uint64_t step);
 /* both in ONE launch: signal `signal_step`, then wait for `wait_step` (0 = nothing to wait for yet) */
 B200OLS_API int b200ols_peer_step_signal_wait(b200ols_ctx *ctx, uint64_t signal_step, uint64_t wait_step);
+/* no launch at all: arm the completion for the NEXT b200ols_least_squares_coefficients call; when that call runs the fused
+ * peer-gather kernel, the kernel's last solver warp signals `signal_step` and waits for `wait_step` itself (any other route:
+ * the engine enqueues the flag kernel behind the call) */
+B200OLS_API int b200ols_peer_arm_step(b200ols_ctx *ctx, uint64_t signal_step, uint64_t wait_step);
 B200OLS_API int b200ols_peer_timed_out(b200ols_ctx *ctx);
 
 /* "next" row: replaces _polars_plugin_predict (src/expressions.rs:706-741).

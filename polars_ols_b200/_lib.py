@@ -34,7 +34,7 @@ EXPORTS = [
     "b200ols_ipc_open", "b200ols_ipc_close", "b200ols_copy_to_host", "b200ols_set_peer_gather",
     "b200ols_recursive_least_squares_state", "b200ols_least_squares_statistics", "b200ols_multi_target_least_squares",
     "b200ols_group_plan_build", "b200ols_group_plan_row_index", "b200ols_group_plan_group_of_row",
-    "b200ols_device_memset", "b200ols_set_peer_flags", "b200ols_peer_step_complete", "b200ols_peer_step_signal", "b200ols_peer_step_wait", "b200ols_peer_step_signal_wait", "b200ols_peer_timed_out",
+    "b200ols_device_memset", "b200ols_set_peer_flags", "b200ols_peer_step_complete", "b200ols_peer_step_signal", "b200ols_peer_step_wait", "b200ols_peer_step_signal_wait", "b200ols_peer_arm_step", "b200ols_peer_timed_out",
 ]
 
 
@@ -158,6 +158,7 @@ def load() -> C.CDLL:
     L.b200ols_peer_step_signal.argtypes = [vp, C.c_uint64]
     L.b200ols_peer_step_wait.argtypes = [vp, C.c_uint64]
     L.b200ols_peer_step_signal_wait.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.b200ols_peer_arm_step.argtypes = [vp, C.c_uint64, C.c_uint64]
     L.b200ols_peer_timed_out.argtypes = [vp]
     L.b200ols_group_plan_build.argtypes = [vp, C.POINTER(KeyColumn), i32, i64, i32, C.POINTER(GroupPlan)]
     L.b200ols_group_plan_row_index.argtypes = [vp, vp, i32]

@@ -111,6 +111,7 @@ extern "C" void b200ols_destroy(b200ols_ctx *c) {
     if (c->tile_dev) cudaFree(c->tile_dev);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->flag_timeout) cudaFree(c->flag_timeout);
+    if (c->done_counter) cudaFree(c->done_counter);
     stager_destroy(c->stager);
     group_plan_destroy(c->gplan);
     for (int h = 0; h < 2; ++h)
@@ -251,7 +252,22 @@ extern "C" int b200ols_set_peer_flags(b200ols_ctx *c, int n_peers, void *const *
     if (n_peers > 0 && !c->flag_timeout) {
         CU(cudaMalloc(reinterpret_cast<void **>(&c->flag_timeout), sizeof(int)));
         CU(cudaMemsetAsync(c->flag_timeout, 0, sizeof(int), c->stream));
+        CU(cudaMalloc(reinterpret_cast<void **>(&c->done_counter), sizeof(unsigned int)));
+        CU(cudaMemsetAsync(c->done_counter, 0, sizeof(unsigned int), c->stream));
     }
+    c->armed_signal = 0;
+    return 0;
+}
+
+// Arms the in-kernel completion for the NEXT b200ols_least_squares_coefficients call on this context: when that call takes
+// the fused peer-gather kernel, its last solver warp signals `signal_step` and waits for `wait_step` (no extra launch);
+// on any other route the engine enqueues the equivalent flag kernel behind the call's kernels.
+extern "C" int b200ols_peer_arm_step(b200ols_ctx *c, uint64_t signal_step, uint64_t wait_step) {
+    if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
+    if (c->n_flag_peers <= 0) return fail(B200OLS_ERR_INVALID, "b200ols_set_peer_flags was not called");
+    if (signal_step == 0) return fail(B200OLS_ERR_INVALID, "signal_step must be >= 1");
+    c->armed_signal = signal_step;
+    c->armed_wait = wait_step;
     return 0;
 }
 
@@ -1278,6 +1294,20 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         for (int r = 0; r < c->n_peers; ++r) gp.peer_beta[r] = c->peer_coef[r];
         gp.peer_group_base = c->peer_group_base;
     }
+    // per-step completion armed by b200ols_peer_arm_step: inside the fused-gather kernel when that is what runs
+    const unsigned long long arm_signal = peer_mode ? c->armed_signal : 0, arm_wait = c->armed_wait;
+    if (peer_mode) c->armed_signal = 0;
+    bool arm_in_kernel = false;
+    if (arm_signal && peer_direct && c->variant == 3 && F <= 16 && mode == B200OLS_COEFFICIENTS) {
+        arm_in_kernel = true;
+        gp.flag_n = c->n_flag_peers;
+        gp.flag_rank = c->flag_rank;
+        for (int r = 0; r < c->n_flag_peers; ++r) gp.flag_peer[r] = c->peer_flags[r];
+        gp.flag_step = arm_signal;
+        gp.flag_wait = arm_wait;
+        gp.done_counter = c->done_counter;
+        gp.flag_timeout = c->flag_timeout;
+    }
 
     // mode = predictions | residuals with whole groups per tile: ONE kernel (gram_pred.cuh) keeps the tile in shared
     // memory until beta is known and predicts from it, so the features are read from HBM once instead of twice
@@ -1471,6 +1501,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
         c->launches++;
         CU(cudaGetLastError());
     }
+    if (arm_signal && !arm_in_kernel) TRY(peer_step(c, arm_signal, arm_wait, arm_wait > 0 ? 3 : 1));
     if (peer_mode && !out->values) return 0;
     if (mode == B200OLS_COEFFICIENTS) {
         const size_t ob = static_cast<size_t>(G) * F * sizeof(double);

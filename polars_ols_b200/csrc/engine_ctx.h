@@ -91,6 +91,8 @@ struct b200ols_ctx {
     int n_flag_peers = 0, flag_rank = 0;
     unsigned long long *peer_flags[8] = {};
     int *flag_timeout = nullptr;  // device: set when a spin gave up
+    unsigned int *done_counter = nullptr;              // device: arrival count of the in-kernel completion
+    unsigned long long armed_signal = 0, armed_wait = 0;  // b200ols_peer_arm_step: consumed by the next fused-gather launch
     // optional device-side timing of the dominant kernel
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;

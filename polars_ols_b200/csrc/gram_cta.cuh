@@ -332,6 +332,33 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) gram_cta_kernel(const GramPara
             if (plain) nfit = (lane == 0) ? static_cast<int>(p.seg_off[seg + 1] - p.seg_off[seg]) : 0;
             gram_epilogue<KB>(p, acc, cy, nfit, seg, Gs, lane);
         }
+        if (p.flag_n > 0) {
+            // per-step completion of the fused gather without a second launch: every solver warp orders its peer stores
+            // before a device-wide arrival count; the warp that arrives last knows every beta of this launch has been
+            // stored into every peer, so it publishes the step (release) and waits for the peers' previous step (acquire)
+            __threadfence_system();
+            unsigned int old = 0;
+            if (lane == 0) old = atomicAdd(p.done_counter, 1u);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == gridDim.x * CTA_SOLVERS - 1) {
+                if (lane == 0) *p.done_counter = 0;  // re-arm for the next launch on this stream
+                __threadfence_system();
+                if (lane < p.flag_n) {
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.flag_peer[lane] + p.flag_rank), "l"(p.flag_step) : "memory");
+                    const unsigned long long *mine = p.flag_peer[p.flag_rank] + lane;
+                    const long long t0 = clock64();
+                    for (;;) {
+                        unsigned long long v;
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+                        if (v >= p.flag_wait) break;
+                        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer died; do not hang the device
+                            *p.flag_timeout = 1;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
     }
 }
 

@@ -52,6 +52,14 @@ struct GramParams {
     int n_peers;
     double *peer_beta[8];             // [total_groups][F] on rank r
     int64_t peer_group_base;          // first global group index of this rank's shard
+    // in-kernel completion of the fused gather (gram_cta_kernel): the LAST solver warp of the grid release-stores
+    // `flag_step` into slot [flag_rank] of every peer's flag array and acquire-spins until its own slots reached `flag_wait`
+    int flag_n;                       // 0 = off
+    int flag_rank;
+    unsigned long long *flag_peer[8];
+    unsigned long long flag_step, flag_wait;
+    unsigned int *done_counter;       // device: solver warps that finished (re-armed by the last one)
+    int *flag_timeout;
 };
 
 template <typename T> struct V2;

@@ -491,6 +491,11 @@ class Engine:
         if rc != 0:
             L.check(rc)
 
+    def peer_arm_step(self, signal_step: int, wait_step: int):
+        rc = self._lib.b200ols_peer_arm_step(self._ctx, signal_step, wait_step)
+        if rc != 0:
+            L.check(rc)
+
     def peer_step_wait(self, step: int):
         rc = self._lib.b200ols_peer_step_wait(self._ctx, step)
         if rc != 0:

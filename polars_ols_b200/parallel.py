@@ -97,6 +97,13 @@ class PeerGather:
         self.engine.peer_step_signal_wait(self.step, self.step - 1)
         return self.step
 
+    def arm_step(self):
+        """BEFORE a step's coefficient call: the fused-gather kernel itself signals this step and waits for the previous one
+        (its last solver warp; no extra launch)"""
+        self.step += 1
+        self.engine.peer_arm_step(self.step, self.step - 1)
+        return self.step
+
     def step_wait(self, step: int):
         """behind later work: the stream continues only when EVERY rank has signalled `step` (its buffer is complete)"""
         self.engine.peer_step_wait(step)
