@@ -65,8 +65,10 @@ __global__ void __launch_bounds__(128) cd_solve_kernel(const SolveParams p) {
             const int l = sl + WIDTH * t;
             gd[t] = (l < F) ? Gs[l * F + l] : 1.0;
         }
-        const double a = p.alpha * nfit;  // alpha *= n_samples (src/least_squares.rs:419)
-        const double l1 = a * p.l1_ratio, l2 = a * (1.0 - p.l1_ratio);
+        // alpha *= n_samples (src/least_squares.rs:419); products rounded on their own (no contraction into the
+        // subtraction / addition that follows), as the reference computes alpha * l1_ratio and alpha * (1 - l1_ratio)
+        const double a = __dmul_rn(p.alpha, nfit);
+        const double l1 = __dmul_rn(a, p.l1_ratio), l2 = __dmul_rn(a, 1.0 - p.l1_ratio);
         // 1 / (|x_j|^2 + a (1 - l1)) once per coordinate: the per-update division of the reference (:431) becomes
         // a multiplication (f64 division is a ~20-instruction sequence and this loop is instruction bound)
 #pragma unroll

@@ -33,6 +33,7 @@
 #include "big.cuh"
 #include "batch_solve.cuh"
 #include "cd_solve.cuh"
+#include "cd_thread.h"
 #include "stats.cuh"
 #include "multi_target.cuh"
 
@@ -1397,7 +1398,15 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
             // (Round 2 tried to write the predictions from the sub-warp that ran the coordinate descent — no predict pass,
             // coefficients never leave the registers.  Bit-identical, but slower on C3: 1.82 ms with scalar loads, 1.52 ms
             // with 16-byte loads against 1.31 ms for CD + predict_kernel; profiles/r02_c3_experiments.json.  Removed.)
-            CU(launch_cd_solve(c->stream, sp, c->sm_count));
+            // k <= 16 and many groups: one thread per group (cd_thread.cu) instead of one sub-warp per group — same
+            // arithmetic in the same order, ~2x fewer issue slots per coordinate step for 16x the groups per warp.
+            // (Round 2 also cut the groups into chunks and ran predict(chunk i) on a second stream under cd(chunk i + 1):
+            // 1.30 -> 1.19 ms on C3 with the sub-warp kernel, nothing with this one (0.98 ms either way), so it was
+            // removed; profiles/r02_c3_experiments.json.)
+            if (const char *v = std::getenv("B200OLS_CD_THREAD")) c->cd_thread = std::atoi(v);  // test hooks, read per call
+            if (const char *v = std::getenv("B200OLS_CD_THREAD_BLOCKS")) c->cd_thread_blocks = std::atoi(v);
+            if (c->cd_thread != 0 && F <= 16 && G >= (c->cd_thread > 1 ? 1 : 1024)) CU(launch_cd_thread(c->stream, sp, c->sm_count, c->cd_thread_blocks));
+            else CU(launch_cd_solve(c->stream, sp, c->sm_count));
         } else if (F <= 16) {
             CU(launch_batch_solve(c->stream, sp));
         } else {

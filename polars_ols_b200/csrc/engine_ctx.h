@@ -93,6 +93,9 @@ struct b200ols_ctx {
     int *flag_timeout = nullptr;  // device: set when a spin gave up
     unsigned int *done_counter = nullptr;              // device: arrival count of the in-kernel completion
     unsigned long long armed_signal = 0, armed_wait = 0;  // b200ols_peer_arm_step: consumed by the next fused-gather launch
+    // coordinate-descent kernel choice (run_static_impl)
+    int cd_thread = 1;                 // B200OLS_CD_THREAD: 0 = sub-warp kernel only, 1 = thread-per-group kernel from 1024 groups, 2 = always (k <= 16)
+    int cd_thread_blocks = 0;          // B200OLS_CD_THREAD_BLOCKS: resident warps per SM of cd_thread_kernel (0 = what fits)
     // optional device-side timing of the dominant kernel
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;

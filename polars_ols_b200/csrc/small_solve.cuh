@@ -8,25 +8,10 @@
 #pragma once
 #include <cstdint>
 
+#include "solve_params.h"
 #include "solvers.cuh"
 
 namespace b200 {
-
-enum : int { ROUTE_CHOL = 0, ROUTE_LU = 1, ROUTE_CD = 2, ROUTE_CD_ACTIVE = 3, ROUTE_FLAGS_ONLY = 4 /* big.cuh: an SVD kernel solves */ };
-
-struct SolveParams {
-    int F;
-    int64_t n_groups;
-    const double *partial;         // [nseg][F*F + F + 1]
-    const int64_t *group_seg_off;  // [n_groups+1] or nullptr (one segment per group)
-    double *work;                  // [n_groups][F*F + 4F]
-    double *beta;                  // [n_groups][F]
-    int32_t *flags;                // [n_groups]
-    int route;
-    double alpha, l1_ratio, tol, illcond_ratio;
-    int64_t max_iter;
-    int positive;
-};
 
 __global__ void __launch_bounds__(128) small_solve_kernel(const SolveParams p) {
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
