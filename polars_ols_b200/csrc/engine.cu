@@ -1206,6 +1206,11 @@ static int run_statistics(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
 
 // `stats` != nullptr: mode = "statistics" (b200ols_least_squares_statistics) — the coefficients are dispatched as
 // for mode = coefficients, the Gram records are always written (no fused solve) and run_statistics() finishes
+static void launch_predict(b200ols_ctx *c, const PredictParams &pr, bool f64, unsigned blocks) {
+    if (f64) predict_kernel<double><<<blocks, 256, 0, c->stream>>>(pr);
+    else predict_kernel<float><<<blocks, 256, 0, c->stream>>>(pr);
+}
+
 static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, int mode, b200ols_output *out,
                            const b200ols_statistics_output *stats = nullptr) {
     if (!c) return fail(B200OLS_ERR_INVALID, "ctx is NULL");
@@ -1537,8 +1542,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     if (!pred_fused || rt.ols_qr_guard || rt.svd_wide) {
         const int64_t warps_needed = (N + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
         const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
-        if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
-        else predict_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
+        launch_predict(c, pr, f->dtype == B200OLS_F64, static_cast<unsigned>(blocks));
         c->launches++;
         CU(cudaGetLastError());
     }
@@ -1839,8 +1843,7 @@ static int run_multi_target_impl(b200ols_ctx *c, const b200ols_frame *f0, int32_
         pr.out_valid = dval ? dval + static_cast<size_t>(t) * N : nullptr;
         const int64_t warps_needed = (N + PREDICT_CHUNK - 1) / PREDICT_CHUNK;
         const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(c->sm_count) * 8));
-        if (f->dtype == B200OLS_F64) predict_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
-        else predict_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, c->stream>>>(pr);
+        launch_predict(c, pr, f->dtype == B200OLS_F64, static_cast<unsigned>(blocks));
         c->launches++;
         CU(cudaGetLastError());
     }

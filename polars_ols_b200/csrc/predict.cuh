@@ -79,8 +79,13 @@ __device__ __forceinline__ void predict_row(const PredictParams &p, int64_t r, c
     predict_store<T>(p, r, acc, s, group);
 }
 
+// PREDICT_COLS feature columns have their 16-byte loads issued together before any arithmetic; 4 columns at 64 registers
+// (4 blocks per SM) measured best on C3: 2 / 3 / 6 / 8 / 16 columns, 48 / 80 registers and a double-buffered variant were
+// all slower (profiles/r02_c3_experiments.json)
+constexpr int PREDICT_COLS = 4;
 template <typename T>
-__global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
+__global__ void __launch_bounds__(256, 4) predict_kernel(const PredictParams p) {
+    constexpr int U = PREDICT_COLS;
     using Vec = typename PV<T>::type;
     constexpr int VN = PV<T>::N;  // rows per lane and iteration: one 16-byte load per column
     const int lane = threadIdx.x & 31;
@@ -123,13 +128,26 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredictParams p) {
 #pragma unroll
                     for (int v = 0; v < VN; ++v) sv[v] = predict_scale<T>(p, wp[v]);
                 }
-#pragma unroll 4
-                for (int j = 0; j < kd; ++j) {
-                    const Vec x4 = *reinterpret_cast<const Vec *>(static_cast<const T *>(p.cols[j]) + r);
-                    const T *xp = reinterpret_cast<const T *>(&x4);
-                    const double b = __ldg(beta + j);
+                auto load_batch = [&](Vec (&xv)[U], int j0) {
 #pragma unroll
-                    for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(static_cast<T>(xp[v] * sv[v])), b, acc[v]);
+                    for (int u = 0; u < U; ++u)
+                        if (j0 + u < kd) xv[u] = *reinterpret_cast<const Vec *>(static_cast<const T *>(p.cols[j0 + u]) + r);
+                };
+                auto use_batch = [&](const Vec (&xv)[U], int j0) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (j0 + u < kd) {
+                            const T *xp = reinterpret_cast<const T *>(&xv[u]);
+                            const double b = __ldg(beta + j0 + u);
+#pragma unroll
+                            for (int v = 0; v < VN; ++v) acc[v] = fma(static_cast<double>(static_cast<T>(xp[v] * sv[v])), b, acc[v]);
+                        }
+                    }
+                };
+                for (int j0 = 0; j0 < kd; j0 += U) {
+                    Vec xv[U];
+                    load_batch(xv, j0);
+                    use_batch(xv, j0);
                 }
                 if (p.intercept) {
                     const double b = __ldg(beta + kd);
