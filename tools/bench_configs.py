@@ -72,7 +72,7 @@ def run_config(cfg: str, steps: int = 10, warmup: int = 3, with_cpu: bool = True
     eng = pls.Engine(0, torch.cuda.current_stream(dev).cuda_stream or 1)
     OL = oracle_lib()
     peak, peak_src = _peak()
-    threads = os.cpu_count() or 1
+    threads = os.cpu_count() or 1          # passed explicitly to the OpenMP legs: `cores` is what actually ran, whatever OMP_NUM_THREADS says
     warmup = max(warmup, 3)
 
     # ---- per config: device batch, call, algorithmic bytes, units, checker, CPU baseline -----------------------------
@@ -213,10 +213,10 @@ def run_config(cfg: str, steps: int = 10, warmup: int = 3, with_cpu: bool = True
             o3 = np.empty(Gs * per)
             w64 = np.ascontiguousarray(wh, dtype=np.float64)
             offs3 = np.arange(Gs + 1, dtype=np.int64) * per
-            OL.orc_grouped_least_squares_predictions(arr, k, w64.ctypes.data, offs3.ctypes.data, Gs, 2, 1e-3, 0.5, 1000, 1e-5, 0, 0, o3.ctypes.data)
+            OL.orc_grouped_least_squares_predictions(arr, k, w64.ctypes.data, offs3.ctypes.data, Gs, 2, 1e-3, 0.5, 1000, 1e-5, 0, threads, o3.ctypes.data)
             t0, reps = time.perf_counter(), 0
             while time.perf_counter() - t0 < 10.0:
-                OL.orc_grouped_least_squares_predictions(arr, k, w64.ctypes.data, offs3.ctypes.data, Gs, 2, 1e-3, 0.5, 1000, 1e-5, 0, 0, o3.ctypes.data)
+                OL.orc_grouped_least_squares_predictions(arr, k, w64.ctypes.data, offs3.ctypes.data, Gs, 2, 1e-3, 0.5, 1000, 1e-5, 0, threads, o3.ctypes.data)
                 reps += 1
             t = (time.perf_counter() - t0) / reps
             cpu = {"value": Gs / t, "unit": UNIT[cfg], "cores": threads, "kind": "port",
@@ -241,7 +241,7 @@ def run_config(cfg: str, steps: int = 10, warmup: int = 3, with_cpu: bool = True
             o5 = np.empty((Gs, k))
             offs5 = np.arange(Gs + 1, dtype=np.int64) * per
             t0 = time.perf_counter()
-            OL.orc_grouped_least_squares_coefficients(arr, k, offs5.ctypes.data, Gs, 2, 1e-4, 1.0, 1000, 1e-5, 0, 0, o5.ctypes.data)
+            OL.orc_grouped_least_squares_coefficients(arr, k, offs5.ctypes.data, Gs, 2, 1e-4, 1.0, 1000, 1e-5, 0, threads, o5.ctypes.data)
             t = time.perf_counter() - t0
             cpu = {"value": Gs / t, "unit": UNIT[cfg], "cores": threads, "kind": "port",
                    "sample": f"first {Gs} groups (row-major copy + residual-form CD on 10000 x 64), OpenMP over groups, {t:.1f} s"}
@@ -249,10 +249,10 @@ def run_config(cfg: str, steps: int = 10, warmup: int = 3, with_cpu: bool = True
         if e2e:
             cpu["gpu_over_cpu_e2e"] = e2e["value"] / cpu["value"]
 
-    dominant = {"C1": "gram_cta_kernel + predict_kernel (latency-bound: 40 KB)", "C3": "gram_multi_kernel<float,2> + cd_solve_kernel + predict_kernel (three passes)",
+    dominant = {"C1": "gram_cta_kernel + predict_kernel (latency-bound: 40 KB)", "C3": "gram_multi_kernel<float,2> + cd_thread_kernel<16> + predict_kernel (three passes)",
                 "C4": "chunk_totals_kernel + rolling_nbr_kernel<double,6> (window-length chunks, neighbour-shared lag rows)",
                 "C4rls": "chunk_totals_kernel (information-form summaries) + rls_scan + rls_fast_main_kernel<double,6>",
-                "C5": "gram_wide_kernel<double> (DMMA, 72 per 8 rows) + cd_solve_kernel"}[cfg]
+                "C5": "gram_wide_kernel<double> (DMMA, 72 per 8 rows) + cd_solve_kernel<32,2>"}[cfg]
     line = {
         "metric": f"{UNIT[cfg].split('/')[0]} per second, {WORKLOAD[cfg]}", "value": value, "unit": UNIT[cfg], "n_gpus": 1, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
