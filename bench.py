@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host->device->host leg (default min(steps, 10))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-every", type=int, default=4,
+                    help="event-time the Gram kernel on every n-th step of the timed region; the event pair costs ~5 us of a 0.12 ms step")
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
@@ -320,6 +322,8 @@ def main():
             peer.step_complete()
         e0.record()
         for i in range(a.steps):
+            if a.profile_every > 1:
+                eng.set_profiling(i % a.profile_every == 0)
             full_step(i)
         drain()                              # every step's gather has completed inside the timed region
         e1.record()
@@ -496,7 +500,8 @@ def main():
         traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "gram_cta_kernel<double,1> (TMA bulk-copy pipeline + DMMA Gram + fused warp Cholesky solve)",
-                "kernel_ms_avg": k_avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": int(len(kern_ms)), "timed_every_nth_step": int(max(1, a.profile_every)),
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": k_avg_ms * a.steps / ms if ms > 0 else None}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ---------------
