@@ -317,7 +317,8 @@ B200OLS_API int b200ols_predict(b200ols_ctx *ctx, int64_t n_rows, int32_t n_coef
  * from (X^T X + alpha I)^-1 by Cholesky (failure -> NaN, as the reference) with df = n - p (alpha = 0) or
  * n - trace(inverse).  kwargs->alpha must not be None (the reference unwraps it).  A group with df <= 0 fails the call
  * with the reference's assertion message.  Arrays live in the frame's memspace; no nulls (NaN stays NaN).  The
- * `feature_names` list of the reference's struct is the caller's input names (host side). */
+ * `feature_names` list of the reference's struct is the caller's input names (host side).  Up to 4096 coefficients
+ * (above 64 through the general path, as the other static modes). */
 typedef struct b200ols_statistics_output {
     double *r2, *mae, *mse;                                           /* [n_groups] */
     double *coefficients, *standard_errors, *t_values, *p_values;     /* [n_groups * n_coef] row-major */

@@ -50,7 +50,7 @@ struct BigParams {
     double *W;                      // [(F+1)][n_rows]
     uint8_t *mask;                  // [n_rows] 1 = row enters the fit
     double *rec;                    // [G][F*F + F + 1]
-    double *work;                   // [G][F*F] factorisation scratch (Cholesky works on a copy: LU fallback needs G)
+    double *work;                   // [G][F*F] factorisation scratch (Cholesky route: always; LU route: when the record must survive) or nullptr
     double *beta;                   // [G][F]
     int32_t *flags;                 // [G]
     int route;                      // ROUTE_*
@@ -398,27 +398,33 @@ __global__ void __launch_bounds__(BIG_SOLVE_THREADS) big_solve_kernel(const BigP
         if (tid == 0) p.flags[g] = 0;
         return;
     }
-    for (int i = tid; i < F; i += BIG_SOLVE_THREADS) {
-        G[static_cast<size_t>(i) * F + i] += p.alpha;
-        z[i] = c[i];
-    }
-    __syncthreads();
+    // the factorisations run on a copy when scratch is provided (always for the Cholesky route, whose LU fallback needs
+    // the matrix again; for the LU route when mode = "statistics" still needs the record afterwards), else in place
+    double *A = p.work ? p.work + static_cast<size_t>(g) * F * F : G;
+    auto load_regularised = [&]() {
+        if (A != G)
+            for (size_t e = tid; e < static_cast<size_t>(F) * F; e += BIG_SOLVE_THREADS) A[e] = G[e];
+        __syncthreads();
+        for (int i = tid; i < F; i += BIG_SOLVE_THREADS) A[static_cast<size_t>(i) * F + i] += p.alpha;
+        __syncthreads();
+    };
+    for (int i = tid; i < F; i += BIG_SOLVE_THREADS) z[i] = c[i];
+    load_regularised();
     int fl = 0;
     bool done = false;
     if (p.route == ROUTE_CHOL) {
-        double *L = p.work + static_cast<size_t>(g) * F * F;
-        for (size_t e = tid; e < static_cast<size_t>(F) * F; e += BIG_SOLVE_THREADS) L[e] = G[e];
         double mn, mx;
-        if (big_chol(L, F, col, &mn, &mx)) {
-            big_chol_solve(L, F, z);
+        if (big_chol(A, F, col, &mn, &mx)) {
+            big_chol_solve(A, F, z);
             if (mx > p.illcond_ratio * mn) fl |= FLAG_ILLCOND;
             done = true;
         } else {
             fl |= FLAG_LU_FALLBACK;
             __syncthreads();
+            load_regularised();  // the failed factorisation overwrote part of the copy
         }
     }
-    if (!done) big_lu_solve(G, F, z, col, red, redi);
+    if (!done) big_lu_solve(A, F, z, col, red, redi);
     if (wide) fl |= FLAG_WIDE;
     for (int i = tid; i < F; i += BIG_SOLVE_THREADS) beta[i] = z[i];
     if (tid == 0) p.flags[g] = fl;

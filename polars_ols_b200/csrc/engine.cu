@@ -31,6 +31,7 @@
 #include "small_solve.cuh"
 #include "svd_solve.cuh"
 #include "big.cuh"
+#include "big_stats.cuh"
 #include "batch_solve.cuh"
 #include "cd_solve.cuh"
 #include "cd_thread.h"
@@ -948,8 +949,11 @@ static int upload_small(b200ols_ctx *c, const void *src, size_t bytes, void **de
     return 0;
 }
 
+static int run_statistics_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, const BigParams &bp,
+                              const b200ols_statistics_output *so);
+
 static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, const StaticRoute &rt, int mode,
-                          b200ols_output *out, bool peer_mode) {
+                          b200ols_output *out, bool peer_mode, const b200ols_statistics_output *stats = nullptr) {
     const int kd = f->n_features, F = kd + (f->add_intercept ? 1 : 0), has_w = f->sample_weights ? 1 : 0;
     const int ncol = kd + 1 + has_w;
     const int64_t G = f->n_groups, N = f->n_rows;
@@ -975,9 +979,10 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
         bytes += static_cast<size_t>(ncol) * (round_up(static_cast<size_t>(N) * esz, 256) + round_up(bm_bytes, 256) + 512) +
                  round_up(static_cast<size_t>(N) * 8, 256) + static_cast<size_t>(N) * 9 + 8192;
     bytes += static_cast<size_t>(F + 1) * N * 8 + static_cast<size_t>(N) + static_cast<size_t>(G) * P * 8 + 4096;   // W, mask, records
-    if (rt.route == ROUTE_CHOL) bytes += static_cast<size_t>(G) * F * F * 8 + 256;                                    // Cholesky copy
+    if (rt.route == ROUTE_CHOL || (stats && rt.route == ROUTE_LU)) bytes += static_cast<size_t>(G) * F * F * 8 + 256;      // factorisation copy
     bytes += static_cast<size_t>(G) * F * (8 + 4 + 8 + 2 * 4 + 2 * 8) + static_cast<size_t>(G) * 4 + 8192;           // beta, perm, z, cd scratch, flags
     if (any_svd) bytes += 2 * static_cast<size_t>(N) * F * 8 + static_cast<size_t>(G) * F * F * 8 + 4096;             // X^T, J, V
+    if (stats) bytes += static_cast<size_t>(G) * (2 * static_cast<size_t>(F) * F + 5 * static_cast<size_t>(F) + STATS_GS + 3) * 8 + 8192;  // factor, L^-1, metrics
     TRY(arena_reserve(c, bytes));
     c->arena_off = 0;
     c->arena_overflow = false;
@@ -1042,7 +1047,7 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
     bp.W = arena_alloc<double>(c, static_cast<size_t>(F + 1) * N + 8);
     bp.mask = arena_alloc<uint8_t>(c, static_cast<size_t>(N) + 8);
     bp.rec = arena_alloc<double>(c, static_cast<size_t>(G) * P);
-    bp.work = rt.route == ROUTE_CHOL ? arena_alloc<double>(c, static_cast<size_t>(G) * F * F) : nullptr;
+    bp.work = (rt.route == ROUTE_CHOL || (stats && rt.route == ROUTE_LU)) ? arena_alloc<double>(c, static_cast<size_t>(G) * F * F) : nullptr;
     bp.beta = arena_alloc<double>(c, static_cast<size_t>(G) * F);
     bp.flags = arena_alloc<int32_t>(c, static_cast<size_t>(G));
     bp.route = rt.svd_all ? ROUTE_FLAGS_ONLY : rt.route;
@@ -1148,6 +1153,7 @@ static int run_static_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_
         }
     }
     CU(cudaGetLastError());
+    if (stats) return run_statistics_big(c, f, kw, bp, stats);
 
     if (peer_mode) {
         PeerScatterParams ps;
@@ -1230,9 +1236,7 @@ static int run_static_impl(b200ols_ctx *c, const b200ols_frame *f, const b200ols
     TRY(free_retired(c));
 
     const int F = f->n_features + (f->add_intercept ? 1 : 0);
-    if (stats && F > 64)
-        return fail(B200OLS_ERR_UNSUPPORTED, "mode=statistics with more than 64 coefficients (%d) is not implemented on the device", F);
-    if (F > 64) return run_static_big(c, f, kw, rt, mode, out, peer_mode);
+    if (F > 64) return run_static_big(c, f, kw, rt, mode, out, peer_mode, stats);
     const int64_t G = f->n_groups, N = f->n_rows;
     const size_t P = static_cast<size_t>(F) * F + F + 1;
     // arena budget
@@ -1586,6 +1590,80 @@ static int device_group_offsets(b200ols_ctx *c, const Staged &st, const Plan &pl
     int64_t *d = arena_alloc<int64_t>(c, static_cast<size_t>(st.n_groups) + 1);
     CU(cudaMemcpyAsync(d, h, ob, cudaMemcpyHostToDevice, c->stream));
     *out = d;
+    return 0;
+}
+
+// mode = "statistics" behind the general path (more than 64 coefficients): big_stats.cuh on what run_static_big left
+static int run_statistics_big(b200ols_ctx *c, const b200ols_frame *f, const b200ols_ols_kwargs *kw, const BigParams &bp,
+                              const b200ols_statistics_output *so) {
+    if (!so->r2 || !so->mae || !so->mse || !so->coefficients || !so->standard_errors || !so->t_values || !so->p_values)
+        return fail(B200OLS_ERR_INVALID, "statistics output: NULL array");
+    if (kw->alpha != kw->alpha) return fail(B200OLS_ERR_INVALID, "mode=statistics requires alpha (called `Option::unwrap()` on a `None` value)");
+    const int F = bp.F;
+    const int64_t G = bp.n_groups;
+    const size_t GF = static_cast<size_t>(G) * F;
+    BigStatsParams bs;
+    std::memset(&bs, 0, sizeof(bs));
+    bs.F = F;
+    bs.n_groups = G;
+    bs.n_rows = bp.n_rows;
+    bs.group_off = bp.group_off;
+    bs.W = bp.W;
+    bs.mask = bp.mask;
+    bs.rec = bp.rec;
+    bs.beta = bp.beta;
+    bs.alpha = kw->alpha;
+    bs.A = arena_alloc<double>(c, GF * F);
+    bs.M = arena_alloc<double>(c, GF * F);
+    bs.beta2 = arena_alloc<double>(c, GF);
+    bs.inv_diag = arena_alloc<double>(c, GF);
+    bs.gstat = arena_alloc<double>(c, static_cast<size_t>(G) * STATS_GS);
+    StatsParams sp;  // stats_final_kernel's view of the same arrays
+    std::memset(&sp, 0, sizeof(sp));
+    sp.F = F;
+    sp.n_groups = G;
+    sp.alpha = kw->alpha;
+    sp.beta2 = bs.beta2;
+    sp.inv_diag = bs.inv_diag;
+    sp.gstat = bs.gstat;
+    const bool host = f->memspace == B200OLS_HOST;
+    double *blk = host ? arena_alloc<double>(c, 3 * static_cast<size_t>(G) + 3 * GF) : nullptr;
+    sp.r2 = host ? blk : so->r2;
+    sp.mae = host ? blk + G : so->mae;
+    sp.mse = host ? blk + 2 * G : so->mse;
+    sp.se = host ? blk + 3 * G : so->standard_errors;
+    sp.tv = host ? blk + 3 * G + GF : so->t_values;
+    sp.pv = host ? blk + 3 * G + 2 * GF : so->p_values;
+    sp.bad_df = arena_alloc<int32_t>(c, 4);
+    ARENA_GUARD(c);
+    CU(cudaMemsetAsync(sp.bad_df, 0, sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(bs.gstat, 0, sizeof(double) * G * STATS_GS, c->stream));
+    if (G > 0) {
+        const size_t smem = big_stats_factor_smem(F);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(big_stats_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        big_stats_factor_kernel<<<static_cast<unsigned>(G), BIG_SOLVE_THREADS, smem, c->stream>>>(bs);
+        big_stats_invdiag_kernel<<<dim3(static_cast<unsigned>((F + 255) / 256), static_cast<unsigned>(std::min<int64_t>(G, 65535))), 256, 0, c->stream>>>(bs);
+        const unsigned rb = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(G, static_cast<int64_t>(c->sm_count) * 8)));
+        big_stats_resid_kernel<<<rb, 256, 0, c->stream>>>(bs);
+        stats_final_kernel<<<static_cast<unsigned>((GF + 127) / 128), 128, 0, c->stream>>>(sp);
+        c->launches += 4;
+        CU(cudaGetLastError());
+    }
+    int32_t bad = 0;
+    if (host) {
+        CU(cudaMemcpyAsync(so->r2, sp.r2, sizeof(double) * G, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->mae, sp.mae, sizeof(double) * G, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->mse, sp.mse, sizeof(double) * G, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->standard_errors, sp.se, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->t_values, sp.tv, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->p_values, sp.pv, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(so->coefficients, bp.beta, sizeof(double) * GF, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CU(cudaMemcpyAsync(so->coefficients, bp.beta, sizeof(double) * GF, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(&bad, sp.bad_df, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (bad > 0) return fail(B200OLS_ERR_INVALID, "Degrees of freedom <= 0. Cannot compute standard errors. (%d group(s))", bad);
     return 0;
 }
 

@@ -653,6 +653,52 @@ def test_statistics_over_groups(model, kw, null_policy):                    # te
     assert r.to_struct()["feature_names"] == names + ["const"]
 
 
+@pytest.mark.parametrize("k,model,kw,null_policy", [(100, "ols", {}, "ignore"), (100, "ridge", {"alpha": 0.7}, "drop"),
+                                                    (150, "lasso", {"alpha": 1e-3}, "ignore"), (300, "ridge", {"alpha": 5.0}, "zero"),
+                                                    (80, "ridge", {"alpha": 0.3, "solve_method": "lu"}, "drop_y_zero_x")])
+def test_statistics_above_64_coefficients(k, model, kw, null_policy):       # src/statistics.rs:76-156 has no bound on k
+    """mode="statistics" behind the general path (big_stats.cuh): Cholesky of X^T X + lambda I in global memory, the
+    diagonal / trace of the inverse from the columns of L^-1, residual metrics over the materialised fit rows."""
+    n = 5 * k + 200
+    d = _make_data(n, k, n_groups=3, scale=1.0, seed=k)
+    rng = np.random.default_rng(4)
+    if null_policy != "ignore":                      # nulls in three columns only: with 10 % per column over 100+ columns no row would survive "drop"
+        for c_ in ("y", "x1", "x7"):
+            d[c_] = (d[c_], rng.random(n) >= 0.1)
+    d["w"] = rng.uniform(0.2, 3.0, size=n)
+    names = _xs(d)
+    e = getattr(col("y").least_squares, model)(*names, mode="statistics", add_intercept=True, sample_weights="w",
+                                                null_policy=null_policy, **kw).over("group")
+    r = Frame(d).select(e)["statistics"]
+    okw = dict(kw)
+    okw.setdefault("alpha", 0.0)
+    if model == "ridge":
+        okw["l1_ratio"] = 0.0
+    if model == "lasso":
+        okw["l1_ratio"] = 1.0
+    refs = _stats_oracle_by_group(d, names, "group", sample_weights=d["w"], add_intercept=True,
+                                  kwargs=S.OLSKwargs(null_policy=null_policy, **okw))
+    _check_stats(r, refs)
+    assert r.to_struct()["feature_names"] == names + ["const"]
+
+
+def test_statistics_above_64_coefficients_wide_group():
+    """more coefficients than rows: with lambda > 0 the inverse exists (df = n - trace(inv)); with lambda = 0 the Cholesky
+    factorisation of the singular X^T X fails and the feature metrics are NaN (src/statistics.rs:101-111)"""
+    rng = np.random.default_rng(9)
+    n, k = 60, 90
+    d = {f"x{i + 1}": rng.normal(size=n) for i in range(k)}
+    d["y"] = rng.normal(size=n)
+    names = [f"x{i + 1}" for i in range(k)]
+    r = Frame(d).select(col("y").least_squares.ridge(*names, alpha=2.0, mode="statistics"))["statistics"]
+    _check_stats(r, [S.least_squares_statistics(d["y"], *[d[c] for c in names], kwargs=S.OLSKwargs(alpha=2.0, l1_ratio=0.0))])
+    r = Frame(d).select(col("y").least_squares.ols(*names, mode="statistics"))["statistics"].to_struct()
+    ref = S.least_squares_statistics(d["y"], *[d[c] for c in names], kwargs=S.OLSKwargs(alpha=0.0))
+    for key in ("standard_errors", "t_values", "p_values"):
+        assert np.isnan(np.asarray(ref[key])).all() and np.isnan(np.asarray(r[key][0])).all(), key
+    assert np.allclose(r["coefficients"][0], ref["coefficients"], rtol=1e-6, atol=1e-9)
+
+
 def test_statistics_f32_device_frame_and_long_group():
     import torch
     rng = np.random.default_rng(3)
