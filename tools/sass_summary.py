@@ -35,4 +35,4 @@ for (k, c), name in zip(counts.items(), demangle):
     print("  " + " ".join(f"{c[x]:>8}" for x in KEYS) + f" {c['_total']:>8}  {name}")
     tot.update(c)
 print("# " + " ".join(f"{tot[x]:>8}" for x in KEYS) + f" {tot['_total']:>8}  ALL KERNELS")
-print("# tcgen05 (UTC*MMA / LDTM / STTM) and TMA tensor loads (UTMALDG): none — see DESIGN.md 4.1 / 4.10 for why (no f64 kind; block-diagonal waste for k = 16 f32)")
+print("# tcgen05 (UTC*MMA / LDTM / STTM) and TMA tensor loads (UTMALDG): none in the library — see DESIGN.md 4.1 / 4.11 (no f64 kind; the tf32 probe tools/tf32_gram_probe.cu, which does contain UTCHMMA / LDTM, measured why not for k = 16 f32)")
