@@ -72,7 +72,7 @@ enum {
 enum {
     B200OLS_OK = 0,
     B200OLS_ERR_INVALID = -1,     /* bad argument (the reference's assert!/expect panics) */
-    B200OLS_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented on the device (static k > 4096; rls / rolling k > 16) */
+    B200OLS_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented on the device (static k > 4096; rls / rolling k > 64) */
     B200OLS_ERR_CUDA = -3,        /* CUDA runtime failure (message has the cudaError string) */
     B200OLS_ERR_NO_DEVICE = -4    /* no CUDA device: there is NO CPU fallback */
 };
